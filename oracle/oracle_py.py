@@ -1,0 +1,206 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so) — TEST INFRASTRUCTURE ONLY.
+
+Importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs; never from ohao_engine_b200/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class Settings(C.Structure):   # ohb_settings (include/ohao_b200.h)
+    _fields_ = [("profile", C.c_uint32), ("max_bounces", C.c_uint32), ("flags", C.c_uint32), ("firefly_clamp_lum", C.c_float),
+                ("sampler_type", C.c_uint32), ("anisotropy_strength", C.c_float), ("anisotropy_rotation", C.c_float),
+                ("subsurface_strength", C.c_float), ("samples_per_frame", C.c_uint32), ("_pad", C.c_uint32 * 3)]
+
+
+class Counters(C.Structure):   # ohb_counters
+    _fields_ = [("samples", C.c_uint64), ("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("closest_hits", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("_reserved", C.c_uint64 * 3)]
+
+
+RAY_DTYPE = np.dtype([("origin", "<f4", (3,)), ("tmin", "<f4"), ("dir", "<f4", (3,)), ("tmax", "<f4")])
+HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4")])
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("positions", C.c_void_p), ("stride_bytes", C.c_uint64), ("nverts", C.c_uint32),
+                ("indices", C.c_void_p), ("ntris", C.c_uint32),
+                ("normals", C.c_void_p), ("uvs", C.c_void_p), ("mat_ids", C.c_void_p),
+                ("instances", C.c_void_p), ("ninstances", C.c_uint32),
+                ("mat_colors", C.c_void_p), ("nmaterials", C.c_uint32),
+                ("textures", C.c_void_p), ("tex_w", C.c_uint32), ("tex_h", C.c_uint32), ("tex_layers", C.c_uint32),
+                ("light_ssbo", C.c_void_p), ("light_bytes", C.c_uint64),
+                ("env", C.c_void_p), ("env_w", C.c_uint32), ("env_h", C.c_uint32)]
+
+
+class RenderArgs(C.Structure):
+    _fields_ = [("view", C.c_float * 16), ("proj", C.c_float * 16), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("first_sample_index", C.c_uint32), ("history_count", C.c_uint32), ("nsamples", C.c_uint32),
+                ("tile_x", C.c_uint32), ("tile_y", C.c_uint32), ("tile_w", C.c_uint32), ("tile_h", C.c_uint32),
+                ("settings", Settings),
+                ("accum", C.c_void_p), ("ldr", C.c_void_p), ("albedo", C.c_void_p), ("normal", C.c_void_p), ("sample_dump", C.c_void_p),
+                ("nthreads", C.c_int32), ("counters", Counters)]
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/liboracle.so (and oracle/_ref when /root/reference exists)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h", ".inc"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    if os.path.isdir("/root/reference/ohao"):
+        subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.orc_scene_create.restype = C.c_void_p
+        _LIB.orc_scene_create.argtypes = [C.POINTER(SceneDesc)]
+        _LIB.orc_scene_destroy.argtypes = [C.c_void_p]
+        _LIB.orc_render_offline.argtypes = [C.c_void_p, C.POINTER(RenderArgs)]
+        _LIB.orc_sampler_1d.restype = C.c_float
+        _LIB.orc_sampler_1d.argtypes = [C.c_uint32] * 5
+        _LIB.orc_sobol_raw.restype = C.c_float
+        _LIB.orc_sobol_raw.argtypes = [C.c_uint32, C.c_uint32]
+        _LIB.orc_owen.restype = C.c_uint32
+        _LIB.orc_owen.argtypes = [C.c_uint32, C.c_uint32]
+        _LIB.orc_sobol_dirs.restype = C.POINTER(C.c_uint32)
+        _LIB.orc_trace_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_int]
+        _LIB.orc_occluded_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        _LIB.orc_env_cdf.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+        _LIB.orc_scene_env_cdf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+        _LIB.orc_env_sample_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        _LIB.orc_set_ray_recorder.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        _LIB.orc_ray_recorder_count.restype = C.c_uint32
+        _LIB.orc_scene_set_materials.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        _LIB.orc_scene_set_lights.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        _LIB.orc_tonemap.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    return _LIB
+
+
+def ref_lib():
+    """The reference's own TUs (oracle/_ref/libohao_ref.so) or None when not built."""
+    p = os.path.join(_HERE, "_ref", "libohao_ref.so")
+    if not os.path.exists(p):
+        return None
+    l = C.CDLL(p)
+    l.ref_sobol_sample1d.restype = C.c_float
+    l.ref_sobol_sample1d.argtypes = [C.c_uint32, C.c_uint32]
+    l.ref_owen.restype = C.c_uint32
+    l.ref_owen.argtypes = [C.c_uint32, C.c_uint32]
+    l.ref_sobol_dirs.restype = C.POINTER(C.c_uint32)
+    l.ref_env_cdf.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    return l
+
+
+def offline_settings(max_bounces=4, flags=1, firefly=0.0, sampler=1) -> Settings:
+    """kOfflineRTSettings (rt_settings.hpp:49-61): 4 bounces, Sobol, AOVs on, no clamp."""
+    s = Settings()
+    s.profile = 0; s.max_bounces = max_bounces; s.flags = flags; s.firefly_clamp_lum = firefly
+    s.sampler_type = sampler; s.samples_per_frame = 1
+    return s
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class OracleScene:
+    def __init__(self, ps):
+        self.ps = ps
+        d = SceneDesc()
+        self._keep = [np.ascontiguousarray(x) for x in (ps.positions, ps.indices, ps.normals, ps.uvs, ps.mat_ids, ps.instances,
+                                                        ps.mat_colors, ps.textures, ps.light_ssbo)]
+        k = self._keep
+        d.positions = _p(k[0]); d.stride_bytes = k[0].strides[0]; d.nverts = ps.nverts
+        d.indices = _p(k[1]); d.ntris = ps.ntris
+        d.normals = _p(k[2]); d.uvs = _p(k[3]); d.mat_ids = _p(k[4])
+        d.instances = _p(k[5]); d.ninstances = len(k[5])
+        d.mat_colors = _p(k[6]); d.nmaterials = ps.nmaterials
+        d.textures = _p(k[7]); d.tex_layers, d.tex_h, d.tex_w = k[7].shape[0], k[7].shape[1], k[7].shape[2]
+        d.light_ssbo = _p(k[8]); d.light_bytes = k[8].nbytes
+        if ps.env is not None:
+            self._env = np.ascontiguousarray(ps.env, np.float32)
+            d.env = _p(self._env); d.env_h, d.env_w = self._env.shape[0], self._env.shape[1]
+        self.h = lib().orc_scene_create(C.byref(d))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_scene_destroy(self.h); self.h = None
+
+    def set_materials(self, mat_colors):
+        mc = np.ascontiguousarray(mat_colors, np.float32)
+        lib().orc_scene_set_materials(self.h, _p(mc), mc.shape[0] // 3)
+
+    def set_lights(self, ssbo):
+        b = np.ascontiguousarray(ssbo, np.uint8)
+        lib().orc_scene_set_lights(self.h, _p(b), b.nbytes)
+
+    def render_offline(self, view, proj, width, height, nsamples, first_sample=0, history=0, accum=None, settings=None,
+                       tile=None, nthreads=None, dump=False, want_ldr=True, want_aov=False):
+        a = RenderArgs()
+        a.view[:] = [float(x) for x in view]; a.proj[:] = [float(x) for x in proj]
+        a.width, a.height = width, height
+        a.first_sample_index, a.history_count, a.nsamples = first_sample, history, nsamples
+        if tile: a.tile_x, a.tile_y, a.tile_w, a.tile_h = tile
+        a.settings = settings or offline_settings()
+        if accum is None: accum = np.zeros((height, width, 4), np.float32)
+        ldr = np.zeros((height, width, 4), np.uint8) if want_ldr else None
+        alb = np.zeros((height, width, 4), np.float32) if want_aov else None
+        nrm = np.zeros((height, width, 4), np.float32) if want_aov else None
+        sd = np.zeros((nsamples, height, width, 4), np.float32) if dump else None
+        a.accum, a.ldr, a.albedo, a.normal, a.sample_dump = _p(accum), _p(ldr), _p(alb), _p(nrm), _p(sd)
+        a.nthreads = nthreads or (os.cpu_count() or 1)
+        lib().orc_render_offline(self.h, C.byref(a))
+        c = a.counters
+        return dict(accum=accum, ldr=ldr, albedo=alb, normal=nrm, samples=sd,
+                    counters=dict(samples=c.samples, closest_rays=c.closest_rays, shadow_rays=c.shadow_rays, closest_hits=c.closest_hits))
+
+    def trace(self, rays, brute=False, nthreads=None):
+        rays = np.ascontiguousarray(rays, RAY_DTYPE); hits = np.zeros(len(rays), HIT_DTYPE)
+        lib().orc_trace_batch(self.h, _p(rays), len(rays), _p(hits), int(brute), nthreads or (os.cpu_count() or 1))
+        return hits
+
+    def occluded(self, rays):
+        rays = np.ascontiguousarray(rays, RAY_DTYPE); occ = np.zeros(len(rays), np.uint8)
+        lib().orc_occluded_batch(self.h, _p(rays), len(rays), _p(occ))
+        return occ
+
+    def env_cdf(self):
+        h, w = self.ps.env.shape[:2]
+        marg = np.zeros(h, np.float32); cond = np.zeros((h, w), np.float32); I = C.c_float()
+        lib().orc_scene_env_cdf(self.h, _p(marg), _p(cond), C.byref(I))
+        return marg, cond, I.value
+
+    def env_sample(self, u12):
+        u = np.ascontiguousarray(u12, np.float32); n = len(u)
+        dp = np.zeros((n, 4), np.float32); pd = np.zeros(n, np.float32)
+        lib().orc_env_sample_batch(self.h, _p(u), n, _p(dp), _p(pd))
+        return dp, pd
+
+    def record_rays(self, view, proj, width, height, nsamples, tile, cap=1 << 20, settings=None, first_sample=0):
+        rays = np.zeros(cap, RAY_DTYPE); hits = np.zeros(cap, HIT_DTYPE); kinds = np.zeros(cap, np.uint8)
+        lib().orc_set_ray_recorder(_p(rays), _p(hits), _p(kinds), cap)
+        try:
+            self.render_offline(view, proj, width, height, nsamples, first_sample=first_sample, tile=tile, nthreads=1, settings=settings, want_ldr=False)
+            n = lib().orc_ray_recorder_count()
+        finally:
+            lib().orc_set_ray_recorder(None, None, None, 0)
+        return rays[:n].copy(), hits[:n].copy(), kinds[:n].copy()
+
+
+def env_cdf(rgba):
+    rgba = np.ascontiguousarray(rgba, np.float32); h, w = rgba.shape[:2]
+    marg = np.zeros(h, np.float32); cond = np.zeros((h, w), np.float32); I = C.c_float()
+    lib().orc_env_cdf(_p(rgba), w, h, _p(marg), _p(cond), C.byref(I))
+    return marg, cond, I.value
