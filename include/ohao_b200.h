@@ -181,6 +181,9 @@ void ohb_reset_counters(ohb_ctx*);
  * since the last ohb_reset_counters, for the roofline line of bench.py. */
 int ohb_get_timing(ohb_ctx*, float* trace_ms, float* shade_ms, float* total_ms);
 int ohb_enable_timing(ohb_ctx*, int enable);
+/* Per-category device time and launch count: [0] closest-hit traversal, [1] shading,
+ * [2] any-hit traversal, [3] film. */
+int ohb_get_timing_detail(ohb_ctx*, float ms[4], uint64_t launches[4]);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,577 @@
+// ohb_api.cu — the C ABI of include/ohao_b200.h: context, device memory, scene upload,
+// acceleration-structure build, the render loop and the readbacks.
+//
+// Host-side mirror of PathTracer (ohao/render/rt/path_tracer.{hpp,cpp}, path_tracer_render.cpp):
+// the context owns its output/accumulation/AOV images and *copies* the scene arrays it is handed
+// (the Vulkan profile borrowed VkBuffers; a C ABI cannot borrow host memory safely), keeps
+// m_sampleIndex / m_historyFrameCount / m_renderSeed with the reference's reset rules
+// (path_tracer.cpp:189-211) and turns one ohb_render() into `nsamples` reference frames.
+// There is no CPU path: every entry point needs a live CUDA context.
+#include "ohb_device.h"
+#include <string>
+#include <vector>
+#include <cstring>
+#include <cstdio>
+#include <cstdlib>
+#include <algorithm>
+
+using namespace ohb;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr; size_t bytes = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= bytes && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        if (n == 0) n = 16;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct M4h { float m[16]; };
+static M4h inverse4(const float* m) {   // cofactor inverse, fp32 (what glm::inverse computes)
+    float inv[16];
+    inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+    inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+    inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+    inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+    inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+    inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+    inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+    inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+    inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+    inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+    inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+    inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+    inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+    inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+    inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+    inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+    float det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+    float id = 1.0f / det;
+    M4h o; for (int i = 0; i < 16; i++) o.m[i] = inv[i] * id;
+    return o;
+}
+
+static std::string g_createError;
+
+}  // namespace
+
+struct ohb_ctx {
+    int device = 0; cudaStream_t stream = nullptr; int numSMs = 148;
+    uint32_t W = 0, H = 0; int profile = 0;
+    ohb_settings settings{};
+    uint32_t seed = 0, sampleIndex = 0, historyCount = 0; bool viewChanged = false;
+    uint32_t tileX = 0, tileY = 0, tileW = 0, tileH = 0;
+    int sumMode = 0;
+    std::string err;
+    uint64_t launches = 0;
+    // scene (host metadata)
+    uint32_t nverts = 0, ntris = 0, nmat = 0; uint64_t posStride = 0;
+    std::vector<ohb_instance> instances;
+    uint32_t lightCount = 0, envMapTexIdx = 0xFFFFFFFFu; float envIntensity = 1.0f;
+    uint32_t texW = 0, texH = 0, texLayers = 0, envW = 0, envH = 0; float envIntegral = 0.0f;
+    bool accelValid = false; int32_t rootRef = 0; uint32_t numActive = 0;
+    ohb_accel_stats stats{};
+    // scene (device)
+    DevBuf positions, indices, normals, uvs, matIds, triInst, instXform, instNormalMat, instInv, matColors, tex, lights, env, marg, cond, rowTotal, integral;
+    // accel (device)
+    DevBuf activeTris, wtri, primLo, primHi, boundsBits, keys, vals, keysTmp, valsTmp, sortTemp, left, right, parentInner, parentLeaf,
+           rangeFirst, rangeLast, nodeLo, nodeHi, visit, newIndex, emitCounter, sah, nodes, tris;
+    // paths (device)
+    DevBuf rayO, rayD, hit, thr, rad, pendA, pendB, meta, fh0, fh1, fh2, fh3, shO, shD, queueA, queueB, smallCounters, devCounters;
+    uint32_t pathCapacity = 0;
+    // film
+    DevBuf accum, ldr, albedoAOV, normalAOV, sampleDump;
+    float* dumpHost = nullptr; size_t dumpCapacity = 0;
+    // hooks
+    DevBuf hookRays, hookOut, hookAux;
+    TimingHooks timing; bool timingOn = false;
+    cudaEvent_t evA = nullptr, evB = nullptr;
+};
+
+#define OHB_FAIL(ctx, msg) do { (ctx)->err = (msg); return 1; } while (0)
+#define CU(ctx, call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(_e); return 1; } } while (0)
+
+static int ensureFilm(ohb_ctx* c) {
+    size_t n = size_t(c->W) * c->H;
+    CU(c, c->accum.reserve(n * 16)); CU(c, c->ldr.reserve(n * 4)); CU(c, c->albedoAOV.reserve(n * 16)); CU(c, c->normalAOV.reserve(n * 16));
+    return 0;
+}
+static int clearFilm(ohb_ctx* c) {
+    size_t n = size_t(c->W) * c->H;
+    CU(c, cudaMemsetAsync(c->accum.p, 0, n * 16, c->stream)); CU(c, cudaMemsetAsync(c->ldr.p, 0, n * 4, c->stream));
+    CU(c, cudaMemsetAsync(c->albedoAOV.p, 0, n * 16, c->stream)); CU(c, cudaMemsetAsync(c->normalAOV.p, 0, n * 16, c->stream));
+    return 0;
+}
+static void defaultSettings(ohb_ctx* c) {
+    ohb_settings s{};
+    if (c->profile == OHB_PROFILE_REALTIME) {   // kRealtimeRTSettings (rt_settings.hpp:37-48); sampler: Sobol (quirk Q3)
+        s.profile = OHB_PROFILE_REALTIME; s.max_bounces = 2; s.flags = OHB_FLAG_ENABLE_AOVS | OHB_FLAG_ENABLE_INTERNAL_DENOISE | OHB_FLAG_ENABLE_FIREFLY_CLAMP;
+        s.firefly_clamp_lum = 10.0f;
+    } else {                                    // kOfflineRTSettings (rt_settings.hpp:49-61)
+        s.profile = OHB_PROFILE_OFFLINE; s.max_bounces = 4; s.flags = OHB_FLAG_ENABLE_AOVS; s.firefly_clamp_lum = 0.0f;
+    }
+    s.sampler_type = OHB_SAMPLER_SOBOL; s.samples_per_frame = 1;
+    c->settings = s;
+}
+
+extern "C" {
+
+uint32_t ohb_abi_version(void) { return OHB_ABI_VERSION; }
+
+const char* ohb_last_error(const ohb_ctx* c) { return c ? c->err.c_str() : g_createError.c_str(); }
+
+ohb_ctx* ohb_create(int device_ordinal, uint32_t width, uint32_t height, int profile) {
+    g_createError.clear();
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { g_createError = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU path)"; return nullptr; }
+    if (device_ordinal < 0 || device_ordinal >= ndev) { g_createError = "device ordinal out of range"; return nullptr; }
+    if (width == 0 || height == 0 || width > 65535u || height > 65535u) { g_createError = "bad resolution"; return nullptr; }
+    if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess) { g_createError = cudaGetErrorString(e); return nullptr; }
+    ohb_ctx* c = new ohb_ctx();
+    c->device = device_ordinal; c->W = width; c->H = height; c->profile = profile;
+    c->tileW = width; c->tileH = height;
+    cudaDeviceProp prop; cudaGetDeviceProperties(&prop, device_ordinal); c->numSMs = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess || (e = uploadConstants()) != cudaSuccess) {
+        g_createError = cudaGetErrorString(e); delete c; return nullptr;
+    }
+    cudaEventCreate(&c->evA); cudaEventCreate(&c->evB);
+    defaultSettings(c);
+    if (ensureFilm(c) || clearFilm(c) || c->smallCounters.reserve(64 * 4) != cudaSuccess || c->devCounters.reserve(8 * 8) != cudaSuccess) {
+        g_createError = c->err.empty() ? "allocation failed" : c->err; ohb_destroy(c); return nullptr;
+    }
+    cudaMemsetAsync(c->smallCounters.p, 0, 64 * 4, c->stream); cudaMemsetAsync(c->devCounters.p, 0, 64, c->stream);
+    // dummy 1-float CDFs like the reference when no env is loaded (light_upload.cpp:505-535)
+    c->marg.reserve(4); c->cond.reserve(4); c->integral.reserve(4);
+    cudaStreamSynchronize(c->stream);
+    return c;
+}
+
+void ohb_destroy(ohb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    DevBuf* all[] = {&c->positions, &c->indices, &c->normals, &c->uvs, &c->matIds, &c->triInst, &c->instXform, &c->instNormalMat, &c->instInv, &c->matColors,
+                     &c->tex, &c->lights, &c->env, &c->marg, &c->cond, &c->rowTotal, &c->integral, &c->activeTris, &c->wtri, &c->primLo, &c->primHi, &c->boundsBits,
+                     &c->keys, &c->vals, &c->keysTmp, &c->valsTmp, &c->sortTemp, &c->left, &c->right, &c->parentInner, &c->parentLeaf, &c->rangeFirst, &c->rangeLast,
+                     &c->nodeLo, &c->nodeHi, &c->visit, &c->newIndex, &c->emitCounter, &c->sah, &c->nodes, &c->tris, &c->rayO, &c->rayD, &c->hit, &c->thr, &c->rad,
+                     &c->pendA, &c->pendB, &c->meta, &c->fh0, &c->fh1, &c->fh2, &c->fh3, &c->shO, &c->shD, &c->queueA, &c->queueB, &c->smallCounters, &c->devCounters,
+                     &c->accum, &c->ldr, &c->albedoAOV, &c->normalAOV, &c->sampleDump, &c->hookRays, &c->hookOut, &c->hookAux};
+    for (DevBuf* b : all) b->release();
+    if (c->evA) cudaEventDestroy(c->evA); if (c->evB) cudaEventDestroy(c->evB);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int ohb_resize(ohb_ctx* c, uint32_t width, uint32_t height) {
+    if (!c) return 1;
+    if (width == 0 || height == 0 || width > 65535u || height > 65535u) OHB_FAIL(c, "bad resolution");
+    cudaSetDevice(c->device);
+    c->W = width; c->H = height; c->tileX = c->tileY = 0; c->tileW = width; c->tileH = height;
+    if (ensureFilm(c) || clearFilm(c)) return 1;
+    ohb_reset_accumulation(c);
+    return 0;
+}
+
+int ohb_set_geometry(ohb_ctx* c, const void* positions, size_t stride_bytes, uint32_t nverts, const uint32_t* idx, uint32_t ntris,
+                     const float* normals, const float* uvs, const uint32_t* mat_ids) {
+    if (!c) return 1;
+    if (!positions || !idx || !normals || !uvs || !mat_ids) OHB_FAIL(c, "ohb_set_geometry: null array");
+    if (stride_bytes < 12 || (stride_bytes & 3)) OHB_FAIL(c, "ohb_set_geometry: stride must be >= 12 and a multiple of 4");
+    if (ntris >= (1u << 29)) OHB_FAIL(c, "ohb_set_geometry: too many triangles (leaf refs hold 29 bits)");
+    cudaSetDevice(c->device);
+    for (size_t i = 0; i < size_t(ntris) * 3; i++) if (idx[i] >= nverts) OHB_FAIL(c, "ohb_set_geometry: index out of range");
+    c->nverts = nverts; c->ntris = ntris; c->posStride = stride_bytes; c->accelValid = false;
+    CU(c, c->positions.reserve(size_t(nverts) * stride_bytes)); CU(c, c->indices.reserve(size_t(ntris) * 12));
+    CU(c, c->normals.reserve(size_t(nverts) * 16)); CU(c, c->uvs.reserve(size_t(nverts) * 8)); CU(c, c->matIds.reserve(size_t(ntris) * 4));
+    CU(c, cudaMemcpyAsync(c->positions.p, positions, size_t(nverts) * stride_bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->indices.p, idx, size_t(ntris) * 12, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->normals.p, normals, size_t(nverts) * 16, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->uvs.p, uvs, size_t(nverts) * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->matIds.p, mat_ids, size_t(ntris) * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int ohb_set_instances(ohb_ctx* c, const ohb_instance* inst, uint32_t n) {
+    if (!c) return 1;
+    if (n && !inst) OHB_FAIL(c, "ohb_set_instances: null array");
+    c->instances.assign(inst, inst + n); c->accelValid = false;
+    return 0;
+}
+
+int ohb_set_materials(ohb_ctx* c, const float* mc, uint32_t nmat) {
+    if (!c) return 1;
+    if (!mc || !nmat) OHB_FAIL(c, "ohb_set_materials: empty");
+    cudaSetDevice(c->device);
+    c->nmat = nmat;
+    CU(c, c->matColors.reserve(size_t(nmat) * 48));
+    CU(c, cudaMemcpyAsync(c->matColors.p, mc, size_t(nmat) * 48, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int ohb_set_textures(ohb_ctx* c, const uint8_t* layers, uint32_t w, uint32_t h, uint32_t n) {
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    if (!layers || !n) { c->texW = c->texH = c->texLayers = 0; return 0; }
+    size_t bytes = size_t(w) * h * 4u * n;
+    CU(c, c->tex.reserve(bytes));
+    CU(c, cudaMemcpyAsync(c->tex.p, layers, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->texW = w; c->texH = h; c->texLayers = n;
+    return 0;
+}
+
+int ohb_set_lights(ohb_ctx* c, const void* ssbo, size_t bytes) {
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    if (!ssbo || bytes < 16) { c->lightCount = 0; c->envMapTexIdx = 0xFFFFFFFFu; c->envIntensity = 1.0f; return 0; }   // no light SSBO (quirk Q13)
+    const uint8_t* b = static_cast<const uint8_t*>(ssbo);
+    uint32_t cnt; memcpy(&cnt, b, 4); memcpy(&c->envMapTexIdx, b + 4, 4); memcpy(&c->envIntensity, b + 8, 4);
+    uint32_t avail = uint32_t((bytes - 16) / 80);
+    if (cnt > avail) OHB_FAIL(c, "ohb_set_lights: lightCount exceeds buffer");
+    c->lightCount = cnt;
+    if (cnt) {
+        CU(c, c->lights.reserve(size_t(cnt) * 80));
+        CU(c, cudaMemcpyAsync(c->lights.p, b + 16, size_t(cnt) * 80, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+int ohb_set_env(ohb_ctx* c, const float* rgba, uint32_t w, uint32_t h) {
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    if (!rgba || !w || !h) { c->envW = c->envH = 0; c->envIntegral = 0.0f; return 0; }
+    size_t n = size_t(w) * h;
+    CU(c, c->env.reserve(n * 16)); CU(c, c->cond.reserve(n * 4)); CU(c, c->marg.reserve(size_t(h) * 4)); CU(c, c->rowTotal.reserve(size_t(h) * 4)); CU(c, c->integral.reserve(4));
+    CU(c, cudaMemcpyAsync(c->env.p, rgba, n * 16, cudaMemcpyHostToDevice, c->stream));
+    launchEnvCdf(c->env.as<f4>(), w, h, c->cond.as<float>(), c->marg.as<float>(), c->rowTotal.as<float>(), c->integral.as<float>(), c->stream, &c->launches);
+    CU(c, cudaMemcpyAsync(&c->envIntegral, c->integral.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->envW = w; c->envH = h;
+    return 0;
+}
+
+int ohb_get_env_cdf(ohb_ctx* c, float* marg, float* cond, float* integral) {
+    if (!c) return 1;
+    if (!c->envW) OHB_FAIL(c, "ohb_get_env_cdf: no environment map");
+    cudaSetDevice(c->device);
+    if (marg) CU(c, cudaMemcpyAsync(marg, c->marg.p, size_t(c->envH) * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (cond) CU(c, cudaMemcpyAsync(cond, c->cond.p, size_t(c->envW) * c->envH * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (integral) *integral = c->envIntegral;
+    return 0;
+}
+
+static void fillScene(ohb_ctx* c, SceneDev& s) {
+    memset(&s, 0, sizeof(s));
+    s.nodes = c->nodes.as<f4>(); s.tris = c->tris.as<f4>(); s.rootRef = c->rootRef; s.numTris = c->accelValid ? c->numActive : 0u;
+    s.indices = c->indices.as<uint32_t>(); s.normals = c->normals.as<f4>(); s.uvs = c->uvs.as<f2>(); s.matIds = c->matIds.as<uint32_t>();
+    s.triInst = c->triInst.as<uint32_t>(); s.instNormalMat = c->instNormalMat.as<f4>(); s.instInv = c->instInv.as<f4>();
+    s.matColors = c->matColors.as<f4>();
+    s.tex = c->tex.as<uint8_t>(); s.texW = c->texW; s.texH = c->texH; s.texLayers = c->texLayers;
+    s.lights = c->lights.as<GPULight>(); s.lightCount = c->lightCount; s.envMapTexIdx = c->envMapTexIdx; s.envIntensity = c->envIntensity;
+    s.env = c->envW ? c->env.as<f4>() : nullptr; s.envW = c->envW; s.envH = c->envH;
+    s.marg = c->marg.as<float>(); s.cond = c->cond.as<float>(); s.envIntegral = c->envIntegral;
+    if (!c->envW) s.envMapTexIdx = 0xFFFFFFFFu;
+}
+
+int ohb_env_sample_batch(ohb_ctx* c, const float* u12, uint32_t n, float* dir_pdf, float* pdf_of_dir) {
+    if (!c) return 1;
+    if (!c->envW) OHB_FAIL(c, "ohb_env_sample_batch: no environment map");
+    cudaSetDevice(c->device);
+    CU(c, c->hookRays.reserve(size_t(n) * 8)); CU(c, c->hookOut.reserve(size_t(n) * 16)); CU(c, c->hookAux.reserve(size_t(n) * 4));
+    CU(c, cudaMemcpyAsync(c->hookRays.p, u12, size_t(n) * 8, cudaMemcpyHostToDevice, c->stream));
+    SceneDev s; fillScene(c, s);
+    launchEnvSample(s, c->hookRays.as<float>(), n, c->hookOut.as<f4>(), c->hookAux.as<float>(), c->stream, &c->launches);
+    CU(c, cudaMemcpyAsync(dir_pdf, c->hookOut.p, size_t(n) * 16, cudaMemcpyDeviceToHost, c->stream));
+    if (pdf_of_dir) CU(c, cudaMemcpyAsync(pdf_of_dir, c->hookAux.p, size_t(n) * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int ohb_build_accel(ohb_ctx* c) {
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    if (!c->ntris) OHB_FAIL(c, "ohb_build_accel: no geometry");
+    // instance tables (normal matrix = transpose(inverse(mat3)), world->object) — pt_closesthit.rchit:66
+    uint32_t ni = uint32_t(c->instances.size());
+    std::vector<uint32_t> triInst(c->ntris, 0xFFFFFFFFu), active;
+    std::vector<float> xf(size_t(ni) * 12 + 12), nm(size_t(ni) * 12 + 12), iv(size_t(ni) * 12 + 12);
+    for (uint32_t i = 0; i < ni; i++) {
+        const ohb_instance& in = c->instances[i];
+        if (uint64_t(in.first_tri) + in.tri_count > c->ntris) OHB_FAIL(c, "ohb_build_accel: instance triangle range out of bounds");
+        memcpy(&xf[size_t(i) * 12], in.xform, 48);
+        const float* a = in.xform;
+        float co[3][3];
+        co[0][0] = a[5] * a[10] - a[6] * a[9];  co[0][1] = a[6] * a[8] - a[4] * a[10]; co[0][2] = a[4] * a[9] - a[5] * a[8];
+        co[1][0] = a[2] * a[9] - a[1] * a[10];  co[1][1] = a[0] * a[10] - a[2] * a[8]; co[1][2] = a[1] * a[8] - a[0] * a[9];
+        co[2][0] = a[1] * a[6] - a[2] * a[5];   co[2][1] = a[2] * a[4] - a[0] * a[6];  co[2][2] = a[0] * a[5] - a[1] * a[4];
+        float det = a[0] * co[0][0] + a[1] * co[0][1] + a[2] * co[0][2];
+        float id = 1.0f / det;
+        for (int r = 0; r < 3; r++) {
+            for (int k = 0; k < 3; k++) nm[size_t(i) * 12 + r * 4 + k] = co[r][k] * id;
+            nm[size_t(i) * 12 + r * 4 + 3] = 0.0f;
+        }
+        for (int r = 0; r < 3; r++) {
+            float* row = &iv[size_t(i) * 12 + r * 4];
+            for (int k = 0; k < 3; k++) row[k] = nm[size_t(i) * 12 + k * 4 + r];
+            row[3] = -(row[0] * a[3] + row[1] * a[7] + row[2] * a[11]);
+        }
+        if ((in.mask & 0xFFu) == 0u) continue;   // invisible to cullMask 0xFF
+        for (uint32_t t = in.first_tri; t < in.first_tri + in.tri_count; t++) { if (triInst[t] == 0xFFFFFFFFu) active.push_back(t); triInst[t] = i; }
+    }
+    uint32_t n = uint32_t(active.size());
+    c->numActive = n;
+    CU(c, c->triInst.reserve(size_t(c->ntris) * 4)); CU(c, c->instXform.reserve(xf.size() * 4)); CU(c, c->instNormalMat.reserve(nm.size() * 4)); CU(c, c->instInv.reserve(iv.size() * 4));
+    CU(c, cudaMemcpyAsync(c->triInst.p, triInst.data(), size_t(c->ntris) * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->instXform.p, xf.data(), xf.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->instNormalMat.p, nm.data(), nm.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->instInv.p, iv.data(), iv.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    memset(&c->stats, 0, sizeof(c->stats));
+    c->stats.num_tris = n;
+    if (n == 0) { c->accelValid = true; c->rootRef = 0; CU(c, cudaStreamSynchronize(c->stream)); return 0; }
+    size_t nn = n;
+    CU(c, c->activeTris.reserve(nn * 4)); CU(c, cudaMemcpyAsync(c->activeTris.p, active.data(), nn * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, c->wtri.reserve(nn * 48)); CU(c, c->primLo.reserve(nn * 16)); CU(c, c->primHi.reserve(nn * 16)); CU(c, c->boundsBits.reserve(32));
+    CU(c, c->keys.reserve(nn * 8)); CU(c, c->vals.reserve(nn * 4)); CU(c, c->keysTmp.reserve(nn * 8)); CU(c, c->valsTmp.reserve(nn * 4));
+    CU(c, c->sortTemp.reserve(size_t(radixSortTempWords(n)) * 4));
+    CU(c, c->left.reserve(nn * 4)); CU(c, c->right.reserve(nn * 4)); CU(c, c->parentInner.reserve(nn * 4)); CU(c, c->parentLeaf.reserve(nn * 4));
+    CU(c, c->rangeFirst.reserve(nn * 4)); CU(c, c->rangeLast.reserve(nn * 4)); CU(c, c->nodeLo.reserve(nn * 16)); CU(c, c->nodeHi.reserve(nn * 16));
+    CU(c, c->visit.reserve(nn * 4)); CU(c, c->newIndex.reserve(nn * 4)); CU(c, c->emitCounter.reserve(4)); CU(c, c->sah.reserve(8));
+    CU(c, c->nodes.reserve(nn * 64)); CU(c, c->tris.reserve(nn * 48));
+    BuildArrays b{};
+    b.positions = c->positions.as<uint8_t>(); b.posStride = c->posStride; b.indices = c->indices.as<uint32_t>(); b.triInst = c->triInst.as<uint32_t>();
+    b.instXform = c->instXform.as<f4>(); b.activeTris = c->activeTris.as<uint32_t>(); b.n = n;
+    b.wtri = c->wtri.as<f4>(); b.primLo = c->primLo.as<f4>(); b.primHi = c->primHi.as<f4>(); b.boundsBits = c->boundsBits.as<uint32_t>();
+    b.keys = c->keys.as<uint64_t>(); b.vals = c->vals.as<uint32_t>();
+    b.left = c->left.as<int32_t>(); b.right = c->right.as<int32_t>(); b.parentInner = c->parentInner.as<int32_t>(); b.parentLeaf = c->parentLeaf.as<int32_t>();
+    b.rangeFirst = c->rangeFirst.as<uint32_t>(); b.rangeLast = c->rangeLast.as<uint32_t>(); b.nodeLo = c->nodeLo.as<f4>(); b.nodeHi = c->nodeHi.as<f4>();
+    b.visit = c->visit.as<uint32_t>(); b.newIndex = c->newIndex.as<int32_t>(); b.emitCounter = c->emitCounter.as<uint32_t>(); b.sah = c->sah.as<float>();
+    b.nodes = c->nodes.as<f4>(); b.tris = c->tris.as<f4>();
+    CU(c, cudaEventRecord(c->evA, c->stream));
+    launchBuild(b, c->keysTmp.as<uint64_t>(), c->valsTmp.as<uint32_t>(), c->sortTemp.as<uint32_t>(), c->stream, &c->launches);
+    CU(c, cudaEventRecord(c->evB, c->stream));
+    uint32_t emitted = 1; float sah[2] = {0, 0}; f4 rootLo{}, rootHi{};
+    if (n >= 2) {
+        CU(c, cudaMemcpyAsync(&emitted, c->emitCounter.p, 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(sah, c->sah.p, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(&rootLo, c->nodeLo.p, 16, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(&rootHi, c->nodeHi.p, 16, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaGetLastError());
+    c->rootRef = (n <= OHB_MAX_LEAF) ? makeLeafRef(0u, n) : 0;
+    c->accelValid = true;
+    cudaEventElapsedTime(&c->stats.build_ms, c->evA, c->evB);
+    c->stats.num_nodes = (n <= OHB_MAX_LEAF) ? 0u : emitted;
+    c->stats.max_leaf_tris = OHB_MAX_LEAF;
+    float ra = boxArea(xyz(rootLo), xyz(rootHi));
+    c->stats.sah_cost = (n > OHB_MAX_LEAF && ra > 0.0f) ? (sah[0] + sah[1]) / ra : float(n);
+    c->stats.num_leaves = c->stats.num_nodes ? c->stats.num_nodes + 1u : 1u;
+    return 0;
+}
+
+int ohb_get_accel_stats(ohb_ctx* c, ohb_accel_stats* s) { if (!c || !s) return 1; *s = c->stats; return 0; }
+
+int ohb_set_settings(ohb_ctx* c, const ohb_settings* s) {
+    if (!c || !s) return 1;
+    if ((s->max_bounces & 0xFFFFu) > 15u) OHB_FAIL(c, "ohb_set_settings: max_bounces > 15");
+    c->settings = *s;
+    uint32_t spf = s->samples_per_frame; c->settings.samples_per_frame = spf < 1u ? 1u : (spf > 64u ? 64u : spf);   // clampSamplesPerFrame
+    return 0;
+}
+int ohb_get_settings(ohb_ctx* c, ohb_settings* s) { if (!c || !s) return 1; *s = c->settings; return 0; }
+void ohb_reset_accumulation(ohb_ctx* c) { if (!c) return; c->sampleIndex = c->seed; c->historyCount = 0; c->viewChanged = false; }
+void ohb_set_seed(ohb_ctx* c, uint32_t seed) { if (!c) return; c->seed = seed; ohb_reset_accumulation(c); }
+void ohb_notify_view_changed(ohb_ctx* c) {
+    if (!c) return;
+    if (c->settings.profile == OHB_PROFILE_OFFLINE) ohb_reset_accumulation(c);   // resetsAccumulationOnViewChange()
+    else c->viewChanged = true;
+}
+uint32_t ohb_frame_index(const ohb_ctx* c) { return c ? c->sampleIndex : 0u; }
+
+int ohb_set_tile(ohb_ctx* c, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h) {
+    if (!c) return 1;
+    if (w == 0 || h == 0 || uint64_t(x0) + w > c->W || uint64_t(y0) + h > c->H) OHB_FAIL(c, "ohb_set_tile: rectangle outside the frame");
+    c->tileX = x0; c->tileY = y0; c->tileW = w; c->tileH = h;
+    return 0;
+}
+
+static int ensurePaths(ohb_ctx* c, uint32_t cap) {
+    if (cap <= c->pathCapacity) return 0;
+    size_t n = cap;
+    CU(c, c->rayO.reserve(n * 16)); CU(c, c->rayD.reserve(n * 16)); CU(c, c->hit.reserve(n * 16)); CU(c, c->thr.reserve(n * 16)); CU(c, c->rad.reserve(n * 16));
+    CU(c, c->pendA.reserve(n * 16)); CU(c, c->pendB.reserve(n * 16)); CU(c, c->meta.reserve(n * 16));
+    CU(c, c->fh0.reserve(n * 16)); CU(c, c->fh1.reserve(n * 16)); CU(c, c->fh2.reserve(n * 16)); CU(c, c->fh3.reserve(n * 16));
+    CU(c, c->shO.reserve(n * 32)); CU(c, c->shD.reserve(n * 32)); CU(c, c->queueA.reserve(n * 4)); CU(c, c->queueB.reserve(n * 4));
+    c->pathCapacity = cap;
+    return 0;
+}
+
+int ohb_render(ohb_ctx* c, const float view[16], const float proj[16], uint32_t nsamples) {
+    if (!c) return 1;
+    if (!view || !proj) OHB_FAIL(c, "ohb_render: null matrix");
+    if (!c->accelValid) { c->err = "ohb_render: no acceleration structure (call ohb_build_accel)"; return 1; }   // reference: silent return (path_tracer_render.cpp:42)
+    if (!c->nmat) OHB_FAIL(c, "ohb_render: no materials");
+    if (c->settings.profile != OHB_PROFILE_OFFLINE) OHB_FAIL(c, "ohb_render: realtime profile is not available in this build");
+    if (nsamples == 0) return 0;
+    cudaSetDevice(c->device);
+    M4h iv = inverse4(view), ip = inverse4(proj);
+    FrameParams fr{};
+    fr.camPos = mk3(iv.m[12], iv.m[13], iv.m[14]); fr.fwd = mk3(-iv.m[8], -iv.m[9], -iv.m[10]);
+    fr.right = mk3(iv.m[0], iv.m[1], iv.m[2]); fr.up = mk3(iv.m[4], iv.m[5], iv.m[6]);
+    float aspect = float(c->W) / float(c->H);
+    fr.tanY = fabsf(ip.m[5]); fr.tanX = fr.tanY * aspect;
+    fr.W = c->W; fr.H = c->H; fr.maxBounces = c->settings.max_bounces & 0xFFFFu; fr.flags = c->settings.flags;
+    bool envOn = c->envW && c->envMapTexIdx != 0xFFFFFFFFu;
+    fr.envW = envOn ? c->envW : 0u; fr.envH = envOn ? float(c->envH) : 0.0f;
+    fr.fireflyClamp = c->settings.firefly_clamp_lum; fr.sss = c->settings.subsurface_strength;
+    fr.aniso = c->settings.anisotropy_strength; fr.anisoRot = c->settings.anisotropy_rotation; fr.jitX = fr.jitY = 0.0f;   // no Halton jitter without NRD/DLSS-RR (Q15)
+    fr.samplerType = c->settings.sampler_type;
+    fr.tileX = c->tileX; fr.tileY = c->tileY; fr.tileW = c->tileW; fr.tileH = c->tileH;
+    uint32_t tilesX = (c->tileW + 7u) / 8u, tilesY = (c->tileH + 3u) / 4u;
+    uint32_t numPixels = tilesX * tilesY * 32u;
+    static const uint32_t maxPaths = []() { const char* e = getenv("OHB_MAX_PATHS"); uint32_t v = e ? uint32_t(strtoul(e, nullptr, 10)) : 0u; return v ? v : (8u << 20); }();
+    uint32_t spb = std::max(1u, std::min(nsamples, maxPaths / std::max(numPixels, 1u)));
+    if (ensurePaths(c, numPixels * spb)) return 1;
+    SceneDev s; fillScene(c, s);
+    float* dumpDev = nullptr;
+    if (c->dumpHost) {
+        size_t need = size_t(nsamples) * c->W * c->H * 4u;
+        if (need > c->dumpCapacity) OHB_FAIL(c, "ohb_render: sample dump buffer too small");
+        CU(c, c->sampleDump.reserve(need * 4)); CU(c, cudaMemsetAsync(c->sampleDump.p, 0, need * 4, c->stream));
+        dumpDev = c->sampleDump.as<float>();
+    }
+    uint32_t* small = c->smallCounters.as<uint32_t>();
+    uint32_t done = 0;
+    while (done < nsamples) {
+        uint32_t k = std::min(spb, nsamples - done);
+        PathArrays P{};
+        P.rayO = c->rayO.as<f4>(); P.rayD = c->rayD.as<f4>(); P.hit = c->hit.as<ohb_hit>(); P.thr = c->thr.as<f4>(); P.rad = c->rad.as<f4>();
+        P.pendA = c->pendA.as<f4>(); P.pendB = c->pendB.as<f4>(); P.meta = c->meta.as<u4>();
+        P.fh0 = c->fh0.as<f4>(); P.fh1 = c->fh1.as<f4>(); P.fh2 = c->fh2.as<f4>(); P.fh3 = c->fh3.as<f4>();
+        P.shO = c->shO.as<f4>(); P.shD = c->shD.as<f4>();
+        P.queueIn = c->queueA.as<uint32_t>(); P.queueOut = c->queueB.as<uint32_t>();
+        P.countIn = small + 0; P.countOut = small + 1; P.shCount = small + 2;
+        P.counters = c->devCounters.as<unsigned long long>();
+        P.albedoAOV = c->albedoAOV.as<f4>(); P.normalAOV = c->normalAOV.as<f4>();
+        P.numPixels = numPixels; P.samplesInBatch = k; P.firstSampleIndex = c->sampleIndex;
+        FilmArrays F{};
+        F.accum = c->accum.as<f4>(); F.ldr = c->ldr.as<uint32_t>(); F.historyCount = c->historyCount; F.sumMode = c->sumMode;
+        F.sampleDump = dumpDev ? dumpDev + size_t(done) * c->W * c->H * 4u : nullptr;
+        launchOfflineBatch(s, fr, P, F, small + 4, c->numSMs, c->stream, &c->launches, c->timingOn ? &c->timing : nullptr);
+        c->sampleIndex += k; c->historyCount += k; done += k;   // path_tracer_render.cpp:1274-1275
+    }
+    c->viewChanged = false;
+    CU(c, cudaGetLastError());
+    if (c->dumpHost) {
+        CU(c, cudaMemcpyAsync(c->dumpHost, c->sampleDump.p, size_t(nsamples) * c->W * c->H * 16u, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+int ohb_synchronize(ohb_ctx* c) {
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaGetLastError());
+    return 0;
+}
+int ohb_read_ldr(ohb_ctx* c, uint8_t* rgba8) {
+    if (!c || !rgba8) return 1;
+    cudaSetDevice(c->device);
+    CU(c, cudaMemcpyAsync(rgba8, c->ldr.p, size_t(c->W) * c->H * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int ohb_read_hdr(ohb_ctx* c, float* accum, float* albedo, float* normal) {
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    size_t bytes = size_t(c->W) * c->H * 16;
+    if (accum) CU(c, cudaMemcpyAsync(accum, c->accum.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (albedo) CU(c, cudaMemcpyAsync(albedo, c->albedoAOV.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (normal) CU(c, cudaMemcpyAsync(normal, c->normalAOV.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+void* ohb_accum_dev_ptr(ohb_ctx* c, size_t* bytes) { if (!c) return nullptr; if (bytes) *bytes = size_t(c->W) * c->H * 16; return c->accum.p; }
+int ohb_set_accum_mode(ohb_ctx* c, int sum_mode) { if (!c) return 1; c->sumMode = sum_mode ? 1 : 0; return 0; }
+int ohb_resolve(ohb_ctx* c) {
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    launchResolve(c->accum.as<f4>(), c->ldr.as<uint32_t>(), c->W * c->H, c->sumMode, c->stream, &c->launches);
+    CU(c, cudaGetLastError());
+    return 0;
+}
+
+static int traceHook(ohb_ctx* c, const ohb_ray* rays, uint32_t n, ohb_hit* hits, uint8_t* occ) {
+    if (!c) return 1;
+    if (!c->accelValid) OHB_FAIL(c, "trace: no acceleration structure");
+    if (n == 0) return 0;
+    cudaSetDevice(c->device);
+    CU(c, c->hookRays.reserve(size_t(n) * sizeof(ohb_ray))); CU(c, c->hookOut.reserve(size_t(n) * 16));
+    CU(c, cudaMemcpyAsync(c->hookRays.p, rays, size_t(n) * sizeof(ohb_ray), cudaMemcpyHostToDevice, c->stream));
+    SceneDev s; fillScene(c, s);
+    launchTraceBatch(s, c->hookRays.as<ohb_ray>(), n, hits ? c->hookOut.as<ohb_hit>() : nullptr, c->hookOut.as<uint8_t>(), c->smallCounters.as<uint32_t>() + 8, c->numSMs, c->stream, &c->launches);
+    if (hits) CU(c, cudaMemcpyAsync(hits, c->hookOut.p, size_t(n) * 16, cudaMemcpyDeviceToHost, c->stream));
+    else      CU(c, cudaMemcpyAsync(occ, c->hookOut.p, n, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaGetLastError());
+    return 0;
+}
+int ohb_trace_batch(ohb_ctx* c, const ohb_ray* rays, uint32_t n, ohb_hit* hits) { if (!rays || !hits) return 1; return traceHook(c, rays, n, hits, nullptr); }
+int ohb_occluded_batch(ohb_ctx* c, const ohb_ray* rays, uint32_t n, uint8_t* occ) { if (!rays || !occ) return 1; return traceHook(c, rays, n, nullptr, occ); }
+
+int ohb_set_sample_dump(ohb_ctx* c, float* host, size_t cap) { if (!c) return 1; c->dumpHost = host; c->dumpCapacity = host ? cap : 0; return 0; }
+
+int ohb_get_counters(ohb_ctx* c, ohb_counters* out) {
+    if (!c || !out) return 1;
+    cudaSetDevice(c->device);
+    unsigned long long d[8];
+    CU(c, cudaMemcpyAsync(d, c->devCounters.p, 64, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    memset(out, 0, sizeof(*out));
+    out->samples = d[0]; out->closest_rays = d[1]; out->shadow_rays = d[2]; out->closest_hits = d[3]; out->kernel_launches = c->launches;
+    return 0;
+}
+void ohb_reset_counters(ohb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaMemsetAsync(c->devCounters.p, 0, 64, c->stream);
+    c->launches = 0; c->timing.reset();
+}
+int ohb_enable_timing(ohb_ctx* c, int enable) { if (!c) return 1; c->timingOn = enable != 0; return 0; }
+int ohb_get_timing(ohb_ctx* c, float* trace_ms, float* shade_ms, float* total_ms) {
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->timing.collect();
+    if (trace_ms) *trace_ms = float(c->timing.ms[0] + c->timing.ms[2]);
+    if (shade_ms) *shade_ms = float(c->timing.ms[1]);
+    if (total_ms) *total_ms = float(c->timing.ms[0] + c->timing.ms[1] + c->timing.ms[2] + c->timing.ms[3]);
+    return 0;
+}
+
+int ohb_get_timing_detail(ohb_ctx* c, float ms[4], uint64_t launches[4]) {
+    if (!c || !ms || !launches) return 1;
+    cudaSetDevice(c->device);
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->timing.collect();
+    for (int i = 0; i < 4; i++) { ms[i] = float(c->timing.ms[i]); launches[i] = c->timing.count[i]; }
+    return 0;
+}
+
+}  // extern "C"

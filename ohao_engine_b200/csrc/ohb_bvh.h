@@ -1,0 +1,227 @@
+// ohb_bvh.h — LBVH construction, per-thread stages (Karras 2012 "Maximizing parallelism in the
+// construction of BVHs, octrees and k-d trees") + leaf collapse + 64-B node emission.
+//
+// Replaces RTAccelerationStructure::{createBLAS, buildTLAS} (rt_acceleration_structure.cpp:205-535),
+// i.e. vkCmdBuildAccelerationStructuresKHR, whose algorithm is inside the Vulkan driver.  The
+// engine's two-level interface is kept at the API (ohb_set_instances); all reference meshes are
+// static (rt_build.cpp:853,865), so instances are flattened into ONE world-space BVH — a TLAS
+// "build" is a re-transform + rebuild, there is no per-ray instance transform.
+//
+// Pipeline (one kernel each, ohb_kernels.cu):
+//   worldTriangles -> sceneBounds -> morton63 -> radix sort (key u64, val u32) -> karras hierarchy
+//   -> bottom-up AABB refit (atomic visit counters) -> collapse subtrees of <= 4 triangles to leaves
+//   -> emit 64-B nodes + 48-B triangles in leaf order -> (optional) treelet SAH restructuring.
+#pragma once
+#include "ohb_traverse.h"
+
+namespace ohb {
+
+struct BuildArrays {
+    // inputs
+    const uint8_t* positions; uint64_t posStride;     // object-space positions, strided
+    const uint32_t* indices;                          // global
+    const uint32_t* triInst;                          // per global tri
+    const f4* instXform;                              // 3 rows per instance (object->world)
+    const uint32_t* activeTris; uint32_t n;           // triangles to build over
+    // intermediates (length n unless noted)
+    f4* wtri;            // 3n : world-space triangles in INPUT order, v0.w = global id
+    f4* primLo; f4* primHi;
+    uint32_t* boundsBits;   // 6 : ordered-uint scene bounds (min xyz, max xyz)
+    uint64_t* keys; uint32_t* vals;          // morton + index (sorted in place by the radix sort)
+    // hierarchy over n-1 internal nodes
+    int32_t* left; int32_t* right;           // child: >=0 internal, <0 => ~leafIndex (sorted position)
+    int32_t* parentInner; int32_t* parentLeaf;
+    uint32_t* rangeFirst; uint32_t* rangeLast;
+    f4* nodeLo; f4* nodeHi;                  // internal node bounds
+    uint32_t* visit;                         // n-1 atomic flags
+    int32_t* newIndex;                       // n-1 : index in the emitted array or -1
+    uint32_t* emitCounter;                   // 1
+    float* sah;                              // 2 : {inner area sum, leaf area*count sum}
+    // outputs
+    f4* nodes; f4* tris;
+};
+
+OHB_HD uint32_t floatOrdered(float f) { uint32_t u = f2u(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+OHB_HD float orderedFloat(uint32_t u) { return u2f((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u); }
+
+OHB_HD void atomicMinU32(uint32_t* p, uint32_t v) {
+#if OHB_DEVICE_CODE
+    atomicMin(p, v);
+#else
+    if (v < *p) *p = v;
+#endif
+}
+OHB_HD void atomicMaxU32(uint32_t* p, uint32_t v) {
+#if OHB_DEVICE_CODE
+    atomicMax(p, v);
+#else
+    if (v > *p) *p = v;
+#endif
+}
+OHB_HD uint32_t atomicIncU32(uint32_t* p) {
+#if OHB_DEVICE_CODE
+    return atomicAdd(p, 1u);
+#else
+    return (*p)++;
+#endif
+}
+OHB_HD void atomicAddF32(float* p, float v) {
+#if OHB_DEVICE_CODE
+    atomicAdd(p, v);
+#else
+    *p += v;
+#endif
+}
+OHB_HD void fenceDevice() {
+#if OHB_DEVICE_CODE
+    __threadfence();
+#endif
+}
+
+// Stage 1: object -> world (spec arithmetic: ((m0*x + m1*y) + m2*z) + m3, one rounding per op).
+OHB_HD f3 xformPoint(const f4* rows, f3 p) {
+    f4 r0 = rows[0], r1 = rows[1], r2 = rows[2];
+    return mk3(xadd(xadd(xadd(xmul(r0.x, p.x), xmul(r0.y, p.y)), xmul(r0.z, p.z)), r0.w),
+               xadd(xadd(xadd(xmul(r1.x, p.x), xmul(r1.y, p.y)), xmul(r1.z, p.z)), r1.w),
+               xadd(xadd(xadd(xmul(r2.x, p.x), xmul(r2.y, p.y)), xmul(r2.z, p.z)), r2.w));
+}
+OHB_HD void buildWorldTri(const BuildArrays& b, uint32_t a) {
+    uint32_t g = b.activeTris[a];
+    const f4* rows = b.instXform + size_t(b.triInst[g]) * 3u;
+    f3 v[3];
+    for (int k = 0; k < 3; k++) {
+        const float* pp = reinterpret_cast<const float*>(b.positions + size_t(b.indices[size_t(g) * 3 + k]) * b.posStride);
+        v[k] = xformPoint(rows, mk3(pp[0], pp[1], pp[2]));
+    }
+    b.wtri[size_t(a) * 3 + 0] = mk4(v[0], u2f(g));
+    b.wtri[size_t(a) * 3 + 1] = mk4(v[1], 0.0f);
+    b.wtri[size_t(a) * 3 + 2] = mk4(v[2], 0.0f);
+    f3 lo = vmin(v[0], vmin(v[1], v[2])), hi = vmax(v[0], vmax(v[1], v[2]));
+    b.primLo[a] = mk4(lo, 0.0f); b.primHi[a] = mk4(hi, 0.0f);
+    atomicMinU32(b.boundsBits + 0, floatOrdered(lo.x)); atomicMinU32(b.boundsBits + 1, floatOrdered(lo.y)); atomicMinU32(b.boundsBits + 2, floatOrdered(lo.z));
+    atomicMaxU32(b.boundsBits + 3, floatOrdered(hi.x)); atomicMaxU32(b.boundsBits + 4, floatOrdered(hi.y)); atomicMaxU32(b.boundsBits + 5, floatOrdered(hi.z));
+}
+
+// Stage 2: 63-bit Morton code of the AABB centre (21 bits per axis).
+OHB_HD uint64_t expandBits21(uint64_t v) {
+    v &= 0x1FFFFFull;
+    v = (v | (v << 32)) & 0x1F00000000FFFFull;
+    v = (v | (v << 16)) & 0x1F0000FF0000FFull;
+    v = (v | (v << 8)) & 0x100F00F00F00F00Full;
+    v = (v | (v << 4)) & 0x10C30C30C30C30C3ull;
+    v = (v | (v << 2)) & 0x1249249249249249ull;
+    return v;
+}
+OHB_HD void buildMorton(const BuildArrays& b, uint32_t a) {
+    f3 lo = mk3(orderedFloat(b.boundsBits[0]), orderedFloat(b.boundsBits[1]), orderedFloat(b.boundsBits[2]));
+    f3 hi = mk3(orderedFloat(b.boundsBits[3]), orderedFloat(b.boundsBits[4]), orderedFloat(b.boundsBits[5]));
+    f3 ext = hi - lo;
+    f3 c = (xyz(b.primLo[a]) + xyz(b.primHi[a])) * 0.5f;
+    float sx = ext.x > 0.0f ? (c.x - lo.x) / ext.x : 0.0f, sy = ext.y > 0.0f ? (c.y - lo.y) / ext.y : 0.0f, sz = ext.z > 0.0f ? (c.z - lo.z) / ext.z : 0.0f;
+    const float S = 2097152.0f;   // 2^21
+    uint64_t ix = uint64_t(fminf(fmaxf(sx * S, 0.0f), S - 1.0f)), iy = uint64_t(fminf(fmaxf(sy * S, 0.0f), S - 1.0f)), iz = uint64_t(fminf(fmaxf(sz * S, 0.0f), S - 1.0f));
+    b.keys[a] = (expandBits21(ix) << 2) | (expandBits21(iy) << 1) | expandBits21(iz);
+    b.vals[a] = a;
+}
+
+// Stage 4: Karras hierarchy.  delta(i,j) = common prefix length of the (key, index) pairs.
+OHB_HD int karrasDelta(const uint64_t* keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    uint64_t a = keys[i], c = keys[j];
+    if (a == c) return 64 + clz32(uint32_t(i) ^ uint32_t(j));
+    return clz64(a ^ c);
+}
+OHB_HD void buildHierarchyNode(const BuildArrays& b, int i) {
+    const int n = int(b.n);
+    const uint64_t* keys = b.keys;
+    int d = (karrasDelta(keys, n, i, i + 1) - karrasDelta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = karrasDelta(keys, n, i, i - d);
+    int lmax = 2;
+    while (karrasDelta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (karrasDelta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = karrasDelta(keys, n, i, j);
+    int s = 0;
+    for (int t = (l + 1) / 2;; t = (t + 1) / 2) {   // t = ceil(l / 2^k), k = 1, 2, ... down to 1
+        if (karrasDelta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+        if (t == 1) break;
+    }
+    int gamma = i + s * d + (d < 0 ? -1 : 0);
+    int lo = i < j ? i : j, hi = i < j ? j : i;
+    int lc, rc;
+    if (lo == gamma) { lc = ~gamma; b.parentLeaf[gamma] = i; } else { lc = gamma; b.parentInner[gamma] = i; }
+    if (hi == gamma + 1) { rc = ~(gamma + 1); b.parentLeaf[gamma + 1] = i; } else { rc = gamma + 1; b.parentInner[gamma + 1] = i; }
+    b.left[i] = lc; b.right[i] = rc;
+    b.rangeFirst[i] = uint32_t(lo); b.rangeLast[i] = uint32_t(hi);
+    if (i == 0) b.parentInner[0] = -1;
+}
+
+// Stage 5: bottom-up refit.  Thread per sorted leaf; the second arrival at a node merges.
+OHB_HD void refitFromLeaf(const BuildArrays& b, uint32_t leaf) {
+    int node = b.parentLeaf[leaf];
+    while (node >= 0) {
+        fenceDevice();
+        if (atomicIncU32(b.visit + node) == 0u) return;    // first arrival: sibling not ready
+        fenceDevice();
+        int lc = b.left[node], rc = b.right[node];
+        f3 llo, lhi, rlo, rhi;
+        if (lc < 0) { uint32_t a = b.vals[~lc]; llo = xyz(b.primLo[a]); lhi = xyz(b.primHi[a]); } else { llo = xyz(b.nodeLo[lc]); lhi = xyz(b.nodeHi[lc]); }
+        if (rc < 0) { uint32_t a = b.vals[~rc]; rlo = xyz(b.primLo[a]); rhi = xyz(b.primHi[a]); } else { rlo = xyz(b.nodeLo[rc]); rhi = xyz(b.nodeHi[rc]); }
+        b.nodeLo[node] = mk4(vmin(llo, rlo), 0.0f); b.nodeHi[node] = mk4(vmax(lhi, rhi), 0.0f);
+        node = b.parentInner[node];
+    }
+}
+
+OHB_HD uint32_t nodeCount(const BuildArrays& b, int i) { return b.rangeLast[i] - b.rangeFirst[i] + 1u; }
+OHB_HD float boxArea(f3 lo, f3 hi) { f3 e = hi - lo; return 2.0f * (e.x * e.y + e.y * e.z + e.z * e.x); }
+
+// Stage 6a: which internal nodes survive the collapse (more than OHB_MAX_LEAF triangles below).
+OHB_HD void assignNodeIndex(const BuildArrays& b, int i) {
+    if (nodeCount(b, i) <= OHB_MAX_LEAF) { b.newIndex[i] = -1; return; }
+    b.newIndex[i] = (i == 0) ? 0 : int32_t(atomicIncU32(b.emitCounter));   // counter starts at 1
+}
+// Conservative outward padding of stored boxes (DESIGN.md "Robustness").
+OHB_HD void padBox(f3& lo, f3& hi) {
+    const float k = 9.5367431640625e-7f;   // 2^-20
+    lo = mk3(lo.x - fabsf(lo.x) * k - 1e-30f, lo.y - fabsf(lo.y) * k - 1e-30f, lo.z - fabsf(lo.z) * k - 1e-30f);
+    hi = mk3(hi.x + fabsf(hi.x) * k + 1e-30f, hi.y + fabsf(hi.y) * k + 1e-30f, hi.z + fabsf(hi.z) * k + 1e-30f);
+}
+OHB_HD void childRefAndBox(const BuildArrays& b, int c, int32_t& ref, f3& lo, f3& hi) {
+    if (c < 0) {
+        uint32_t pos = uint32_t(~c); uint32_t a = b.vals[pos];
+        ref = makeLeafRef(pos, 1u); lo = xyz(b.primLo[a]); hi = xyz(b.primHi[a]);
+    } else {
+        lo = xyz(b.nodeLo[c]); hi = xyz(b.nodeHi[c]);
+        uint32_t cnt = nodeCount(b, c);
+        ref = (cnt <= OHB_MAX_LEAF) ? makeLeafRef(b.rangeFirst[c], cnt) : b.newIndex[c];
+    }
+}
+// Stage 6b: emit the 64-B node of a surviving internal node + SAH bookkeeping.
+OHB_HD void emitNode(const BuildArrays& b, int i) {
+    int32_t ni = b.newIndex[i];
+    if (ni < 0) return;
+    int32_t r0, r1; f3 lo0, hi0, lo1, hi1;
+    childRefAndBox(b, b.left[i], r0, lo0, hi0);
+    childRefAndBox(b, b.right[i], r1, lo1, hi1);
+    float a0 = boxArea(lo0, hi0), a1 = boxArea(lo1, hi1);
+    float inner = (i == 0 ? boxArea(xyz(b.nodeLo[0]), xyz(b.nodeHi[0])) : 0.0f) + (r0 >= 0 ? a0 : 0.0f) + (r1 >= 0 ? a1 : 0.0f);
+    float leaf = (r0 < 0 ? a0 * float(leafCount(r0)) : 0.0f) + (r1 < 0 ? a1 * float(leafCount(r1)) : 0.0f);
+    atomicAddF32(b.sah + 0, inner); atomicAddF32(b.sah + 1, leaf);
+    padBox(lo0, hi0); padBox(lo1, hi1);
+    f4* np = b.nodes + size_t(ni) * 4u;
+    np[0] = mk4(lo0.x, hi0.x, lo0.y, hi0.y);
+    np[1] = mk4(lo1.x, hi1.x, lo1.y, hi1.y);
+    np[2] = mk4(lo0.z, hi0.z, lo1.z, hi1.z);
+    np[3] = mk4(u2f(uint32_t(r0)), u2f(uint32_t(r1)), 0.0f, 0.0f);
+}
+// Stage 7: triangles into leaf (sorted) order.
+OHB_HD void emitTri(const BuildArrays& b, uint32_t pos) {
+    uint32_t a = b.vals[pos];
+    b.tris[size_t(pos) * 3 + 0] = b.wtri[size_t(a) * 3 + 0];
+    b.tris[size_t(pos) * 3 + 1] = b.wtri[size_t(a) * 3 + 1];
+    b.tris[size_t(pos) * 3 + 2] = b.wtri[size_t(a) * 3 + 2];
+}
+
+}  // namespace ohb

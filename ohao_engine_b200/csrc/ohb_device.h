@@ -1,0 +1,39 @@
+// ohb_device.h — launch wrappers exported by ohb_kernels.cu to the C-ABI layer (ohb_api.cu).
+#pragma once
+#include "ohb_bvh.h"
+#include "ohb_integrator.h"
+#include <cuda_runtime.h>
+#include <vector>
+
+namespace ohb {
+
+// CUDA-event timing of kernel categories on the launching stream (bench.py roofline line):
+// 0 = closest-hit traversal, 1 = shading, 2 = any-hit traversal, 3 = film.
+struct TimingHooks {
+    struct Span { cudaEvent_t a, b; int cat; };
+    std::vector<Span> spans; size_t used = 0; cudaEvent_t pendingStart[4] = {nullptr, nullptr, nullptr, nullptr};
+    double ms[4] = {0, 0, 0, 0}; uint64_t count[4] = {0, 0, 0, 0};
+    void begin(int cat, cudaStream_t st) {
+        if (used == spans.size()) { Span s; cudaEventCreate(&s.a); cudaEventCreate(&s.b); s.cat = cat; spans.push_back(s); }
+        spans[used].cat = cat; cudaEventRecord(spans[used].a, st);
+    }
+    void end(int, cudaStream_t st) { cudaEventRecord(spans[used].b, st); used++; }
+    void collect() {   // call after the stream is synchronised
+        for (size_t i = 0; i < used; i++) { float t = 0; cudaEventElapsedTime(&t, spans[i].a, spans[i].b); ms[spans[i].cat] += t; count[spans[i].cat]++; }
+        used = 0;
+    }
+    void reset() { collect(); for (int i = 0; i < 4; i++) { ms[i] = 0; count[i] = 0; } }
+    ~TimingHooks() { for (auto& s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); } }
+};
+
+cudaError_t uploadConstants();
+uint32_t radixSortTempWords(uint32_t n);
+void launchBuild(const BuildArrays& b, uint64_t* keysTmp, uint32_t* valsTmp, uint32_t* sortTemp, cudaStream_t st, uint64_t* launches);
+void launchEnvCdf(const f4* env, uint32_t W, uint32_t H, float* cond, float* marg, float* rowTotal, float* integral, cudaStream_t st, uint64_t* launches);
+void launchEnvSample(const SceneDev& sc, const float* u12, uint32_t n, f4* dirPdf, float* pdfOfDir, cudaStream_t st, uint64_t* launches);
+void launchOfflineBatch(const SceneDev& sc, const FrameParams& fr, PathArrays P, const FilmArrays& F,
+                        uint32_t* work, int numSMs, cudaStream_t st, uint64_t* launches, TimingHooks* th);
+void launchResolve(f4* accum, uint32_t* ldr, uint32_t n, int sumMode, cudaStream_t st, uint64_t* launches);
+void launchTraceBatch(const SceneDev& sc, const ohb_ray* rays, uint32_t n, ohb_hit* hits, uint8_t* occ, uint32_t* work, int numSMs, cudaStream_t st, uint64_t* launches);
+
+}  // namespace ohb

@@ -1,0 +1,366 @@
+// ohb_kernels.cu — sm_100a kernels of the B200 path tracer and their launch wrappers.
+//
+// Every kernel here is a thin scheduling shell around the per-thread code of ohb_bvh.h /
+// ohb_traverse.h / ohb_integrator.h.  Scheduling choices (DESIGN.md "Kernels"):
+//   * traversal kernels are persistent: gridDim = SMs x resident blocks, each warp pulls 32 rays at
+//     a time from a global work counter, so the tail of an incoherent wavefront does not idle SMs;
+//   * queue pushes are warp-aggregated (one atomic per warp), no host round trip between the
+//     iterations of a wavefront: queue sizes live in device memory and kernels read them;
+//   * the radix sort ranks keys with __match_any_sync per warp-private digit counters (stable,
+//     no shared-memory atomics in the scatter loop).
+#include "ohb_device.h"
+#include <cuda_runtime.h>
+
+namespace ohb {
+
+cudaError_t uploadConstants() { return cudaSuccess; }   // constants are statically initialised (ohb_scene.h)
+
+static inline unsigned gridFor(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// =============================================================================================
+// BVH build
+// =============================================================================================
+__global__ void k_world_tris(BuildArrays b) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < b.n) buildWorldTri(b, i); }
+__global__ void k_morton(BuildArrays b) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < b.n) buildMorton(b, i); }
+__global__ void k_hierarchy(BuildArrays b) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i + 1 < b.n) buildHierarchyNode(b, int(i)); }
+__global__ void k_refit(BuildArrays b) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < b.n) refitFromLeaf(b, i); }
+__global__ void k_assign_index(BuildArrays b) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i + 1 < b.n) assignNodeIndex(b, int(i)); }
+__global__ void k_emit_nodes(BuildArrays b) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i + 1 < b.n) emitNode(b, int(i)); }
+__global__ void k_emit_tris(BuildArrays b) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < b.n) emitTri(b, i); }
+__global__ void k_init_build(BuildArrays b) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 < b.n) b.visit[i] = 0u;
+    if (i == 0) {
+        b.boundsBits[0] = b.boundsBits[1] = b.boundsBits[2] = 0xFFFFFFFFu;
+        b.boundsBits[3] = b.boundsBits[4] = b.boundsBits[5] = 0u;
+        *b.emitCounter = 1u; b.sah[0] = 0.0f; b.sah[1] = 0.0f;
+    }
+}
+
+// ---- exclusive scan of u32 (block = 256 threads x 8 items) -----------------------------------
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+__global__ void k_scan_block(uint32_t* data, uint32_t n, uint32_t* blockSums) {
+    __shared__ uint32_t warpSums[SCAN_THREADS / 32];
+    uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS]; uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < n) ? data[base + k] : 0u; sum += v[k]; }
+    uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (uint32_t)o) inc += t; }
+    if (lane == 31u) warpSums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < SCAN_THREADS / 32 ? warpSums[lane] : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= (uint32_t)o) w += t; }
+        if (lane < SCAN_THREADS / 32) warpSums[lane] = w;
+    }
+    __syncthreads();
+    uint32_t excl = inc - sum + (warp ? warpSums[warp - 1] : 0u);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) data[base + k] = excl; excl += v[k]; }
+    if (threadIdx.x == SCAN_THREADS - 1 && blockSums) blockSums[blockIdx.x] = excl;
+}
+__global__ void k_scan_add(uint32_t* data, uint32_t n, const uint32_t* blockSums) {
+    uint32_t i = blockIdx.x * SCAN_TILE + threadIdx.x;
+    uint32_t add = blockSums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { uint32_t j = i + k * SCAN_THREADS; if (j < n) data[j] += add; }
+}
+// temp must hold ceil(n/2048) + ceil(that/2048) + ... + 8 entries
+void exclusiveScanU32(uint32_t* data, uint32_t n, uint32_t* temp, cudaStream_t st, uint64_t* launches) {
+    uint32_t nb = gridFor(n, SCAN_TILE);
+    k_scan_block<<<nb, SCAN_THREADS, 0, st>>>(data, n, nb > 1 ? temp : nullptr); (*launches)++;
+    if (nb > 1) {
+        exclusiveScanU32(temp, nb, temp + nb, st, launches);
+        k_scan_add<<<nb, SCAN_THREADS, 0, st>>>(data, n, temp); (*launches)++;
+    }
+}
+
+// ---- LSD radix sort, 8 bits per pass, key u64 / value u32 --------------------------------------
+#define RS_THREADS 256
+#define RS_WARPS 8
+#define RS_ROUNDS 16
+#define RS_TILE (RS_THREADS * RS_ROUNDS)
+__global__ void k_radix_hist(const uint64_t* keys, uint32_t n, int shift, uint32_t* blockHist, uint32_t numBlocks) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0u;
+    __syncthreads();
+    uint32_t base = blockIdx.x * RS_TILE;
+    for (uint32_t i = threadIdx.x; i < RS_TILE; i += RS_THREADS) {
+        uint32_t idx = base + i;
+        if (idx < n) atomicAdd(&h[uint32_t(keys[idx] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    blockHist[threadIdx.x * numBlocks + blockIdx.x] = h[threadIdx.x];
+}
+__global__ void k_radix_scatter(const uint64_t* keysIn, const uint32_t* valsIn, uint64_t* keysOut, uint32_t* valsOut,
+                                uint32_t n, int shift, const uint32_t* scannedHist, uint32_t numBlocks) {
+    __shared__ uint32_t wh[RS_WARPS][256];
+    uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    for (uint32_t i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wh[0][0])[i] = 0u;
+    __syncthreads();
+    uint32_t chunk = blockIdx.x * RS_TILE + warp * (32u * RS_ROUNDS);
+    for (int r = 0; r < RS_ROUNDS; r++) {
+        uint32_t idx = chunk + r * 32u + lane;
+        bool valid = idx < n;
+        uint32_t digit = valid ? (uint32_t(keysIn[idx] >> shift) & 255u) : 256u;
+        unsigned peers = __match_any_sync(0xffffffffu, digit);
+        if (valid && lane == uint32_t(__ffs(int(peers)) - 1)) wh[warp][digit] += uint32_t(__popc(peers));
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        uint32_t d = threadIdx.x;
+        uint32_t run = scannedHist[d * numBlocks + blockIdx.x];
+        for (int w = 0; w < RS_WARPS; w++) { uint32_t t = wh[w][d]; wh[w][d] = run; run += t; }
+    }
+    __syncthreads();
+    for (int r = 0; r < RS_ROUNDS; r++) {
+        uint32_t idx = chunk + r * 32u + lane;
+        bool valid = idx < n;
+        uint64_t key = valid ? keysIn[idx] : 0ull;
+        uint32_t digit = valid ? (uint32_t(key >> shift) & 255u) : 256u;
+        unsigned peers = __match_any_sync(0xffffffffu, digit);
+        uint32_t rank = uint32_t(__popc(peers & ((1u << lane) - 1u)));
+        if (valid) {
+            uint32_t dst = wh[warp][digit] + rank;
+            keysOut[dst] = key; valsOut[dst] = valsIn[idx];
+        }
+        __syncwarp();
+        if (valid && lane == uint32_t(__ffs(int(peers)) - 1)) wh[warp][digit] += uint32_t(__popc(peers));
+        __syncwarp();
+    }
+}
+uint32_t radixSortTempWords(uint32_t n) { uint32_t nb = gridFor(n, RS_TILE); uint32_t h = 256u * nb; return h + h / 1024u + 4096u; }
+// Sorts (keys, vals) ascending; result ends in keys/vals (8 passes = even number of ping-pongs).
+void radixSort64(uint64_t* keys, uint32_t* vals, uint64_t* keysTmp, uint32_t* valsTmp, uint32_t n, uint32_t* temp, cudaStream_t st, uint64_t* launches) {
+    uint32_t nb = gridFor(n, RS_TILE);
+    uint32_t* hist = temp; uint32_t* scanTmp = temp + 256u * nb;
+    uint64_t* kin = keys; uint32_t* vin = vals; uint64_t* kout = keysTmp; uint32_t* vout = valsTmp;
+    for (int pass = 0; pass < 8; pass++) {
+        int shift = pass * 8;
+        k_radix_hist<<<nb, RS_THREADS, 0, st>>>(kin, n, shift, hist, nb); (*launches)++;
+        exclusiveScanU32(hist, 256u * nb, scanTmp, st, launches);
+        k_radix_scatter<<<nb, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, hist, nb); (*launches)++;
+        uint64_t* tk = kin; kin = kout; kout = tk; uint32_t* tv = vin; vin = vout; vout = tv;
+    }
+}
+
+void launchBuild(const BuildArrays& b, uint64_t* keysTmp, uint32_t* valsTmp, uint32_t* sortTemp, cudaStream_t st, uint64_t* launches) {
+    const unsigned T = 256; unsigned g = gridFor(b.n, T);
+    k_init_build<<<g, T, 0, st>>>(b);
+    k_world_tris<<<g, T, 0, st>>>(b);
+    k_morton<<<g, T, 0, st>>>(b);
+    *launches += 3;
+    radixSort64(b.keys, b.vals, keysTmp, valsTmp, b.n, sortTemp, st, launches);
+    if (b.n >= 2) {
+        k_hierarchy<<<g, T, 0, st>>>(b);
+        k_refit<<<g, T, 0, st>>>(b);
+        k_assign_index<<<g, T, 0, st>>>(b);
+        k_emit_nodes<<<g, T, 0, st>>>(b);
+        *launches += 4;
+    }
+    k_emit_tris<<<g, T, 0, st>>>(b); (*launches)++;
+}
+
+// =============================================================================================
+// Env CDF build — EnvCDF::build (env_cdf.cpp:13-61) in the reference's summation order:
+// one thread per row runs the sequential fp32 prefix sum; one thread runs the marginal.
+// =============================================================================================
+__global__ void k_env_rows(const f4* env, uint32_t W, uint32_t H, float* cond, float* rowTotal) {
+    uint32_t y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= H) return;
+    const float pi = 3.14159265358979323846f;
+    float sinTheta = sinf(pi * (float(y) + 0.5f) / float(H));
+    float* row = cond + size_t(y) * W;
+    float run = 0.0f;
+    for (uint32_t x = 0; x < W; x++) {
+        f4 p = env[size_t(y) * W + x];
+        float lum = __fadd_rn(__fadd_rn(__fmul_rn(0.2126f, p.x), __fmul_rn(0.7152f, p.y)), __fmul_rn(0.0722f, p.z));
+        run = __fadd_rn(run, __fmul_rn(lum, sinTheta));
+        row[x] = run;
+    }
+    if (run > 0.0f) for (uint32_t x = 0; x < W; x++) row[x] = __fdiv_rn(row[x], run);
+    else            for (uint32_t x = 0; x < W; x++) row[x] = float(x + 1) / float(W);
+    rowTotal[y] = run;
+}
+__global__ void k_env_marginal(const float* rowTotal, uint32_t H, float* marg, float* integral) {
+    if (blockIdx.x || threadIdx.x) return;
+    float total = 0.0f;
+    for (uint32_t y = 0; y < H; y++) { total = __fadd_rn(total, rowTotal[y]); marg[y] = total; }
+    *integral = total;
+    if (total > 0.0f) for (uint32_t y = 0; y < H; y++) marg[y] = __fdiv_rn(marg[y], total);
+    else              for (uint32_t y = 0; y < H; y++) marg[y] = float(y + 1) / float(H);
+}
+void launchEnvCdf(const f4* env, uint32_t W, uint32_t H, float* cond, float* marg, float* rowTotal, float* integral, cudaStream_t st, uint64_t* launches) {
+    k_env_rows<<<gridFor(H, 64), 64, 0, st>>>(env, W, H, cond, rowTotal);
+    k_env_marginal<<<1, 32, 0, st>>>(rowTotal, H, marg, integral);
+    *launches += 2;
+}
+__global__ void k_env_sample(SceneDev sc, const float* u12, uint32_t n, f4* dirPdf, float* pdfOfDir) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    f3 d; float p; sampleEnvMap(sc, u12[2 * i], u12[2 * i + 1], d, p);
+    dirPdf[i] = mk4(d, p);
+    if (pdfOfDir) pdfOfDir[i] = pdfEnvMap(sc, d);
+}
+void launchEnvSample(const SceneDev& sc, const float* u12, uint32_t n, f4* dirPdf, float* pdfOfDir, cudaStream_t st, uint64_t* launches) {
+    k_env_sample<<<gridFor(n, 128), 128, 0, st>>>(sc, u12, n, dirPdf, pdfOfDir); (*launches)++;
+}
+
+// =============================================================================================
+// Traversal kernels (persistent, warp-granular dynamic fetch)
+// =============================================================================================
+#define TRACE_THREADS 128
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_closest(SceneDev sc, PathArrays P, uint32_t* work) {
+    const uint32_t n = *P.countIn;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t hits = 0;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(work, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        uint32_t i = base + lane;
+        if (i < n) {
+            uint32_t p = P.queueIn[i];
+            f4 o = P.rayO[p], d = P.rayD[p];
+            ohb_hit h = traceClosest(sc, xyz(o), xyz(d), 0.001f, 10000.0f);
+            reinterpret_cast<float4*>(P.hit)[p] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+            hits += (h.prim != OHB_MISS);
+        }
+    }
+    hits = __reduce_add_sync(0xffffffffu, hits);
+    if (lane == 0 && hits) atomicAdd(P.counters + 3, (unsigned long long)hits);
+}
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_shadow(SceneDev sc, PathArrays P, uint32_t* work) {
+    const uint32_t n = *P.shCount;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(work, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        uint32_t i = base + lane;
+        if (i < n) {
+            f4 o = P.shO[i], d = P.shD[i];
+            if (traceAny(sc, xyz(o), xyz(d), 0.001f, o.w)) {
+                uint32_t tag = __float_as_uint(d.w);
+                f4* pend = (tag & 1u) ? P.pendB : P.pendA;
+                pend[tag >> 1] = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+        }
+    }
+}
+#define SHADE_THREADS 128
+__global__ void __launch_bounds__(SHADE_THREADS) k_raygen(FrameParams fr, PathArrays P, uint32_t total) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    raygenPath(fr, P, p);
+    if (OHB_ST_STAGE(P.meta[p].w) != ST_DONE) { uint32_t q = alloc_slot(P.countIn); P.queueIn[q] = p; }
+}
+__global__ void __launch_bounds__(SHADE_THREADS) k_shade(SceneDev sc, FrameParams fr, PathArrays P) {
+    const uint32_t n = *P.countIn;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t p = P.queueIn[i];
+        if (shadePath(sc, fr, P, p)) { uint32_t q = alloc_slot(P.countOut); P.queueOut[q] = p; }
+    }
+}
+// Between iterations: account the rays just traced, clear the queues that are about to be refilled.
+__global__ void k_advance(PathArrays P, uint32_t* work, int afterRaygen) {
+    if (blockIdx.x || threadIdx.x) return;
+    if (afterRaygen) { P.counters[0] += *P.countIn; }
+    else { P.counters[1] += *P.countIn; P.counters[2] += *P.shCount; *P.countIn = 0u; }
+    *P.shCount = 0u; work[0] = 0u; work[1] = 0u;
+}
+__global__ void k_zero_u32(uint32_t* p, uint32_t n) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = 0u; }
+__global__ void k_film(FrameParams fr, PathArrays P, FilmArrays F) {
+    uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix < P.numPixels) filmPixel(fr, P, F, pix);
+}
+__global__ void k_resolve(f4* accum, uint32_t* ldr, uint32_t n, int sumMode) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    f4 a = accum[i];
+    f3 mean = sumMode ? xyz(a) / fmaxf(a.w, 1.0f) : xyz(a);
+    ldr[i] = tonemapRGBA8(mean);
+}
+
+// One batch of `samplesInBatch` samples for every pixel of the tile: raygen, (1 + 2*maxBounces)
+// wavefront iterations, film.  All launches are asynchronous on `st`.
+void launchOfflineBatch(const SceneDev& sc, const FrameParams& fr, PathArrays P, const FilmArrays& F,
+                        uint32_t* work, int numSMs, cudaStream_t st, uint64_t* launches, TimingHooks* th) {
+    uint32_t total = P.numPixels * P.samplesInBatch;
+    k_zero_u32<<<1, 32, 0, st>>>(P.countIn, 1); k_zero_u32<<<1, 32, 0, st>>>(P.countOut, 1);
+    k_raygen<<<gridFor(total, SHADE_THREADS), SHADE_THREADS, 0, st>>>(fr, P, total);
+    k_advance<<<1, 32, 0, st>>>(P, work, 1);
+    *launches += 4;
+    unsigned traceGrid = unsigned(numSMs) * 8u;
+    unsigned shadeGrid = unsigned(numSMs) * 8u;
+    uint32_t iters = 1u + 2u * fr.maxBounces;
+    for (uint32_t it = 0; it < iters; it++) {
+        if (th) th->begin(0, st);
+        k_trace_closest<<<traceGrid, TRACE_THREADS, 0, st>>>(sc, P, work);
+        if (th) th->end(0, st);
+        if (th) th->begin(1, st);
+        k_shade<<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P);
+        if (th) th->end(1, st);
+        if (th) th->begin(2, st);
+        k_trace_shadow<<<traceGrid, TRACE_THREADS, 0, st>>>(sc, P, work + 1);
+        if (th) th->end(2, st);
+        k_advance<<<1, 32, 0, st>>>(P, work, 0);
+        *launches += 4;
+        // ping-pong the path queues
+        uint32_t* tq = P.queueIn; P.queueIn = P.queueOut; P.queueOut = tq;
+        uint32_t* tc = P.countIn; P.countIn = P.countOut; P.countOut = tc;
+    }
+    if (th) th->begin(3, st);
+    k_film<<<gridFor(P.numPixels, 128), 128, 0, st>>>(fr, P, F); (*launches)++;
+    if (th) th->end(3, st);
+}
+void launchResolve(f4* accum, uint32_t* ldr, uint32_t n, int sumMode, cudaStream_t st, uint64_t* launches) {
+    k_resolve<<<gridFor(n, 256), 256, 0, st>>>(accum, ldr, n, sumMode); (*launches)++;
+}
+
+// ---- parity hooks: trace caller-supplied rays ---------------------------------------------------
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_batch(SceneDev sc, const ohb_ray* rays, uint32_t n, ohb_hit* hits, uint32_t* work) {
+    const uint32_t lane = threadIdx.x & 31u;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(work, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        uint32_t i = base + lane;
+        if (i < n) {
+            ohb_ray r = rays[i];
+            hits[i] = traceClosest(sc, mk3(r.origin[0], r.origin[1], r.origin[2]), mk3(r.dir[0], r.dir[1], r.dir[2]), r.tmin, r.tmax);
+        }
+    }
+}
+__global__ void __launch_bounds__(TRACE_THREADS) k_occluded_batch(SceneDev sc, const ohb_ray* rays, uint32_t n, uint8_t* occ, uint32_t* work) {
+    const uint32_t lane = threadIdx.x & 31u;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(work, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        uint32_t i = base + lane;
+        if (i < n) {
+            ohb_ray r = rays[i];
+            occ[i] = traceAny(sc, mk3(r.origin[0], r.origin[1], r.origin[2]), mk3(r.dir[0], r.dir[1], r.dir[2]), r.tmin, r.tmax) ? 1 : 0;
+        }
+    }
+}
+void launchTraceBatch(const SceneDev& sc, const ohb_ray* rays, uint32_t n, ohb_hit* hits, uint8_t* occ, uint32_t* work, int numSMs, cudaStream_t st, uint64_t* launches) {
+    k_zero_u32<<<1, 32, 0, st>>>(work, 2);
+    if (hits) k_trace_batch<<<numSMs * 8, TRACE_THREADS, 0, st>>>(sc, rays, n, hits, work);
+    else      k_occluded_batch<<<numSMs * 8, TRACE_THREADS, 0, st>>>(sc, rays, n, occ, work);
+    *launches += 2;
+}
+
+}  // namespace ohb

@@ -327,3 +327,171 @@ def cornell_box(actor_order: str = "libstdc++") -> PackedScene:
 
 def cornell_camera() -> Camera:
     return Camera(position=(0.0, 0.0, 13.0), yaw=-90.0, pitch=0.0, fov=38.0)
+
+
+# ------------------------------------------------------------------------------------------
+# Synthetic stand-ins for the assets that cannot travel to the GPU box (configs 2-4).
+# /root/reference (DamagedHelmet.glb, env_outdoor.hdr) does not exist there, so the "Helmet-class"
+# and "2 M-triangle" workloads are seeded procedural scenes of the named triangle counts, texture
+# sets and resolutions.
+# ------------------------------------------------------------------------------------------
+def procedural_env(width: int = 1024, height: int = 512, sun_dir=(0.35, 0.75, 0.55), sun_radiance: float = 4000.0,
+                   seed: int = 7) -> np.ndarray:
+    """Outdoor-HDRI stand-in: sky gradient + small very bright sun + dark ground, RGBA32F [h][w][4].
+
+    Row 0 is theta = 0 (+Y) for the CDF/importance sampling convention (env_sampling.glsl:40-49);
+    the miss shader looks it up with v flipped (quirk Q4) — both use this one image."""
+    rng = np.random.default_rng(seed)
+    v = (np.arange(height, dtype=np.float64) + 0.5) / height
+    u = (np.arange(width, dtype=np.float64) + 0.5) / width
+    theta = v[:, None] * np.pi; phi = (u[None, :] - 0.5) * 2 * np.pi
+    d = np.stack([np.sin(theta) * np.cos(phi), np.cos(theta) * np.ones_like(phi), np.sin(theta) * np.sin(phi)], -1)
+    up = np.clip(d[..., 1], -1, 1)
+    sky = np.where(up[..., None] > 0, (1 - up[..., None]) * np.array([0.9, 0.95, 1.0]) + up[..., None] * np.array([0.25, 0.45, 0.95]),
+                   np.array([0.18, 0.16, 0.14]) * (1 + 0.5 * up[..., None]))
+    clouds = 0.15 * (np.sin(7 * phi + 3 * theta) * np.sin(5 * theta + 1.3) + 1) * (up > 0)
+    sky = sky * (1.0 + clouds[..., None]) * 1.2
+    sd = np.asarray(sun_dir, np.float64); sd /= np.linalg.norm(sd)
+    cosang = d @ sd
+    sun = np.exp(np.minimum((cosang - 1.0) / 2.0e-4, 0.0)) * sun_radiance
+    img = sky + sun[..., None] * np.array([1.0, 0.93, 0.82])
+    img += 0.01 * rng.random(img.shape)
+    out = np.ones((height, width, 4), np.float32); out[..., :3] = img.astype(np.float32)
+    return out
+
+
+def _displaced_sphere(sectors: int, stacks: int, radius: float, amp: float, seed: int):
+    rng = np.random.default_rng(seed)
+    i = np.arange(stacks + 1, dtype=np.float64); j = np.arange(sectors + 1, dtype=np.float64)
+    phi = np.pi * i / stacks; theta = 2 * np.pi * j / sectors
+    sp, cp = np.sin(phi)[:, None], np.cos(phi)[:, None]; st, ct = np.sin(theta)[None, :], np.cos(theta)[None, :]
+    n = np.stack([ct * sp, cp * np.ones_like(ct), st * sp], -1)
+    k = rng.integers(2, 9, size=(6, 3)); ph = rng.random(6) * 6.28
+    disp = sum(np.sin(n @ k[q].astype(np.float64) + ph[q]) for q in range(6)) / 6.0
+    pos = n * (radius * (1.0 + amp * disp))[..., None]
+    pos[:, -1] = pos[:, 0]   # close the seam
+    P = pos.reshape(-1, 3)
+    idx = np.empty((stacks, sectors, 6), np.int64)
+    a = (np.arange(stacks)[:, None] * (sectors + 1) + np.arange(sectors)[None, :]); b = a + sectors + 1
+    idx[..., 0] = a; idx[..., 1] = b; idx[..., 2] = a + 1; idx[..., 3] = b; idx[..., 4] = b + 1; idx[..., 5] = a + 1
+    I = idx.reshape(-1, 3)
+    fn = np.cross(P[I[:, 1]] - P[I[:, 0]], P[I[:, 2]] - P[I[:, 0]])
+    vn = np.zeros_like(P)
+    for c in range(3): np.add.at(vn, I[:, c], fn)
+    # orient outward and normalise (degenerate pole fans fall back to the radial direction)
+    radial = P / np.maximum(np.linalg.norm(P, axis=1, keepdims=True), 1e-12)
+    flip = np.sum(vn * radial, 1) < 0; vn[flip] = -vn[flip]
+    ln = np.linalg.norm(vn, axis=1, keepdims=True)
+    vn = np.where(ln > 1e-12, vn / np.maximum(ln, 1e-12), radial)
+    uv = np.stack([np.broadcast_to(j[None, :] / sectors, (stacks + 1, sectors + 1)), np.broadcast_to(i[:, None] / stacks, (stacks + 1, sectors + 1))], -1).reshape(-1, 2)
+    return P.astype(f32), vn.astype(f32), uv.astype(f32), I.reshape(-1).astype(np.uint32)
+
+
+def _procedural_textures(size: int, seed: int):
+    """albedo (sRGB-ish), tangent-space normal, ORM (AO, rough, metal), emissive — RGBA8 [size][size][4]."""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:size, 0:size].astype(np.float64) / size
+    def noise(fx, fy, p): return 0.5 + 0.5 * np.sin(2 * np.pi * (fx * x + fy * y) + p)
+    n1 = noise(3, 5, 0.3) * noise(7, 2, 1.1); n2 = noise(13, 11, 2.0); n3 = noise(29, 31, 0.7)
+    alb = np.stack([0.55 + 0.4 * n1, 0.45 + 0.35 * n2, 0.35 + 0.3 * n3, np.ones_like(x)], -1)
+    gx = 0.25 * np.cos(2 * np.pi * (13 * x + 11 * y) + 2.0); gy = 0.25 * np.cos(2 * np.pi * (29 * x + 31 * y) + 0.7)
+    nz = np.sqrt(np.maximum(1 - gx * gx - gy * gy, 0.0))
+    nrm = np.stack([0.5 + 0.5 * gx, 0.5 + 0.5 * gy, 0.5 + 0.5 * nz, np.ones_like(x)], -1)
+    panels = ((np.floor(x * 8) + np.floor(y * 8)) % 2)
+    orm = np.stack([0.8 + 0.2 * n1, 0.25 + 0.6 * n2, panels * 0.9 + 0.05, np.ones_like(x)], -1)
+    em = np.zeros((size, size, 4)); em[..., 3] = 1
+    spots = (noise(5, 4, 0.0) > 0.97) & (noise(4, 6, 1.0) > 0.9)
+    em[spots, 0] = 1.0; em[spots, 1] = 0.6; em[spots, 2] = 0.2
+    q = lambda a: np.clip(a * 255.0 + 0.5, 0, 255).astype(np.uint8)
+    _ = rng
+    return q(alb), q(nrm), q(orm), q(em)
+
+
+def helmet_class(ntris: int = 50000, tex_size: int = 2048, env_size=(1024, 512), seed: int = 1) -> PackedScene:
+    """Config 2 stand-in: one ~`ntris` displaced-sphere hero with the helmet's 5-texture PBR material
+    (albedo, normal, ORM, emissive -> also spawns the reference's auto emissive sphere light,
+    light_upload.cpp:183-247), a 2-triangle ground quad, 3 studio sphere lights, outdoor env."""
+    stacks = max(4, int(round(math.sqrt(ntris / 5.0)))); sectors = max(8, ntris // (2 * stacks))
+    P, N, UV, I = _displaced_sphere(sectors, stacks, 1.0, 0.12, seed)
+    alb, nrm, orm, em = _procedural_textures(tex_size, seed)
+    hero = Mesh(positions=P, normals=N, uvs=UV, indices=I, xform=trs((0.0, 1.15, 0.0), (1.0, 1.0, 1.0)), base_color=(1.0, 1.0, 1.0),
+                roughness=1.0, metallic=1.0, albedo_tex=alb, normal_tex=nrm, rough_metal_tex=orm, emissive_tex=em, name="Hero")
+    g = 12.0
+    ground = quad_mesh((-g, 0, -g), (-g, 0, g), (g, 0, g), (g, 0, -g), (0, 1, 0)); ground.base_color = (0.5, 0.5, 0.5); ground.roughness = 0.8; ground.name = "Ground"
+    lights = [Light(position=(4.0, 5.0, 3.0), color=(1.0, 0.95, 0.9), intensity=60.0, radius=0.5),
+              Light(position=(-5.0, 3.0, 2.0), color=(0.6, 0.7, 1.0), intensity=25.0, radius=0.8),
+              Light(position=(0.0, 4.0, -5.0), color=(1.0, 1.0, 1.0), intensity=30.0, radius=0.4)]
+    # auto-generated emissive mesh light (light_upload.cpp:183-247)
+    bright = (em[..., :3].astype(np.float32) / 255.0)
+    lum = bright @ np.array([0.2126, 0.7152, 0.0722], np.float32)
+    mask = lum > 0.05
+    if mask.any() and float(lum[mask].sum()) > 0.1:
+        col = bright[mask].mean(0); inten = min(float(lum[mask].sum()) * 0.1, 20.0)
+        bmin, bmax = P.min(0), P.max(0)
+        center = (bmin + bmax) * 0.5 + np.array([0.0, 1.15, 0.0], np.float32)
+        lights.append(Light(position=tuple(float(v) for v in center), color=tuple(float(v) for v in col), intensity=inten,
+                            radius=float(np.linalg.norm(bmax - bmin) * 0.3)))
+    env = procedural_env(env_size[0], env_size[1])
+    return pack_scene([hero, ground], lights, env=env, name=f"helmet_class_{I.size // 3 + 2}")
+
+
+def helmet_camera() -> Camera:
+    return Camera(position=(0.0, 1.4, 4.2), yaw=-90.0, pitch=-4.0, fov=40.0)
+
+
+def synthetic_2m(nblobs: int = 1000, tris_per_blob: int = 2000, seed: int = 12345, extent: float = 100.0, env_size=(1024, 512),
+                 nmaterials: int = 16) -> PackedScene:
+    """Config 3/4 stand-in: `nblobs` displaced spheres of `tris_per_blob` triangles scattered in an
+    `extent`-metre cube over a 2-triangle ground, 16 materials (rough U[0.05,1], metal in {0,1} p=0.3,
+    albedo U[0.1,0.9]^3), 8 sphere lights, outdoor env.  Flattened to ONE actor with per-triangle material ids."""
+    rng = np.random.default_rng(seed)
+    stacks = max(4, int(round(math.sqrt(tris_per_blob / 3.2)))); sectors = max(8, tris_per_blob // (2 * stacks))
+    P0, N0, UV0, I0 = _displaced_sphere(sectors, stacks, 1.0, 0.15, seed)
+    nv, nt = P0.shape[0], I0.size // 3
+    centers = np.stack([rng.uniform(-extent / 2, extent / 2, nblobs), rng.uniform(1.5, extent * 0.35, nblobs), rng.uniform(-extent / 2, extent / 2, nblobs)], -1)
+    radii = rng.uniform(0.8, 3.0, nblobs)
+    rot = rng.uniform(0, 2 * np.pi, nblobs)
+    c, s = np.cos(rot), np.sin(rot)
+    Px = P0[None, :, 0] * c[:, None] + P0[None, :, 2] * s[:, None]; Pz = -P0[None, :, 0] * s[:, None] + P0[None, :, 2] * c[:, None]
+    Nx = N0[None, :, 0] * c[:, None] + N0[None, :, 2] * s[:, None]; Nz = -N0[None, :, 0] * s[:, None] + N0[None, :, 2] * c[:, None]
+    P = np.stack([Px, np.broadcast_to(P0[None, :, 1], Px.shape), Pz], -1) * radii[:, None, None] + centers[:, None, :]
+    N = np.stack([Nx, np.broadcast_to(N0[None, :, 1], Nx.shape), Nz], -1)
+    I = (I0[None, :].astype(np.int64) + (np.arange(nblobs, dtype=np.int64) * nv)[:, None]).reshape(-1)
+    UV = np.broadcast_to(UV0[None], (nblobs, nv, 2)).reshape(-1, 2)
+    blob_mat = rng.integers(0, nmaterials, nblobs)
+    g = extent * 0.75
+    GP = np.array([(-g, 0, -g), (-g, 0, g), (g, 0, g), (g, 0, -g)], np.float64); GN = np.tile(np.array([0, 1, 0.0]), (4, 1))
+    base = nblobs * nv
+    positions = np.concatenate([P.reshape(-1, 3), GP]).astype(f32); normals3 = np.concatenate([N.reshape(-1, 3), GN]).astype(f32)
+    uvs = np.concatenate([UV, np.zeros((4, 2))]).astype(f32)
+    indices = np.concatenate([I, np.array([0, 1, 2, 0, 2, 3], np.int64) + base]).astype(np.uint32)
+    mat_ids = np.concatenate([np.repeat(blob_mat, nt), np.array([nmaterials, nmaterials])]).astype(np.uint32)
+    nverts = positions.shape[0]
+    pos_rec = np.zeros((nverts, VERTEX_STRIDE // 4), f32); pos_rec[:, 0:3] = positions; pos_rec[:, 6:9] = normals3
+    nrm4 = np.zeros((nverts, 4), f32); nrm4[:, :3] = normals3
+    # materials: 16 random + ground; every material owns a 1x1 solid diffuse layer (quirk Q1)
+    albedo = rng.uniform(0.1, 0.9, (nmaterials, 3)); rough = rng.uniform(0.05, 1.0, nmaterials); metal = (rng.random(nmaterials) < 0.3).astype(np.float64)
+    albedo = np.concatenate([albedo, [[0.45, 0.45, 0.42]]]); rough = np.append(rough, 0.9); metal = np.append(metal, 0.0)
+    nobits = np.array([NO_TEX], "<u4").view("<f4")[0]
+    mc = np.zeros(((nmaterials + 1) * 3, 4), f32); tex = np.zeros((nmaterials + 1, 1, 1, 4), np.uint8)
+    for m in range(nmaterials + 1):
+        mc[m * 3 + 0] = [albedo[m, 0], albedo[m, 1], albedo[m, 2], np.array([m], "<u4").view("<f4")[0]]
+        mc[m * 3 + 1] = [rough[m], metal[m], nobits, nobits]
+        mc[m * 3 + 2] = [nobits, 0, 0, 0]
+        tex[m, 0, 0] = [_linear_to_srgb8(albedo[m, 0]), _linear_to_srgb8(albedo[m, 1]), _linear_to_srgb8(albedo[m, 2]), 255]
+    inst = np.zeros(1, INSTANCE_DTYPE); inst["first_tri"] = 0; inst["tri_count"] = mat_ids.shape[0]; inst["xform"] = trs(); inst["mask"] = 0xFF
+    lights = [Light(position=(float(rng.uniform(-extent / 3, extent / 3)), float(rng.uniform(extent * 0.2, extent * 0.45)), float(rng.uniform(-extent / 3, extent / 3))),
+                    color=tuple(float(v) for v in rng.uniform(0.5, 1.0, 3)), intensity=float(rng.uniform(2000, 6000)), radius=float(rng.uniform(1.0, 3.0))) for _ in range(8)]
+    hdr = bytearray(b"\xff" * 16); hdr[0:4] = struct.pack("<I", len(lights)); hdr[4:8] = struct.pack("<I", nmaterials + 1); hdr[8:12] = struct.pack("<f", 1.0)
+    ssbo = bytes(hdr) + b"".join(l.pack() for l in lights)
+    env = procedural_env(env_size[0], env_size[1])
+    return PackedScene(positions=pos_rec, indices=indices, normals=nrm4, uvs=uvs, mat_ids=mat_ids, instances=inst, mat_colors=mc, textures=tex,
+                       light_ssbo=np.frombuffer(ssbo, np.uint8).copy(), env=env, name=f"synthetic_{mat_ids.shape[0]}")
+
+
+def synthetic_camera(extent: float = 100.0, angle_deg: float = 0.0) -> Camera:
+    """Slow orbit camera of config 3 (0.5 deg / frame)."""
+    r = extent * 0.62; a = math.radians(angle_deg)
+    pos = (r * math.sin(a), extent * 0.22, r * math.cos(a))
+    yaw = math.degrees(math.atan2(-pos[2], -pos[0]))
+    return Camera(position=pos, yaw=yaw, pitch=-12.0, fov=50.0)

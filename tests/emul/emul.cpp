@@ -1,0 +1,217 @@
+// tests/emul/emul.cpp — HOST EMULATOR OF THE CUDA KERNELS.  TEST TOOLING ONLY.
+//
+// The build container has no GPU, so the per-thread code of the product kernels
+// (ohao_engine_b200/csrc/ohb_{bvh,traverse,integrator}.h — the very same source nvcc compiles for
+// sm_100a) is compiled here with g++ and driven by single-threaded loops that mimic the kernel
+// launch sequence of ohb_kernels.cu.  This lets `pytest -m "not gpu"` check the LBVH builder, the
+// traversal and the wavefront state machine against the oracle before any GPU minute is spent.
+// It is NOT a fallback: nothing in ohao_engine_b200/ links or loads this file, it is slow, and the
+// radix sort / scan / queue kernels (device-only code) are replaced by std::stable_sort here.
+#include "../../ohao_engine_b200/csrc/ohb_bvh.h"
+#include "../../ohao_engine_b200/csrc/ohb_integrator.h"
+#include <vector>
+#include <algorithm>
+#include <numeric>
+#include <cstring>
+#include <cmath>
+
+using namespace ohb;
+
+struct EmulScene {
+    std::vector<uint8_t> positions; uint64_t stride = 0; uint32_t nverts = 0, ntris = 0;
+    std::vector<uint32_t> indices, matIds, triInst, active;
+    std::vector<f4> normals, matColors, instXform, instNormalMat, instInv, env;
+    std::vector<f2> uvs;
+    std::vector<uint8_t> tex; uint32_t texW = 0, texH = 0, texLayers = 0;
+    std::vector<GPULight> lights; uint32_t lightCount = 0, envMapTexIdx = 0xFFFFFFFFu; float envIntensity = 1.0f;
+    uint32_t envW = 0, envH = 0; std::vector<float> marg, cond; float envIntegral = 0;
+    std::vector<f4> nodes, tris; int32_t rootRef = 0; uint32_t numActive = 0, numNodes = 0; float sah = 0;
+    SceneDev dev() const {
+        SceneDev s; memset(&s, 0, sizeof(s));
+        s.nodes = nodes.data(); s.tris = tris.data(); s.rootRef = rootRef; s.numTris = numActive;
+        s.indices = indices.data(); s.normals = normals.data(); s.uvs = uvs.data(); s.matIds = matIds.data(); s.triInst = triInst.data();
+        s.instNormalMat = instNormalMat.data(); s.instInv = instInv.data(); s.matColors = matColors.data();
+        s.tex = tex.data(); s.texW = texW; s.texH = texH; s.texLayers = texLayers;
+        s.lights = lights.data(); s.lightCount = lightCount; s.envMapTexIdx = envW ? envMapTexIdx : 0xFFFFFFFFu; s.envIntensity = envIntensity;
+        s.env = envW ? env.data() : nullptr; s.envW = envW; s.envH = envH; s.marg = marg.data(); s.cond = cond.data(); s.envIntegral = envIntegral;
+        return s;
+    }
+};
+
+extern "C" {
+
+struct emul_scene_desc {
+    const void* positions; uint64_t stride_bytes; uint32_t nverts;
+    const uint32_t* indices; uint32_t ntris;
+    const float* normals; const float* uvs; const uint32_t* mat_ids;
+    const ohb_instance* instances; uint32_t ninstances;
+    const float* mat_colors; uint32_t nmaterials;
+    const uint8_t* textures; uint32_t tex_w, tex_h, tex_layers;
+    const void* light_ssbo; uint64_t light_bytes;
+    const float* env; uint32_t env_w, env_h;
+    const float* marg; const float* cond; float env_integral;   // CDFs supplied by the caller (device kernel not emulated)
+};
+
+void* emul_scene_create(const emul_scene_desc* d) {
+    EmulScene* s = new EmulScene();
+    s->stride = d->stride_bytes; s->nverts = d->nverts; s->ntris = d->ntris;
+    s->positions.assign((const uint8_t*)d->positions, (const uint8_t*)d->positions + size_t(d->nverts) * d->stride_bytes);
+    s->indices.assign(d->indices, d->indices + size_t(d->ntris) * 3);
+    s->normals.resize(d->nverts); memcpy(s->normals.data(), d->normals, size_t(d->nverts) * 16);
+    s->uvs.resize(d->nverts); memcpy(s->uvs.data(), d->uvs, size_t(d->nverts) * 8);
+    s->matIds.assign(d->mat_ids, d->mat_ids + d->ntris);
+    s->matColors.resize(size_t(d->nmaterials) * 3); memcpy(s->matColors.data(), d->mat_colors, size_t(d->nmaterials) * 48);
+    if (d->textures && d->tex_layers) { s->texW = d->tex_w; s->texH = d->tex_h; s->texLayers = d->tex_layers; s->tex.assign(d->textures, d->textures + size_t(d->tex_w) * d->tex_h * 4 * d->tex_layers); }
+    if (d->light_ssbo && d->light_bytes >= 16) {
+        const uint8_t* lb = (const uint8_t*)d->light_ssbo;
+        memcpy(&s->lightCount, lb, 4); memcpy(&s->envMapTexIdx, lb + 4, 4); memcpy(&s->envIntensity, lb + 8, 4);
+        s->lights.resize(s->lightCount + 1); memcpy(s->lights.data(), lb + 16, size_t(s->lightCount) * 80);
+    }
+    if (d->env && d->env_w) {
+        s->envW = d->env_w; s->envH = d->env_h; s->env.resize(size_t(d->env_w) * d->env_h); memcpy(s->env.data(), d->env, s->env.size() * 16);
+        s->marg.assign(d->marg, d->marg + d->env_h); s->cond.assign(d->cond, d->cond + size_t(d->env_w) * d->env_h); s->envIntegral = d->env_integral;
+    } else { s->marg.assign(1, 1.0f); s->cond.assign(1, 1.0f); }
+    // ---- same host prologue as ohb_build_accel -------------------------------------------------
+    uint32_t ni = d->ninstances;
+    s->triInst.assign(d->ntris, 0xFFFFFFFFu);
+    s->instXform.resize(size_t(ni) * 3 + 3); s->instNormalMat.resize(size_t(ni) * 3 + 3); s->instInv.resize(size_t(ni) * 3 + 3);
+    for (uint32_t i = 0; i < ni; i++) {
+        const ohb_instance& in = d->instances[i];
+        const float* a = in.xform;
+        memcpy(&s->instXform[size_t(i) * 3], a, 48);
+        float co[3][3];
+        co[0][0] = a[5] * a[10] - a[6] * a[9];  co[0][1] = a[6] * a[8] - a[4] * a[10]; co[0][2] = a[4] * a[9] - a[5] * a[8];
+        co[1][0] = a[2] * a[9] - a[1] * a[10];  co[1][1] = a[0] * a[10] - a[2] * a[8]; co[1][2] = a[1] * a[8] - a[0] * a[9];
+        co[2][0] = a[1] * a[6] - a[2] * a[5];   co[2][1] = a[2] * a[4] - a[0] * a[6];  co[2][2] = a[0] * a[5] - a[1] * a[4];
+        float det = a[0] * co[0][0] + a[1] * co[0][1] + a[2] * co[0][2], id = 1.0f / det;
+        float nm[12], iv[12];
+        for (int r = 0; r < 3; r++) { for (int k = 0; k < 3; k++) nm[r * 4 + k] = co[r][k] * id; nm[r * 4 + 3] = 0; }
+        for (int r = 0; r < 3; r++) { for (int k = 0; k < 3; k++) iv[r * 4 + k] = nm[k * 4 + r]; iv[r * 4 + 3] = -(iv[r * 4] * a[3] + iv[r * 4 + 1] * a[7] + iv[r * 4 + 2] * a[11]); }
+        memcpy(&s->instNormalMat[size_t(i) * 3], nm, 48); memcpy(&s->instInv[size_t(i) * 3], iv, 48);
+        if ((in.mask & 0xFFu) == 0u) continue;
+        for (uint32_t t = in.first_tri; t < in.first_tri + in.tri_count && t < d->ntris; t++) { if (s->triInst[t] == 0xFFFFFFFFu) s->active.push_back(t); s->triInst[t] = i; }
+    }
+    // ---- emulate launchBuild ---------------------------------------------------------------------
+    uint32_t n = uint32_t(s->active.size()); s->numActive = n;
+    if (n == 0) return s;
+    std::vector<f4> wtri(size_t(n) * 3), primLo(n), primHi(n), nodeLo(n), nodeHi(n);
+    std::vector<uint32_t> bounds(6), vals(n), rf(n), rl(n), visit(n, 0), emitCounter(1, 1);
+    std::vector<uint64_t> keys(n);
+    std::vector<int32_t> left(n), right(n), pin(n, -1), pleaf(n, -1), newIndex(n, -1);
+    std::vector<float> sah(2, 0.0f);
+    s->nodes.assign(size_t(n) * 4, f4{0, 0, 0, 0}); s->tris.resize(size_t(n) * 3);
+    BuildArrays b{};
+    b.positions = s->positions.data(); b.posStride = s->stride; b.indices = s->indices.data(); b.triInst = s->triInst.data(); b.instXform = s->instXform.data();
+    b.activeTris = s->active.data(); b.n = n; b.wtri = wtri.data(); b.primLo = primLo.data(); b.primHi = primHi.data(); b.boundsBits = bounds.data();
+    b.keys = keys.data(); b.vals = vals.data(); b.left = left.data(); b.right = right.data(); b.parentInner = pin.data(); b.parentLeaf = pleaf.data();
+    b.rangeFirst = rf.data(); b.rangeLast = rl.data(); b.nodeLo = nodeLo.data(); b.nodeHi = nodeHi.data(); b.visit = visit.data(); b.newIndex = newIndex.data();
+    b.emitCounter = emitCounter.data(); b.sah = sah.data(); b.nodes = s->nodes.data(); b.tris = s->tris.data();
+    bounds[0] = bounds[1] = bounds[2] = 0xFFFFFFFFu; bounds[3] = bounds[4] = bounds[5] = 0u;
+    for (uint32_t i = 0; i < n; i++) buildWorldTri(b, i);
+    for (uint32_t i = 0; i < n; i++) buildMorton(b, i);
+    {   // stand-in for radixSort64 (device-only): stable sort by key
+        std::vector<uint32_t> order(n); std::iota(order.begin(), order.end(), 0u);
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return keys[x] < keys[y]; });
+        std::vector<uint64_t> k2(n); std::vector<uint32_t> v2(n);
+        for (uint32_t i = 0; i < n; i++) { k2[i] = keys[order[i]]; v2[i] = vals[order[i]]; }
+        keys.swap(k2); vals.swap(v2); b.keys = keys.data(); b.vals = vals.data();
+    }
+    if (n >= 2) {
+        for (uint32_t i = 0; i + 1 < n; i++) buildHierarchyNode(b, int(i));
+        for (uint32_t i = 0; i < n; i++) refitFromLeaf(b, i);
+        for (uint32_t i = 0; i + 1 < n; i++) assignNodeIndex(b, int(i));
+        for (uint32_t i = 0; i + 1 < n; i++) emitNode(b, int(i));
+    }
+    for (uint32_t i = 0; i < n; i++) emitTri(b, i);
+    s->rootRef = (n <= OHB_MAX_LEAF) ? makeLeafRef(0u, n) : 0;
+    s->numNodes = (n <= OHB_MAX_LEAF) ? 0u : emitCounter[0];
+    float ra = n >= 2 ? boxArea(xyz(nodeLo[0]), xyz(nodeHi[0])) : 0.0f;
+    s->sah = ra > 0 ? (sah[0] + sah[1]) / ra : float(n);
+    return s;
+}
+void emul_scene_destroy(void* h) { delete (EmulScene*)h; }
+void emul_accel_stats(void* h, uint32_t* numNodes, float* sah) { EmulScene* s = (EmulScene*)h; *numNodes = s->numNodes; *sah = s->sah; }
+
+void emul_trace_batch(void* h, const ohb_ray* rays, uint32_t n, ohb_hit* hits) {
+    SceneDev sc = ((EmulScene*)h)->dev();
+    for (uint32_t i = 0; i < n; i++)
+        hits[i] = traceClosest(sc, mk3(rays[i].origin[0], rays[i].origin[1], rays[i].origin[2]), mk3(rays[i].dir[0], rays[i].dir[1], rays[i].dir[2]), rays[i].tmin, rays[i].tmax);
+}
+void emul_occluded_batch(void* h, const ohb_ray* rays, uint32_t n, uint8_t* occ) {
+    SceneDev sc = ((EmulScene*)h)->dev();
+    for (uint32_t i = 0; i < n; i++)
+        occ[i] = traceAny(sc, mk3(rays[i].origin[0], rays[i].origin[1], rays[i].origin[2]), mk3(rays[i].dir[0], rays[i].dir[1], rays[i].dir[2]), rays[i].tmin, rays[i].tmax);
+}
+void emul_env_sample_batch(void* h, const float* u12, uint32_t n, float* dirPdf, float* pdfOfDir) {
+    SceneDev sc = ((EmulScene*)h)->dev();
+    for (uint32_t i = 0; i < n; i++) { f3 d; float p; sampleEnvMap(sc, u12[2 * i], u12[2 * i + 1], d, p); dirPdf[4 * i] = d.x; dirPdf[4 * i + 1] = d.y; dirPdf[4 * i + 2] = d.z; dirPdf[4 * i + 3] = p; pdfOfDir[i] = pdfEnvMap(sc, d); }
+}
+
+struct emul_render_args {
+    float view[16], proj[16]; uint32_t width, height, first_sample_index, history_count, nsamples;
+    uint32_t tile_x, tile_y, tile_w, tile_h; ohb_settings settings;
+    float* accum; uint8_t* ldr; float* albedo; float* normal; float* sample_dump; uint64_t counters[4];
+};
+static void inv4(const float* m, float* out) {
+    double a[4][8];
+    for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) { a[r][c] = m[c * 4 + r]; a[r][c + 4] = r == c; }
+    for (int i = 0; i < 4; i++) {
+        int p = i; for (int r = i + 1; r < 4; r++) if (fabs(a[r][i]) > fabs(a[p][i])) p = r;
+        for (int c = 0; c < 8; c++) std::swap(a[i][c], a[p][c]);
+        double d = a[i][i]; for (int c = 0; c < 8; c++) a[i][c] /= d;
+        for (int r = 0; r < 4; r++) if (r != i) { double f = a[r][i]; for (int c = 0; c < 8; c++) a[r][c] -= f * a[i][c]; }
+    }
+    for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) out[c * 4 + r] = float(a[r][c + 4]);
+}
+// Mimics ohb_render + launchOfflineBatch with one batch per call.
+int emul_render_offline(void* h, emul_render_args* a) {
+    EmulScene* es = (EmulScene*)h; SceneDev sc = es->dev();
+    float iv[16], ip[16]; inv4(a->view, iv); inv4(a->proj, ip);
+    FrameParams fr{};
+    fr.camPos = mk3(iv[12], iv[13], iv[14]); fr.fwd = mk3(-iv[8], -iv[9], -iv[10]); fr.right = mk3(iv[0], iv[1], iv[2]); fr.up = mk3(iv[4], iv[5], iv[6]);
+    fr.tanY = fabsf(ip[5]); fr.tanX = fr.tanY * (float(a->width) / float(a->height));
+    fr.W = a->width; fr.H = a->height; fr.maxBounces = a->settings.max_bounces & 0xFFFFu; fr.flags = a->settings.flags;
+    bool envOn = es->envW && es->envMapTexIdx != 0xFFFFFFFFu;
+    fr.envW = envOn ? es->envW : 0u; fr.envH = envOn ? float(es->envH) : 0.0f;
+    fr.fireflyClamp = a->settings.firefly_clamp_lum; fr.sss = a->settings.subsurface_strength; fr.aniso = a->settings.anisotropy_strength; fr.anisoRot = a->settings.anisotropy_rotation;
+    fr.samplerType = a->settings.sampler_type;
+    fr.tileX = a->tile_x; fr.tileY = a->tile_y; fr.tileW = a->tile_w ? a->tile_w : a->width; fr.tileH = a->tile_h ? a->tile_h : a->height;
+    uint32_t tilesX = (fr.tileW + 7u) / 8u, tilesY = (fr.tileH + 3u) / 4u, numPixels = tilesX * tilesY * 32u;
+    uint32_t total = numPixels * a->nsamples;
+    std::vector<f4> rayO(total), rayD(total), thr(total), rad(total), pendA(total), pendB(total), fh0(total), fh1(total), fh2(total), fh3(total), shO(size_t(total) * 2), shD(size_t(total) * 2);
+    std::vector<ohb_hit> hit(total); std::vector<u4> meta(total); std::vector<uint32_t> qa(total), qb(total);
+    uint32_t small[4] = {0, 0, 0, 0}; unsigned long long counters[8] = {0};
+    size_t npx = size_t(a->width) * a->height;
+    std::vector<f4> albedo(npx), normal(npx), accum(npx); std::vector<uint32_t> ldr(npx);
+    memcpy(accum.data(), a->accum, npx * 16);
+    PathArrays P{};
+    P.rayO = rayO.data(); P.rayD = rayD.data(); P.hit = hit.data(); P.thr = thr.data(); P.rad = rad.data(); P.pendA = pendA.data(); P.pendB = pendB.data(); P.meta = meta.data();
+    P.fh0 = fh0.data(); P.fh1 = fh1.data(); P.fh2 = fh2.data(); P.fh3 = fh3.data(); P.shO = shO.data(); P.shD = shD.data();
+    P.queueIn = qa.data(); P.queueOut = qb.data(); P.countIn = &small[0]; P.countOut = &small[1]; P.shCount = &small[2]; P.counters = counters;
+    P.albedoAOV = albedo.data(); P.normalAOV = normal.data(); P.numPixels = numPixels; P.samplesInBatch = a->nsamples; P.firstSampleIndex = a->first_sample_index;
+    for (uint32_t p = 0; p < total; p++) { raygenPath(fr, P, p); if (OHB_ST_STAGE(P.meta[p].w) != ST_DONE) P.queueIn[(*P.countIn)++] = p; }
+    counters[0] += *P.countIn;
+    uint32_t iters = 1u + 2u * fr.maxBounces;
+    for (uint32_t it = 0; it < iters; it++) {
+        uint32_t n = *P.countIn;
+        for (uint32_t i = 0; i < n; i++) { uint32_t p = P.queueIn[i]; P.hit[p] = traceClosest(sc, xyz(P.rayO[p]), xyz(P.rayD[p]), 0.001f, 10000.0f); counters[3] += P.hit[p].prim != OHB_MISS; }
+        for (uint32_t i = 0; i < n; i++) { uint32_t p = P.queueIn[i]; if (shadePath(sc, fr, P, p)) P.queueOut[(*P.countOut)++] = p; }
+        uint32_t ns = *P.shCount;
+        for (uint32_t i = 0; i < ns; i++) {
+            f4 o = P.shO[i], d = P.shD[i];
+            if (traceAny(sc, xyz(o), xyz(d), 0.001f, o.w)) { uint32_t tag = f2u(d.w); ((tag & 1u) ? P.pendB : P.pendA)[tag >> 1] = mk4(0, 0, 0, 0); }
+        }
+        counters[1] += n; counters[2] += ns; *P.countIn = 0; *P.shCount = 0;
+        std::swap(P.queueIn, P.queueOut); std::swap(P.countIn, P.countOut);
+    }
+    FilmArrays F{}; F.accum = accum.data(); F.ldr = ldr.data(); F.sampleDump = a->sample_dump; F.historyCount = a->history_count; F.sumMode = 0;
+    for (uint32_t pix = 0; pix < numPixels; pix++) filmPixel(fr, P, F, pix);
+    memcpy(a->accum, accum.data(), npx * 16);
+    if (a->ldr) memcpy(a->ldr, ldr.data(), npx * 4);
+    if (a->albedo) memcpy(a->albedo, albedo.data(), npx * 16);
+    if (a->normal) memcpy(a->normal, normal.data(), npx * 16);
+    for (int i = 0; i < 4; i++) a->counters[i] = counters[i];
+    return 0;
+}
+
+}  // extern "C"

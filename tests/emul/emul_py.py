@@ -1,0 +1,95 @@
+"""ctypes binding of tests/emul/libemul.so — host emulator of the CUDA kernels (TEST TOOLING ONLY)."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+from oracle import oracle_py as O
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class SceneDesc(C.Structure):
+    _fields_ = O.SceneDesc._fields_ + [("marg", C.c_void_p), ("cond", C.c_void_p), ("env_integral", C.c_float)]
+
+
+class RenderArgs(C.Structure):
+    _fields_ = [("view", C.c_float * 16), ("proj", C.c_float * 16), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("first_sample_index", C.c_uint32), ("history_count", C.c_uint32), ("nsamples", C.c_uint32),
+                ("tile_x", C.c_uint32), ("tile_y", C.c_uint32), ("tile_w", C.c_uint32), ("tile_h", C.c_uint32),
+                ("settings", O.Settings),
+                ("accum", C.c_void_p), ("ldr", C.c_void_p), ("albedo", C.c_void_p), ("normal", C.c_void_p), ("sample_dump", C.c_void_p),
+                ("counters", C.c_uint64 * 4)]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        subprocess.check_call(["make", "-C", _HERE, "libemul.so"], stdout=subprocess.DEVNULL)
+        _LIB = C.CDLL(os.path.join(_HERE, "libemul.so"))
+        _LIB.emul_scene_create.restype = C.c_void_p
+        _LIB.emul_scene_create.argtypes = [C.POINTER(SceneDesc)]
+        _LIB.emul_scene_destroy.argtypes = [C.c_void_p]
+        _LIB.emul_trace_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        _LIB.emul_occluded_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        _LIB.emul_env_sample_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        _LIB.emul_render_offline.argtypes = [C.c_void_p, C.POINTER(RenderArgs)]
+        _LIB.emul_accel_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
+    return _LIB
+
+
+_p = O._p
+
+
+class EmulScene:
+    def __init__(self, ps):
+        self.ps = ps
+        d = SceneDesc()
+        k = self._keep = [np.ascontiguousarray(x) for x in (ps.positions, ps.indices, ps.normals, ps.uvs, ps.mat_ids, ps.instances,
+                                                            ps.mat_colors, ps.textures, ps.light_ssbo)]
+        d.positions = _p(k[0]); d.stride_bytes = k[0].strides[0]; d.nverts = ps.nverts
+        d.indices = _p(k[1]); d.ntris = ps.ntris; d.normals = _p(k[2]); d.uvs = _p(k[3]); d.mat_ids = _p(k[4])
+        d.instances = _p(k[5]); d.ninstances = len(k[5]); d.mat_colors = _p(k[6]); d.nmaterials = ps.nmaterials
+        d.textures = _p(k[7]); d.tex_layers, d.tex_h, d.tex_w = k[7].shape[0], k[7].shape[1], k[7].shape[2]
+        d.light_ssbo = _p(k[8]); d.light_bytes = k[8].nbytes
+        if ps.env is not None:
+            self._env = np.ascontiguousarray(ps.env, np.float32)
+            self._marg, self._cond, integral = O.env_cdf(self._env)   # the device CDF kernel is not emulated
+            d.env = _p(self._env); d.env_h, d.env_w = self._env.shape[:2]
+            d.marg = _p(self._marg); d.cond = _p(self._cond); d.env_integral = integral
+        self.h = lib().emul_scene_create(C.byref(d))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().emul_scene_destroy(self.h); self.h = None
+
+    def stats(self):
+        n = C.c_uint32(); s = C.c_float(); lib().emul_accel_stats(self.h, C.byref(n), C.byref(s)); return n.value, s.value
+
+    def trace(self, rays):
+        rays = np.ascontiguousarray(rays, O.RAY_DTYPE); hits = np.zeros(len(rays), O.HIT_DTYPE)
+        lib().emul_trace_batch(self.h, _p(rays), len(rays), _p(hits)); return hits
+
+    def occluded(self, rays):
+        rays = np.ascontiguousarray(rays, O.RAY_DTYPE); occ = np.zeros(len(rays), np.uint8)
+        lib().emul_occluded_batch(self.h, _p(rays), len(rays), _p(occ)); return occ
+
+    def env_sample(self, u12):
+        u = np.ascontiguousarray(u12, np.float32); n = len(u); dp = np.zeros((n, 4), np.float32); pd = np.zeros(n, np.float32)
+        lib().emul_env_sample_batch(self.h, _p(u), n, _p(dp), _p(pd)); return dp, pd
+
+    def render_offline(self, view, proj, width, height, nsamples, first_sample=0, history=0, accum=None, settings=None, tile=None, dump=False):
+        a = RenderArgs()
+        a.view[:] = [float(x) for x in view]; a.proj[:] = [float(x) for x in proj]
+        a.width, a.height, a.first_sample_index, a.history_count, a.nsamples = width, height, first_sample, history, nsamples
+        if tile: a.tile_x, a.tile_y, a.tile_w, a.tile_h = tile
+        a.settings = settings or O.offline_settings()
+        if accum is None: accum = np.zeros((height, width, 4), np.float32)
+        ldr = np.zeros((height, width, 4), np.uint8); alb = np.zeros((height, width, 4), np.float32); nrm = np.zeros((height, width, 4), np.float32)
+        sd = np.zeros((nsamples, height, width, 4), np.float32) if dump else None
+        a.accum, a.ldr, a.albedo, a.normal, a.sample_dump = _p(accum), _p(ldr), _p(alb), _p(nrm), _p(sd)
+        lib().emul_render_offline(self.h, C.byref(a))
+        c = a.counters
+        return dict(accum=accum, ldr=ldr, albedo=alb, normal=nrm, samples=sd,
+                    counters=dict(samples=c[0], closest_rays=c[1], shadow_rays=c[2], closest_hits=c[3]))
