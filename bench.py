@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py — Msamples/s of the path-tracing hot path at 1920x1080 (BASELINE.json metric).
+
+One "step" = one ohb_render() of `--spp-step` samples per pixel over the whole 1080p frame of the
+workload (default: configs[1], the Helmet-class ~50K-triangle scene under an HDRI with env importance
+sampling + MIS, offline integrator; 16 steps x 16 spp = its 256 spp).  A *sample* is one full OHAO path
+tree.  `value` is device-timed with the scene resident in HBM; `e2e` goes through the
+C ABI with host buffers in and the RGBA8 image out every step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload helmet|cornell|synthetic2m]
+  python bench.py --impl reference      # the CPU restatement of the reference shaders on host cores
+
+Multi-GPU (torchrun, one rank per GPU): the scene is replicated, rank g renders its own contiguous block
+of sample indices in sum mode (weak scaling: per-GPU work fixed), and ONE NCCL reduce of the RGBA32F
+accumulation image to rank 0 + resolve closes the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+W, H = 1920, 1080
+METRIC = "Msamples/s at 1920x1080"
+
+
+def b_ray(ntris: int) -> int:
+    """Algorithmic bytes per ray query: ray in 32 + hit out 16 + 64 B x D(N) nodes + 4 x 48 B triangles."""
+    d = math.ceil(math.log2(max(ntris, 4) / 4)) + 1
+    return 32 + 16 + 64 * d + 48 * 4
+
+
+def make_workload(name: str):
+    from ohao_engine_b200 import scenes
+    if name == "helmet":
+        return scenes.helmet_class(), scenes.helmet_camera(), "helmet-class 50K tris + 5x2048^2 textures + 1024x512 HDRI, env IS + MIS, offline, 4 bounces"
+    if name == "cornell":
+        return scenes.cornell_box(), scenes.cornell_camera(), "cornell_box 2058 tris, 12 sphere lights, offline, 4 bounces"
+    if name == "synthetic2m":
+        return scenes.synthetic_2m(), scenes.synthetic_camera(), "synthetic 2M tris, 8 lights + HDRI, offline, 4 bounces"
+    raise SystemExit(f"unknown workload {name}")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(gpu_index)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        try: self.p.wait(timeout=5)
+        except Exception: self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons, pw = [], [], set(), []
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 8: continue
+            try: sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+            except ValueError: continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[4:8]):
+                if v.lower().startswith("active"): reasons.add(name)
+        try: os.unlink(self.f.name)
+        except OSError: pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_oracle_rate(ps, cam, seconds: float, nthreads: int):
+    """Msamples/s of the CPU restatement (oracle) on full 1080p frames of 1 spp, for about `seconds`."""
+    from oracle import oracle_py as O
+    osc = O.OracleScene(ps)
+    v, p = cam.view(), cam.proj(W, H)
+    acc = np.zeros((H, W, 4), np.float32)
+    t0 = time.perf_counter(); n = 0
+    while True:
+        osc.render_offline(v, p, W, H, 1, first_sample=n, history=n, accum=acc, nthreads=nthreads, want_ldr=False)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt >= seconds or n >= 64: break
+    return W * H * n / dt / 1e6, n, dt
+
+
+def run_reference(args, rank: int):
+    """The reference arm: the reference's own implementation cannot be built here or on the GPU box (Vulkan RT
+    pipeline + GLSL, no Vulkan SDK/ICD/glslc — DESIGN.md), so this times the CPU restatement of its shaders
+    (oracle/, kind "port") with every host thread on the same workload; each step = 1 spp over the 1080p frame."""
+    if rank != 0:
+        return
+    from oracle import oracle_py as O
+    ps, cam, desc = make_workload(args.workload)
+    osc = O.OracleScene(ps)
+    cores = os.cpu_count() or 1
+    v, p = cam.view(), cam.proj(W, H)
+    acc = np.zeros((H, W, 4), np.float32)
+    idx = 0
+    for _ in range(args.warmup):
+        osc.render_offline(v, p, W, H, 1, first_sample=idx, history=idx, accum=acc, nthreads=cores, want_ldr=False); idx += 1
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        osc.render_offline(v, p, W, H, 1, first_sample=idx, history=idx, accum=acc, nthreads=cores, want_ldr=True); idx += 1
+    dt = time.perf_counter() - t0
+    val = W * H * args.steps / dt / 1e6
+    sample = f"{args.steps} steps x 1 spp x 1920x1080 of the same scene (our arm: {args.spp_step} spp per step)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "resolution": [W, H], "spp_per_step": 1, "integrator": "offline"},
+        "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="helmet", choices=["helmet", "cornell", "synthetic2m"])
+    ap.add_argument("--spp-step", type=int, default=16, help="samples per pixel per step")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bounded CPU-baseline sample (rank 0, N=1 only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from ohao_engine_b200 import binding as B
+    ps, cam, desc = make_workload(args.workload)
+    r = B.Renderer(W, H, device=local)
+    r.set_scene(ps)
+    st = r.accel_stats()
+    v, p = cam.view(), cam.proj(W, H)
+    spp = args.spp_step
+    block = (args.warmup + args.steps) * spp          # sample indices per rank: contiguous block, rank-major
+    if world > 1:
+        r.set_accum_mode(True)
+    r.set_render_seed(rank * block)
+
+    accum_t = None
+    if world > 1:
+        ptr, nbytes = r.accum_dev_ptr()
+
+        class _Alias:      # zero-copy view of the library's accumulation image for the NCCL reduce
+            __cuda_array_interface__ = {"shape": (H * W * 4,), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+        accum_t = torch.as_tensor(_Alias(), device=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        r.synchronize(); torch.cuda.synchronize()
+
+    # ---- warm-up -----------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        r.render(v, p, spp)
+    barrier()
+
+    # ---- timed region: device-resident ---------------------------------------------------------------
+    r.reset_counters(); r.enable_timing(True)
+    clocks = ClockSampler(local) if rank == 0 else None
+    barrier()
+    r.timer_start()
+    for _ in range(args.steps):
+        r.render(v, p, spp)
+    if world > 1:
+        r.synchronize()
+        dist.reduce(accum_t, dst=0, op=dist.ReduceOp.SUM)       # NCCL over NVLink: one reduce per image
+        torch.cuda.synchronize()
+        if rank == 0: r.resolve()
+    ms = r.timer_stop()
+    barrier()
+    clk = clocks.stop() if clocks else None
+    cnt = r.counters(); tim = r.timing()
+    r.enable_timing(False)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        agg = torch.tensor([cnt["samples"], cnt["closest_rays"], cnt["shadow_rays"], cnt["closest_hits"], cnt["kernel_launches"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+        tot = dict(zip(("samples", "closest_rays", "shadow_rays", "closest_hits", "kernel_launches"), [int(x) for x in agg.tolist()]))
+    else:
+        tot = cnt
+    samples_total = W * H * spp * args.steps * world
+    value = samples_total / (ms * 1e-3) / 1e6
+
+    # ---- e2e: through the C ABI with host buffers, H2D of the step's inputs + D2H of its image every step ----
+    mat = np.ascontiguousarray(ps.mat_colors, np.float32); lights = np.ascontiguousarray(ps.light_ssbo, np.uint8)
+    ldr = np.empty((H, W, 4), np.uint8)
+    h2d = mat.nbytes + lights.nbytes + 128; d2h = ldr.nbytes
+    r.reset_accumulation()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r.update_rt_material_params(mat); r.update_rt_light_params(lights)      # updateRTMaterialParams / updateRTLightParams
+        r.render(v, p, spp)
+        if world > 1: r.resolve()
+        r.get_pixels(ldr)                                                          # getPixelSpan(): blocking readback
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
+    e2e_val = samples_total / e2e_s / 1e6
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        br = b_ray(st.num_tris)
+        tc = tim["trace_closest"]; nl = max(tc["launches"], 1)
+        rays_per_launch = cnt["closest_rays"] / nl
+        avg_ms = tc["ms"] / nl
+        achieved = rays_per_launch * br / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+        kernel_ms = {k: round(x["ms"], 3) for k, x in tim.items()}
+        out = {
+            "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "resolution": [W, H], "spp_per_step": spp, "integrator": "offline", "tris": int(st.num_tris),
+                       "bvh_nodes": int(st.num_nodes), "bvh_sah": round(float(st.sah_cost), 2), "bvh_build_ms": round(float(st.build_ms), 3),
+                       "parallelism": f"spp-shard x{world}" if world > 1 else "single GPU",
+                       "l2": "path-state working set %.1f GB per step >> 126 MB L2 (no explicit flush)" % (W * H * min(spp, 4) * 288 / 1e9)},
+            "rays": {"per_sample": (tot["closest_rays"] + tot["shadow_rays"]) / max(tot["samples"], 1),
+                     "closest_per_sample": tot["closest_rays"] / max(tot["samples"], 1), "shadow_per_sample": tot["shadow_rays"] / max(tot["samples"], 1),
+                     "mrays_per_s": (tot["closest_rays"] + tot["shadow_rays"]) / (ms * 1e-3) / 1e6,
+                     "gsamples_sbe_per_s": (tot["closest_rays"] + tot["shadow_rays"]) / (ms * 1e-3) / 2e9},
+            "kernel_ms": kernel_ms,
+            "roofline": {"bound": "hbm", "kernel": "k_trace_closest", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "bytes_per_ray": br, "rays_per_launch": rays_per_launch, "avg_launch_ms": avg_ms,
+                         "share_of_step": tc["ms"] / ms if ms > 0 else None},
+            "e2e": {"value": e2e_val, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(cnt["kernel_launches"]),
+            "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            cv, nfr, dt = cpu_oracle_rate(ps, cam, args.cpu_seconds, cores)
+            out["cpu_baseline"] = {"value": cv, "unit": "Msamples/s", "cores": cores, "kind": "port",
+                                   "sample": f"{nfr} x 1 spp x 1920x1080 frames of the same scene in {dt:.1f} s (CPU restatement of the reference shaders, all host threads)"}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -184,6 +184,10 @@ int ohb_enable_timing(ohb_ctx*, int enable);
 /* Per-category device time and launch count: [0] closest-hit traversal, [1] shading,
  * [2] any-hit traversal, [3] film. */
 int ohb_get_timing_detail(ohb_ctx*, float ms[4], uint64_t launches[4]);
+/* Whole-region device timer: two CUDA events recorded on the context's stream (the stream every
+ * kernel of this context is launched on).  ohb_timer_stop synchronises and returns the elapsed ms. */
+int ohb_timer_start(ohb_ctx*);
+int ohb_timer_stop(ohb_ctx*, float* elapsed_ms);
 
 #ifdef __cplusplus
 }

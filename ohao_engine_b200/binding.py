@@ -80,6 +80,8 @@ ABI = {
     "ohb_get_timing": (_I, [_VP, C.POINTER(_F), C.POINTER(_F), C.POINTER(_F)]),
     "ohb_get_timing_detail": (_I, [_VP, C.POINTER(_F * 4), C.POINTER(C.c_uint64 * 4)]),
     "ohb_enable_timing": (_I, [_VP, _I]),
+    "ohb_timer_start": (_I, [_VP]),
+    "ohb_timer_stop": (_I, [_VP, C.POINTER(_F)]),
 }
 
 _LIB: Optional[C.CDLL] = None
@@ -248,6 +250,11 @@ class Renderer:
 
     def reset_counters(self): self.lib.ohb_reset_counters(self.h)
     def enable_timing(self, on: bool = True): self._ck(self.lib.ohb_enable_timing(self.h, int(on)), "ohb_enable_timing")
+
+    def timer_start(self): self._ck(self.lib.ohb_timer_start(self.h), "ohb_timer_start")
+
+    def timer_stop(self) -> float:
+        ms = C.c_float(); self._ck(self.lib.ohb_timer_stop(self.h, C.byref(ms)), "ohb_timer_stop"); return float(ms.value)
 
     def timing(self) -> dict:
         ms = (C.c_float * 4)(); cnt = (C.c_uint64 * 4)()

@@ -93,7 +93,7 @@ struct ohb_ctx {
     // hooks
     DevBuf hookRays, hookOut, hookAux;
     TimingHooks timing; bool timingOn = false;
-    cudaEvent_t evA = nullptr, evB = nullptr;
+    cudaEvent_t evA = nullptr, evB = nullptr, evT0 = nullptr, evT1 = nullptr;
 };
 
 #define OHB_FAIL(ctx, msg) do { (ctx)->err = (msg); return 1; } while (0)
@@ -143,7 +143,7 @@ ohb_ctx* ohb_create(int device_ordinal, uint32_t width, uint32_t height, int pro
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess || (e = uploadConstants()) != cudaSuccess) {
         g_createError = cudaGetErrorString(e); delete c; return nullptr;
     }
-    cudaEventCreate(&c->evA); cudaEventCreate(&c->evB);
+    cudaEventCreate(&c->evA); cudaEventCreate(&c->evB); cudaEventCreate(&c->evT0); cudaEventCreate(&c->evT1);
     defaultSettings(c);
     if (ensureFilm(c) || clearFilm(c) || c->smallCounters.reserve(64 * 4) != cudaSuccess || c->devCounters.reserve(8 * 8) != cudaSuccess) {
         g_createError = c->err.empty() ? "allocation failed" : c->err; ohb_destroy(c); return nullptr;
@@ -166,7 +166,10 @@ void ohb_destroy(ohb_ctx* c) {
                      &c->pendA, &c->pendB, &c->meta, &c->fh0, &c->fh1, &c->fh2, &c->fh3, &c->shO, &c->shD, &c->queueA, &c->queueB, &c->smallCounters, &c->devCounters,
                      &c->accum, &c->ldr, &c->albedoAOV, &c->normalAOV, &c->sampleDump, &c->hookRays, &c->hookOut, &c->hookAux};
     for (DevBuf* b : all) b->release();
-    if (c->evA) cudaEventDestroy(c->evA); if (c->evB) cudaEventDestroy(c->evB);
+    if (c->evA) cudaEventDestroy(c->evA);
+    if (c->evB) cudaEventDestroy(c->evB);
+    if (c->evT0) cudaEventDestroy(c->evT0);
+    if (c->evT1) cudaEventDestroy(c->evT1);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -571,6 +574,21 @@ int ohb_get_timing_detail(ohb_ctx* c, float ms[4], uint64_t launches[4]) {
     CU(c, cudaStreamSynchronize(c->stream));
     c->timing.collect();
     for (int i = 0; i < 4; i++) { ms[i] = float(c->timing.ms[i]); launches[i] = c->timing.count[i]; }
+    return 0;
+}
+
+int ohb_timer_start(ohb_ctx* c) {
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    CU(c, cudaEventRecord(c->evT0, c->stream));
+    return 0;
+}
+int ohb_timer_stop(ohb_ctx* c, float* ms) {
+    if (!c || !ms) return 1;
+    cudaSetDevice(c->device);
+    CU(c, cudaEventRecord(c->evT1, c->stream));
+    CU(c, cudaEventSynchronize(c->evT1));
+    CU(c, cudaEventElapsedTime(ms, c->evT0, c->evT1));
     return 0;
 }
 
