@@ -247,11 +247,20 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         br = b_ray(st.num_tris)
-        tc = tim["trace_closest"]; nl = max(tc["launches"], 1)
-        rays_per_launch = cnt["closest_rays"] / nl
-        avg_ms = tc["ms"] / nl
-        achieved = rays_per_launch * br / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
-        kernel_ms = {k: round(x["ms"], 3) for k, x in tim.items()}
+        # algorithmic bytes per unit of each kernel (DESIGN.md "Kernels"): rays x B_ray(N) for the traversal kernels,
+        # 248 B per path for k_surface (ray 32 + hit 16 + 136 B surface gather + 64 B payload), 304 B per path for k_bounce
+        units = {"trace_closest": (cnt["closest_rays"], br), "trace_shadow": (cnt["shadow_rays"], br),
+                 "surface": (cnt["closest_rays"], 248), "bounce": (cnt["closest_rays"], 304), "film": (cnt["samples"], 36)}
+        kern = {}
+        for k, x in tim.items():
+            if x["launches"] == 0: continue
+            nunits, bpu = units[k]
+            avg = x["ms"] / x["launches"]
+            ach = (nunits / x["launches"]) * bpu / (avg * 1e-3) / 1e9 if avg > 0 else 0.0
+            kern[k] = {"ms": round(x["ms"], 3), "launches": x["launches"], "share_of_step": round(x["ms"] / ms, 4), "bytes_per_unit": bpu,
+                       "units_per_launch": nunits / x["launches"], "avg_launch_ms": avg, "achieved_gbs": ach, "frac": ach / peak}
+        dom = max(kern, key=lambda k: kern[k]["ms"])
+        dk = kern[dom]
         out = {
             "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -263,10 +272,10 @@ def main():
                      "closest_per_sample": tot["closest_rays"] / max(tot["samples"], 1), "shadow_per_sample": tot["shadow_rays"] / max(tot["samples"], 1),
                      "mrays_per_s": (tot["closest_rays"] + tot["shadow_rays"]) / (ms * 1e-3) / 1e6,
                      "gsamples_sbe_per_s": (tot["closest_rays"] + tot["shadow_rays"]) / (ms * 1e-3) / 2e9},
-            "kernel_ms": kernel_ms,
-            "roofline": {"bound": "hbm", "kernel": "k_trace_closest", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "bytes_per_ray": br, "rays_per_launch": rays_per_launch, "avg_launch_ms": avg_ms,
-                         "share_of_step": tc["ms"] / ms if ms > 0 else None},
+            "kernels": kern,
+            "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": dk["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dk["frac"],
+                         "traffic": None, "peak_source": peak_src, "bytes_per_unit": dk["bytes_per_unit"], "units_per_launch": dk["units_per_launch"],
+                         "avg_launch_ms": dk["avg_launch_ms"], "share_of_step": dk["share_of_step"]},
             "e2e": {"value": e2e_val, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(cnt["kernel_launches"]),
             "clocks": clk,

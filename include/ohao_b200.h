@@ -137,6 +137,8 @@ int ohb_get_env_cdf(ohb_ctx*, float* marginal_h, float* conditional_wh, float* i
 /* Parity hook: evaluates sampleEnvMap / pdfEnvMap (env_sampling.glsl:53-94) on the device for
  * n (u1,u2) pairs -> dir_pdf[4n] = (dir.xyz, pdf) and pdf_of_dir[n] = pdfEnvMap(dir). */
 int ohb_env_sample_batch(ohb_ctx*, const float* u12, uint32_t n, float* dir_pdf, float* pdf_of_dir);
+/* Parity hook: pdfEnvMap (env_sampling.glsl:79-94) for n caller-supplied unit directions dirs3[3n]. */
+int ohb_env_pdf_batch(ohb_ctx*, const float* dirs3, uint32_t n, float* pdf);
 
 /* ---- acceleration structure: createBLAS + buildTLAS (rt_acceleration_structure.cpp:205-535) -- */
 int ohb_build_accel(ohb_ctx*);                         /* LBVH (Morton + radix sort) + SAH treelets */
@@ -181,9 +183,9 @@ void ohb_reset_counters(ohb_ctx*);
  * since the last ohb_reset_counters, for the roofline line of bench.py. */
 int ohb_get_timing(ohb_ctx*, float* trace_ms, float* shade_ms, float* total_ms);
 int ohb_enable_timing(ohb_ctx*, int enable);
-/* Per-category device time and launch count: [0] closest-hit traversal, [1] shading,
- * [2] any-hit traversal, [3] film. */
-int ohb_get_timing_detail(ohb_ctx*, float ms[4], uint64_t launches[4]);
+/* Per-category device time and launch count: [0] closest-hit traversal, [1] bounce (raygen body: NEE, MIS,
+ * lobe sampling), [2] any-hit traversal, [3] film, [4] surface (closest-hit / miss shaders), [5..7] reserved. */
+int ohb_get_timing_detail(ohb_ctx*, float ms[8], uint64_t launches[8]);
 /* Whole-region device timer: two CUDA events recorded on the context's stream (the stream every
  * kernel of this context is launched on).  ohb_timer_stop synchronises and returns the elapsed ms. */
 int ohb_timer_start(ohb_ctx*);

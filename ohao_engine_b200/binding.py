@@ -56,6 +56,7 @@ ABI = {
     "ohb_set_env": (_I, [_VP, _VP, _U32, _U32]),
     "ohb_get_env_cdf": (_I, [_VP, _VP, _VP, C.POINTER(_F)]),
     "ohb_env_sample_batch": (_I, [_VP, _VP, _U32, _VP, _VP]),
+    "ohb_env_pdf_batch": (_I, [_VP, _VP, _U32, _VP]),
     "ohb_build_accel": (_I, [_VP]),
     "ohb_get_accel_stats": (_I, [_VP, C.POINTER(AccelStats)]),
     "ohb_set_settings": (_I, [_VP, C.POINTER(Settings)]),
@@ -78,7 +79,7 @@ ABI = {
     "ohb_get_counters": (_I, [_VP, C.POINTER(Counters)]),
     "ohb_reset_counters": (None, [_VP]),
     "ohb_get_timing": (_I, [_VP, C.POINTER(_F), C.POINTER(_F), C.POINTER(_F)]),
-    "ohb_get_timing_detail": (_I, [_VP, C.POINTER(_F * 4), C.POINTER(C.c_uint64 * 4)]),
+    "ohb_get_timing_detail": (_I, [_VP, C.POINTER(_F * 8), C.POINTER(C.c_uint64 * 8)]),
     "ohb_enable_timing": (_I, [_VP, _I]),
     "ohb_timer_start": (_I, [_VP]),
     "ohb_timer_stop": (_I, [_VP, C.POINTER(_F)]),
@@ -244,6 +245,10 @@ class Renderer:
         u = np.ascontiguousarray(u12, np.float32); n = len(u); dp = np.zeros((n, 4), np.float32); pd = np.zeros(n, np.float32)
         self._ck(self.lib.ohb_env_sample_batch(self.h, _p(u), n, _p(dp), _p(pd)), "ohb_env_sample_batch"); return dp, pd
 
+    def env_pdf(self, dirs):
+        d = np.ascontiguousarray(dirs, np.float32); pd = np.zeros(len(d), np.float32)
+        self._ck(self.lib.ohb_env_pdf_batch(self.h, _p(d), len(d), _p(pd)), "ohb_env_pdf_batch"); return pd
+
     def counters(self) -> dict:
         c = Counters(); self._ck(self.lib.ohb_get_counters(self.h, C.byref(c)), "ohb_get_counters")
         return dict(samples=c.samples, closest_rays=c.closest_rays, shadow_rays=c.shadow_rays, closest_hits=c.closest_hits, kernel_launches=c.kernel_launches)
@@ -257,7 +262,7 @@ class Renderer:
         ms = C.c_float(); self._ck(self.lib.ohb_timer_stop(self.h, C.byref(ms)), "ohb_timer_stop"); return float(ms.value)
 
     def timing(self) -> dict:
-        ms = (C.c_float * 4)(); cnt = (C.c_uint64 * 4)()
+        ms = (C.c_float * 8)(); cnt = (C.c_uint64 * 8)()
         self._ck(self.lib.ohb_get_timing_detail(self.h, C.byref(ms), C.byref(cnt)), "ohb_get_timing_detail")
-        names = ("trace_closest", "shade", "trace_shadow", "film")
+        names = ("trace_closest", "bounce", "trace_shadow", "film", "surface")
         return {n: dict(ms=float(ms[i]), launches=int(cnt[i])) for i, n in enumerate(names)}

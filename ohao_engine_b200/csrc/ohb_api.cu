@@ -85,7 +85,7 @@ struct ohb_ctx {
     DevBuf activeTris, wtri, primLo, primHi, boundsBits, keys, vals, keysTmp, valsTmp, sortTemp, left, right, parentInner, parentLeaf,
            rangeFirst, rangeLast, nodeLo, nodeHi, visit, newIndex, emitCounter, sah, nodes, tris;
     // paths (device)
-    DevBuf rayO, rayD, hit, thr, rad, pendA, pendB, meta, fh0, fh1, fh2, fh3, shO, shD, queueA, queueB, smallCounters, devCounters;
+    DevBuf rayO, rayD, hit, thr, rad, pendA, pendB, meta, fh0, fh1, fh2, fh3, pay0, pay1, pay2, pay3, shO, shD, queueA, queueB, smallCounters, devCounters;
     uint32_t pathCapacity = 0;
     // film
     DevBuf accum, ldr, albedoAOV, normalAOV, sampleDump;
@@ -163,7 +163,7 @@ void ohb_destroy(ohb_ctx* c) {
                      &c->tex, &c->lights, &c->env, &c->marg, &c->cond, &c->rowTotal, &c->integral, &c->activeTris, &c->wtri, &c->primLo, &c->primHi, &c->boundsBits,
                      &c->keys, &c->vals, &c->keysTmp, &c->valsTmp, &c->sortTemp, &c->left, &c->right, &c->parentInner, &c->parentLeaf, &c->rangeFirst, &c->rangeLast,
                      &c->nodeLo, &c->nodeHi, &c->visit, &c->newIndex, &c->emitCounter, &c->sah, &c->nodes, &c->tris, &c->rayO, &c->rayD, &c->hit, &c->thr, &c->rad,
-                     &c->pendA, &c->pendB, &c->meta, &c->fh0, &c->fh1, &c->fh2, &c->fh3, &c->shO, &c->shD, &c->queueA, &c->queueB, &c->smallCounters, &c->devCounters,
+                     &c->pendA, &c->pendB, &c->meta, &c->fh0, &c->fh1, &c->fh2, &c->fh3, &c->pay0, &c->pay1, &c->pay2, &c->pay3, &c->shO, &c->shD, &c->queueA, &c->queueB, &c->smallCounters, &c->devCounters,
                      &c->accum, &c->ldr, &c->albedoAOV, &c->normalAOV, &c->sampleDump, &c->hookRays, &c->hookOut, &c->hookAux};
     for (DevBuf* b : all) b->release();
     if (c->evA) cudaEventDestroy(c->evA);
@@ -303,6 +303,21 @@ int ohb_env_sample_batch(ohb_ctx* c, const float* u12, uint32_t n, float* dir_pd
     return 0;
 }
 
+int ohb_env_pdf_batch(ohb_ctx* c, const float* dirs3, uint32_t n, float* pdf) {
+    if (!c) return 1;
+    if (!c->envW) OHB_FAIL(c, "ohb_env_pdf_batch: no environment map");
+    if (!dirs3 || !pdf) OHB_FAIL(c, "ohb_env_pdf_batch: null array");
+    if (n == 0) return 0;
+    cudaSetDevice(c->device);
+    CU(c, c->hookRays.reserve(size_t(n) * 12)); CU(c, c->hookAux.reserve(size_t(n) * 4));
+    CU(c, cudaMemcpyAsync(c->hookRays.p, dirs3, size_t(n) * 12, cudaMemcpyHostToDevice, c->stream));
+    SceneDev s; fillScene(c, s);
+    launchEnvPdf(s, c->hookRays.as<float>(), n, c->hookAux.as<float>(), c->stream, &c->launches);
+    CU(c, cudaMemcpyAsync(pdf, c->hookAux.p, size_t(n) * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int ohb_build_accel(ohb_ctx* c) {
     if (!c) return 1;
     cudaSetDevice(c->device);
@@ -417,6 +432,7 @@ static int ensurePaths(ohb_ctx* c, uint32_t cap) {
     CU(c, c->rayO.reserve(n * 16)); CU(c, c->rayD.reserve(n * 16)); CU(c, c->hit.reserve(n * 16)); CU(c, c->thr.reserve(n * 16)); CU(c, c->rad.reserve(n * 16));
     CU(c, c->pendA.reserve(n * 16)); CU(c, c->pendB.reserve(n * 16)); CU(c, c->meta.reserve(n * 16));
     CU(c, c->fh0.reserve(n * 16)); CU(c, c->fh1.reserve(n * 16)); CU(c, c->fh2.reserve(n * 16)); CU(c, c->fh3.reserve(n * 16));
+    CU(c, c->pay0.reserve(n * 16)); CU(c, c->pay1.reserve(n * 16)); CU(c, c->pay2.reserve(n * 16)); CU(c, c->pay3.reserve(n * 16));
     CU(c, c->shO.reserve(n * 32)); CU(c, c->shD.reserve(n * 32)); CU(c, c->queueA.reserve(n * 4)); CU(c, c->queueB.reserve(n * 4));
     c->pathCapacity = cap;
     return 0;
@@ -464,6 +480,7 @@ int ohb_render(ohb_ctx* c, const float view[16], const float proj[16], uint32_t 
         P.rayO = c->rayO.as<f4>(); P.rayD = c->rayD.as<f4>(); P.hit = c->hit.as<ohb_hit>(); P.thr = c->thr.as<f4>(); P.rad = c->rad.as<f4>();
         P.pendA = c->pendA.as<f4>(); P.pendB = c->pendB.as<f4>(); P.meta = c->meta.as<u4>();
         P.fh0 = c->fh0.as<f4>(); P.fh1 = c->fh1.as<f4>(); P.fh2 = c->fh2.as<f4>(); P.fh3 = c->fh3.as<f4>();
+        P.pay0 = c->pay0.as<f4>(); P.pay1 = c->pay1.as<f4>(); P.pay2 = c->pay2.as<f4>(); P.pay3 = c->pay3.as<f4>();
         P.shO = c->shO.as<f4>(); P.shD = c->shD.as<f4>();
         P.queueIn = c->queueA.as<uint32_t>(); P.queueOut = c->queueB.as<uint32_t>();
         P.countIn = small + 0; P.countOut = small + 1; P.shCount = small + 2;
@@ -563,17 +580,17 @@ int ohb_get_timing(ohb_ctx* c, float* trace_ms, float* shade_ms, float* total_ms
     CU(c, cudaStreamSynchronize(c->stream));
     c->timing.collect();
     if (trace_ms) *trace_ms = float(c->timing.ms[0] + c->timing.ms[2]);
-    if (shade_ms) *shade_ms = float(c->timing.ms[1]);
-    if (total_ms) *total_ms = float(c->timing.ms[0] + c->timing.ms[1] + c->timing.ms[2] + c->timing.ms[3]);
+    if (shade_ms) *shade_ms = float(c->timing.ms[1] + c->timing.ms[4]);
+    if (total_ms) { double t = 0; for (int i = 0; i < 8; i++) t += c->timing.ms[i]; *total_ms = float(t); }
     return 0;
 }
 
-int ohb_get_timing_detail(ohb_ctx* c, float ms[4], uint64_t launches[4]) {
+int ohb_get_timing_detail(ohb_ctx* c, float ms[8], uint64_t launches[8]) {
     if (!c || !ms || !launches) return 1;
     cudaSetDevice(c->device);
     CU(c, cudaStreamSynchronize(c->stream));
     c->timing.collect();
-    for (int i = 0; i < 4; i++) { ms[i] = float(c->timing.ms[i]); launches[i] = c->timing.count[i]; }
+    for (int i = 0; i < 8; i++) { ms[i] = float(c->timing.ms[i]); launches[i] = c->timing.count[i]; }
     return 0;
 }
 

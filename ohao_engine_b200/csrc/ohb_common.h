@@ -59,7 +59,20 @@ OHB_HD float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
 OHB_HD f3 mix(f3 a, f3 b, float t) { return a * (1.0f - t) + b * t; }
 OHB_HD f3 mix(f3 a, f3 b, f3 t) { return a * (mk3(1.0f) - t) + b * t; }
 OHB_HD f3 reflect(f3 I, f3 N) { return I - N * (2.0f * dot(N, I)); }
-OHB_HD f3 vpow(f3 a, float e) { return mk3(powf(a.x, e), powf(a.y, e), powf(a.z, e)); }
+// Accurate libm-grade transcendentals, ONE shared copy per kernel: the slow paths of sinf/cosf/powf/atan2f
+// are hundreds of instructions each, and inlining them at ~40 call sites made the shading kernel 200 KB of
+// SASS that thrashed the instruction cache (ncu: stall_no_instruction 13.4 of 21 cycles per issue, r01).
+#if defined(__CUDACC__)
+#define OHB_SHARED_FN static __device__ __host__ __noinline__
+#else
+#define OHB_SHARED_FN static inline
+#endif
+OHB_SHARED_FN float ohb_sin(float x) { return sinf(x); }
+OHB_SHARED_FN float ohb_cos(float x) { return cosf(x); }
+OHB_SHARED_FN float ohb_pow(float x, float e) { return powf(x, e); }
+OHB_SHARED_FN float ohb_atan2(float y, float x) { return atan2f(y, x); }
+OHB_HD f3 vpow(f3 a, float e) { return mk3(ohb_pow(a.x, e), ohb_pow(a.y, e), ohb_pow(a.z, e)); }
+OHB_HD float pow5(float x) { float x2 = x * x; return x2 * x2 * x; }
 OHB_HD float maxcomp(f3 a) { return fmaxf(a.x, fmaxf(a.y, a.z)); }
 OHB_HD float signf(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
 OHB_HD float smoothstepf(float e0, float e1, float x) { float t = clampf((x - e0) / (e1 - e0), 0.0f, 1.0f); return t * t * (3.0f - 2.0f * t); }

@@ -8,11 +8,11 @@
 namespace ohb {
 
 // CUDA-event timing of kernel categories on the launching stream (bench.py roofline line):
-// 0 = closest-hit traversal, 1 = shading, 2 = any-hit traversal, 3 = film.
+// 0 = closest-hit traversal, 1 = bounce (raygen body), 2 = any-hit traversal, 3 = film, 4 = surface (hit/miss shaders), 5-7 spare.
 struct TimingHooks {
     struct Span { cudaEvent_t a, b; int cat; };
-    std::vector<Span> spans; size_t used = 0; cudaEvent_t pendingStart[4] = {nullptr, nullptr, nullptr, nullptr};
-    double ms[4] = {0, 0, 0, 0}; uint64_t count[4] = {0, 0, 0, 0};
+    std::vector<Span> spans; size_t used = 0; 
+    double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0}; uint64_t count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     void begin(int cat, cudaStream_t st) {
         if (used == spans.size()) { Span s; cudaEventCreate(&s.a); cudaEventCreate(&s.b); s.cat = cat; spans.push_back(s); }
         spans[used].cat = cat; cudaEventRecord(spans[used].a, st);
@@ -22,7 +22,7 @@ struct TimingHooks {
         for (size_t i = 0; i < used; i++) { float t = 0; cudaEventElapsedTime(&t, spans[i].a, spans[i].b); ms[spans[i].cat] += t; count[spans[i].cat]++; }
         used = 0;
     }
-    void reset() { collect(); for (int i = 0; i < 4; i++) { ms[i] = 0; count[i] = 0; } }
+    void reset() { collect(); for (int i = 0; i < 8; i++) { ms[i] = 0; count[i] = 0; } }
     ~TimingHooks() { for (auto& s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); } }
 };
 
@@ -31,6 +31,7 @@ uint32_t radixSortTempWords(uint32_t n);
 void launchBuild(const BuildArrays& b, uint64_t* keysTmp, uint32_t* valsTmp, uint32_t* sortTemp, cudaStream_t st, uint64_t* launches);
 void launchEnvCdf(const f4* env, uint32_t W, uint32_t H, float* cond, float* marg, float* rowTotal, float* integral, cudaStream_t st, uint64_t* launches);
 void launchEnvSample(const SceneDev& sc, const float* u12, uint32_t n, f4* dirPdf, float* pdfOfDir, cudaStream_t st, uint64_t* launches);
+void launchEnvPdf(const SceneDev& sc, const float* dirs3, uint32_t n, float* pdf, cudaStream_t st, uint64_t* launches);
 void launchOfflineBatch(const SceneDev& sc, const FrameParams& fr, PathArrays P, const FilmArrays& F,
                         uint32_t* work, int numSMs, cudaStream_t st, uint64_t* launches, TimingHooks* th);
 void launchResolve(f4* accum, uint32_t* ldr, uint32_t n, int sumMode, cudaStream_t st, uint64_t* launches);

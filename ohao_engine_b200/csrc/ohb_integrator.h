@@ -5,7 +5,10 @@
 // a state machine: every wavefront iteration traces ONE closest-hit ray per live path
 // (k_trace_closest), shades it (shadePath below: closest-hit/miss shader + the raygen's per-bounce
 // body), emits at most two visibility rays whose contributions are parked in `pend` until the
-// any-hit kernel has answered, and writes the next ray.  Stage B (specular chain) and Stage C
+// any-hit kernel has answered, and writes the next ray.  Shading itself is two kernels per iteration:
+// k_surface (= the closest-hit / miss SHADERS: geometry + texture gathers -> 64-B payload record) and
+// k_bounce (= the raygen's per-bounce body: NEE, MIS, lobe sampling, state machine), so each stays small
+// enough for the instruction cache and its warps diverge two ways at most (hit / miss).  Stage B (specular chain) and Stage C
 // (diffuse chain) of one sample run back-to-back on the same path slot because the Sobol dimension
 // counter is shared: C's first dimension depends on how many B consumed.  Contributions are added
 // in exactly the reference's order, so a sample's radiance differs from the megakernel only by
@@ -31,6 +34,7 @@ struct PathArrays {
     f4* pendA; f4* pendB;          // parked light-NEE / env-NEE contributions (zeroed by k_trace_shadow when occluded)
     u4* meta;                      // x = px | py << 16, y = sampleIdx, z = dimIdx, w = state bits
     f4* fh0; f4* fh1; f4* fh2; f4* fh3;   // first hit kept for the Stage C set-up: (pos, rough) (N, metal) (albedo, -) (rayDir, -)
+    f4* pay0; f4* pay1; f4* pay2; f4* pay3;   // RayPayload of the last query: (hitPos|color, hitDist) (N, att.x | envPdf) (albedo, att.y) (emission, att.z)
     f4* shO; f4* shD;              // visibility-ray queue: (origin, tmax) (dir, bits(path << 1 | slot))
     uint32_t* shCount;
     uint32_t* queueIn; uint32_t* queueOut; uint32_t* countIn; uint32_t* countOut;
@@ -44,16 +48,19 @@ struct PathArrays {
 struct Payload { f3 color, attenuation, hitPos, hitNormal, hitAlbedo; float hitDist, envPdf; };
 
 // pt_miss.rmiss:52-82
+OHB_HD f3 envRadiance(const SceneDev& sc, f3 dir) {   // dir normalised; dirToEquirect + bilinear fetch x envIntensity
+    float phi = ohb_atan2(dir.z, dir.x);
+    float theta = asinf(clampf(dir.y, -1.0f, 1.0f));
+    f2 uv; uv.x = phi / 6.2831853f + 0.5f; uv.y = theta / 3.1415926f + 0.5f;
+    float envS = (sc.envIntensity > 0.0f) ? sc.envIntensity : 1.0f;
+    return xyz(sampleEnvTexture(sc, uv)) * envS;
+}
 OHB_HD void missShader(const SceneDev& sc, const FrameParams& fr, f3 rayDir, Payload& p) {
     p.hitDist = -1.0f;
     bool haveEnv = sc.envMapTexIdx != 0xFFFFFFFFu && sc.env != nullptr;
     if (haveEnv) {
         f3 dir = normalize(rayDir);
-        float phi = atan2f(dir.z, dir.x);
-        float theta = asinf(clampf(dir.y, -1.0f, 1.0f));
-        f2 uv; uv.x = phi / 6.2831853f + 0.5f; uv.y = theta / 3.1415926f + 0.5f;
-        float envS = (sc.envIntensity > 0.0f) ? sc.envIntensity : 1.0f;
-        p.color = xyz(sampleEnvTexture(sc, uv)) * envS;
+        p.color = envRadiance(sc, dir);
         p.envPdf = (fr.envW > 0u && fr.envH > 0.0f) ? pdfEnvMap(sc, dir) : 0.0f;
     } else {
         p.color = mk3(0.0f); p.envPdf = 0.0f;
@@ -136,8 +143,13 @@ OHB_HD f3 cosineHemisphere(f3 N, f2 u) {   // pt_raygen_offline.rgen:93-100
     f3 B = cross(N, T);
     float r = sqrtf(u.x);
     float phi = 6.2831853f * u.y;
-    return normalize(T * r * cosf(phi) + B * r * sinf(phi) + N * sqrtf(fmaxf(0.0f, 1.0f - r * r)));
+    return normalize(T * r * ohb_cos(phi) + B * r * ohb_sin(phi) + N * sqrtf(fmaxf(0.0f, 1.0f - r * r)));
 }
+#if defined(__CUDACC__)
+static __device__ __host__ __noinline__ f3 cosineHemisphereShared(f3 N, f2 u) { return cosineHemisphere(N, u); }   // 4 call sites, one copy
+#else
+static inline f3 cosineHemisphereShared(f3 N, f2 u) { return cosineHemisphere(N, u); }
+#endif
 OHB_HD float misBalance(float a, float b) { return a / fmaxf(a + b, 1e-6f); }   // mis.glsl:7-9
 OHB_HD float ggxD_anisoOrIso(f3 N, f3 H, float NdotH, float roughness, float anisotropy, float rotation) {   // ggx_aniso.glsl:24-58
     if (anisotropy < 0.001f) {
@@ -149,7 +161,7 @@ OHB_HD float ggxD_anisoOrIso(f3 N, f3 H, float NdotH, float roughness, float ani
     f3 ref = fabsf(dot(up, N)) > 0.97f ? mk3(1, 0, 0) : up;
     f3 T = normalize(ref - N * dot(ref, N));
     f3 B = cross(N, T);
-    float c = cosf(rotation), s = sinf(rotation);
+    float c = ohb_cos(rotation), s = ohb_sin(rotation);
     f3 Tr = T * c + B * s, Br = B * c - T * s;
     float r2 = roughness * roughness;
     float aspect = sqrtf(1.0f - anisotropy * 0.9f);
@@ -158,7 +170,7 @@ OHB_HD float ggxD_anisoOrIso(f3 N, f3 H, float NdotH, float roughness, float ani
     float dd = (TdotH * TdotH / rT) + (BdotH * BdotH / rB) + NdotH * NdotH;
     return 1.0f / (3.14159265f * rT * rB * dd * dd + 0.0001f);
 }
-OHB_HD f3 schlick(f3 F0, float c) { return F0 + (mk3(1.0f) - F0) * powf(1.0f - c, 5.0f); }
+OHB_HD f3 schlick(f3 F0, float c) { return F0 + (mk3(1.0f) - F0) * pow5(1.0f - c); }   // pow(x, 5.0) as 3 multiplies (<= 2 ulp)
 OHB_HD float specProbOf(f3 rayDir, f3 N, f3 F0, float rough, float metal) {
     float cosI = fabsf(dot(normalize(rayDir), N));
     float sp = maxcomp(schlick(F0, cosI)) * (1.0f - rough * 0.9f);
@@ -186,7 +198,7 @@ OHB_HD LightSample sampleLight(const SceneDev& sc, Sampler& sm, uint32_t& dimIdx
         float cosT = 1.0f - 2.0f * u.x;
         float sinT = sqrtf(fmaxf(0.0f, 1.0f - cosT * cosT));
         float phi = 6.2831853f * u.y;
-        f3 offset = mk3(sinT * cosf(phi), sinT * sinf(phi), cosT) * r;
+        f3 offset = mk3(sinT * ohb_cos(phi), sinT * ohb_sin(phi), cosT) * r;
         f3 toL = (center + offset) - hitPos; float dist = length(toL);
         ls.L = toL / dist; ls.shadowDist = dist - 0.02f;
         if (type < 0.5f) {
@@ -195,7 +207,7 @@ OHB_HD LightSample sampleLight(const SceneDev& sc, Sampler& sm, uint32_t& dimIdx
         } else {
             float cosAngle = dot(-ls.L, lightDir);
             const float d2r = 0.017453292519943295f;
-            float innerCos = cosf(dp.w * d2r), outerCos = cosf(ex.w * d2r);
+            float innerCos = ohb_cos(dp.w * d2r), outerCos = ohb_cos(ex.w * d2r);
             float spot = clampf((cosAngle - outerCos) / (innerCos - outerCos + 0.001f), 0.0f, 1.0f);
             spot *= spot;
             ls.weight = area / (dist * dist) * spot;
@@ -255,7 +267,7 @@ struct ShadeCtx {
                 float DS = a2S / (3.14159f * dS * dS + 1e-4f);
                 float kS = (rS + 1.0f) * (rS + 1.0f) / 8.0f;
                 float GS = (NdotL / (NdotL * (1.0f - kS) + kS)) * (NdotV / (NdotV * (1.0f - kS) + kS));
-                f3 FS = mk3(0.028f) + (mk3(1.0f) - mk3(0.028f)) * powf(1.0f - VdotH, 5.0f);
+                f3 FS = mk3(0.028f) + (mk3(1.0f) - mk3(0.028f)) * pow5(1.0f - VdotH);
                 spec += (DS * GS * FS / (4.0f * NdotV * NdotL + 1e-3f)) * (fr.sss * 0.4f);
             }
             f3 kD = (mk3(1.0f) - F) * (1.0f - metal);
@@ -287,8 +299,7 @@ struct ShadeCtx {
         float NdotL = fmaxf(dot(N, envDir), 0.0f);
         if (!(NdotL > 0.0f && envPdf > 0.0f)) return;
         // payload.color of the visibility ray's miss shader == env radiance along envDir
-        Payload mp; missShader(sc, fr, envDir, mp);
-        f3 envRad = mp.color;
+        f3 envRad = envRadiance(sc, envDir);
         f3 V = normalize(-inDir), H = normalize(envDir + V);
         float NdotH = fmaxf(dot(N, H), 0.001f), NdotV = fmaxf(dot(N, V), 0.001f), VdotH = fmaxf(dot(V, H), 0.001f);
         float D;
@@ -336,137 +347,144 @@ OHB_HD void raygenPath(const FrameParams& fr, const PathArrays& P, uint32_t p) {
     P.rad[p] = mk4(0, 0, 0, 0);
 }
 
-// Shade one path after its closest-hit query returned.  Returns true if the path traces again.
-OHB_HD bool shadePath(const SceneDev& sc, const FrameParams& fr, const PathArrays& P, uint32_t p) {
+// k_surface: the closest-hit / miss shader of path p's last query -> payload record.
+OHB_HD void surfacePath(const SceneDev& sc, const FrameParams& fr, const PathArrays& P, uint32_t p) {
+    f3 o = xyz(P.rayO[p]), d = xyz(P.rayD[p]);
+    ohb_hit h = P.hit[p];
+    Payload pl;
+    if (h.prim == OHB_MISS) {
+        missShader(sc, fr, d, pl);
+        P.pay0[p] = mk4(pl.color, -1.0f); P.pay1[p] = mk4(pl.envPdf, 0.0f, 0.0f, 0.0f);
+    } else {
+        closestHitShader(sc, o, d, h, pl);
+        P.pay0[p] = mk4(pl.hitPos, pl.hitDist); P.pay1[p] = mk4(pl.hitNormal, pl.attenuation.x);
+        P.pay2[p] = mk4(pl.hitAlbedo, pl.attenuation.y); P.pay3[p] = mk4(pl.color, pl.attenuation.z);
+    }
+}
+
+// reflect + roughness jitter + below-horizon re-sample: :573-592 (B set-up) == :843-862 == :1151-1170
+OHB_HD f3 sampleSpecDir(ShadeCtx& cx, f3 d, f3 N, float rough) {
+    f3 refl = reflect(d, N);
+    if (rough > 0.01f) {
+        f2 ju = cx.sm.get2D(cx.dimIdx); cx.dimIdx += 2u;
+        refl = normalize(refl + cosineHemisphereShared(refl, ju) * rough);
+        if (dot(refl, N) < 0.0f) { f2 fu = cx.sm.get2D(cx.dimIdx); cx.dimIdx += 2u; refl = cosineHemisphereShared(N, fu); }
+    }
+    return refl;
+}
+
+// k_bounce: the raygen's per-bounce body for path p, after k_surface.  Returns true if the path traces again.
+OHB_HD bool bouncePath(const SceneDev& sc, const FrameParams& fr, const PathArrays& P, uint32_t p) {
     ShadeCtx cx(sc, fr, P);
     u4 m = P.meta[p];
     cx.path = p; cx.state = m.w;
     uint32_t px = m.x & 0xFFFFu, py = m.x >> 16;
     cx.sm.init(fr.samplerType, px, py, m.y);
-    if (fr.samplerType == OHB_SAMPLER_PCG) cx.sm.pcg = m.z; else cx.dimIdx = m.z;
-    if (fr.samplerType == OHB_SAMPLER_PCG) cx.dimIdx = 0u;
+    if (fr.samplerType == OHB_SAMPLER_PCG) { cx.sm.pcg = m.z; cx.dimIdx = 0u; } else cx.dimIdx = m.z;
     f3 rad = xyz(P.rad[p]);
     if (cx.state & OHB_ST_PEND_A) rad += xyz(P.pendA[p]);
     if (cx.state & OHB_ST_PEND_B) rad += xyz(P.pendB[p]);
     cx.state &= ~(OHB_ST_PEND_A | OHB_ST_PEND_B);
     uint32_t stage = OHB_ST_STAGE(cx.state), bounce = OHB_ST_BOUNCE(cx.state);
-    f3 o = xyz(P.rayO[p]), d = xyz(P.rayD[p]);
-    ohb_hit h = P.hit[p];
-    Payload pl;
-    if (h.prim == OHB_MISS) missShader(sc, fr, d, pl);
-    else closestHitShader(sc, o, d, h, pl);
+    const bool primary = (stage == ST_PRIMARY), specChain = (stage == ST_CHAIN_B);
+    f3 d = xyz(P.rayD[p]);
+    f4 q0 = P.pay0[p], q1 = P.pay1[p];
+    const bool isMiss = q0.w < 0.0f;
 
-    f3 nextO = mk3(0.0f), nextD = mk3(0.0f), thr = mk3(0.0f); float lastPdf = 0.0f; bool lastDelta = false;
-    bool startC = false, finished = false;
-    // first-hit data (needed at C set-up): either just produced (stage A) or reloaded (end of B)
-    f3 fhPos = mk3(0.0f), fhN = mk3(0.0f), fhAlbedo = mk3(0.0f);
+    f3 nextO = mk3(0.0f), nextD = mk3(0.0f), thr = mk3(1.0f); float lastPdf = 0.0f; bool lastDelta = false;
+    if (!primary) { f4 t4 = P.thr[p]; thr = xyz(t4); lastPdf = t4.w; lastDelta = (cx.state & OHB_ST_DELTA) != 0u; }
+    bool startC = false, finished = false, chainEnds = false;
+    f3 fhPos = mk3(0.0f), fhN = mk3(0.0f), fhAlbedo = mk3(0.0f);   // first-hit data for the Stage C set-up
 
-    if (stage == ST_PRIMARY) {
+    bool aov = false; size_t pi = 0;
+    if (primary) {
         bool lastSample = (m.y == P.firstSampleIndex + P.samplesInBatch - 1u);
-        bool aov = (fr.flags & OHB_FLAG_ENABLE_AOVS) && lastSample && P.albedoAOV;
-        size_t pi = size_t(py) * fr.W + px;
-        if (pl.hitDist < 0.0f) {
-            rad = pl.color;
-            if (aov) { P.albedoAOV[pi] = mk4(pl.color, 1.0f); P.normalAOV[pi] = mk4(0, 0, 0, 0); }
+        aov = (fr.flags & OHB_FLAG_ENABLE_AOVS) && lastSample && P.albedoAOV;
+        pi = size_t(py) * fr.W + px;
+    }
+    if (isMiss) {
+        f3 color = xyz(q0); float envPdf = q1.x;
+        if (primary) {
+            rad = color;
+            if (aov) { P.albedoAOV[pi] = mk4(color, 1.0f); P.normalAOV[pi] = mk4(0, 0, 0, 0); }
             finished = true;
         } else {
-            f3 hp = pl.hitPos, N = pl.hitNormal, albedo = pl.hitAlbedo, em = pl.color;
-            if (aov) { P.albedoAOV[pi] = mk4(albedo, 1.0f); P.normalAOV[pi] = mk4(N * 0.5f + mk3(0.5f), 1.0f); }
-            float rough, metal; unpackHitPbr(pl.attenuation, rough, metal);
-            f3 F0 = mix(mk3(0.04f), albedo, metal);
-            float curvature = clampf(pl.attenuation.z, 0.0f, 1.0f);
-            if (length(em) > 0.001f) rad += em;
-            if (sc.lightCount > 0u) cx.lightNEE(hp, N, d, albedo, F0, rough, metal, curvature, true, mk3(1.0f));
-            if (cx.envOn) cx.envNEE(hp, N, d, albedo, F0, rough, metal, true, mk3(1.0f));
-            // Stage B set-up (:573-614)
-            f3 refl = reflect(d, N);
-            if (rough > 0.01f) {
-                f2 ju = cx.sm.get2D(cx.dimIdx); cx.dimIdx += 2u;
-                refl = normalize(refl + cosineHemisphere(refl, ju) * rough);
-                if (dot(refl, N) < 0.0f) { f2 fu = cx.sm.get2D(cx.dimIdx); cx.dimIdx += 2u; refl = cosineHemisphere(N, fu); }
-            }
-            thr = mix(mk3(1.0f), albedo, metal);
-            if (rough < 0.05f) { lastPdf = 1.0f; lastDelta = true; }
-            else {
-                f3 Hs = normalize(-d + refl);
-                float NdotH = fmaxf(dot(N, Hs), 0.001f), VdotH = fmaxf(dot(-d, Hs), 0.001f);
-                float Ds = ggxD_anisoOrIso(N, Hs, NdotH, rough, fr.aniso, fr.anisoRot);
-                lastPdf = Ds * NdotH / (4.0f * VdotH + 1e-4f); lastDelta = false;
-            }
-            nextO = hp + N * 0.01f; nextD = refl;
-            P.fh0[p] = mk4(hp, rough); P.fh1[p] = mk4(N, metal); P.fh2[p] = mk4(albedo, 0.0f); P.fh3[p] = mk4(d, 0.0f);
-            if (fr.maxBounces >= 1u) { stage = ST_CHAIN_B; bounce = 1u; }
-            else { startC = true; fhPos = hp; fhN = N; fhAlbedo = albedo; stage = ST_CHAIN_B; }
+            float w = 1.0f;
+            if (envPdf > 0.0f && fr.envW > 0u && !lastDelta) w = misBalance(lastPdf, envPdf);
+            rad += thr * color * w;
+            chainEnds = true;
         }
     } else {
-        // one iteration of the Stage B (:616-895) or Stage C (:923-1201) loop body
-        bool specChain = (stage == ST_CHAIN_B);
-        f4 t4 = P.thr[p]; thr = xyz(t4); lastPdf = t4.w; lastDelta = (cx.state & OHB_ST_DELTA) != 0u;
-        bool chainEnds = false;
-        if (pl.hitDist < 0.0f) {
-            float w = 1.0f;
-            if (pl.envPdf > 0.0f && fr.envW > 0u && !lastDelta) w = misBalance(lastPdf, pl.envPdf);
-            rad += thr * pl.color * w;
-            chainEnds = true;
-        } else {
-            f3 hp = pl.hitPos, N = pl.hitNormal, albedo = pl.hitAlbedo, em = pl.color;
-            if (length(em) > 0.001f) rad += thr * em;
-            float rough, metal; unpackHitPbr(pl.attenuation, rough, metal);
-            f3 F0 = mix(mk3(0.04f), albedo, metal);
-            if (sc.lightCount > 0u) cx.lightNEE(hp, N, d, albedo, F0, rough, metal, 0.0f, false, thr);
-            if (cx.envOn) cx.envNEE(hp, N, d, albedo, F0, rough, metal, false, thr);
-            bool killed = false;
-            if (bounce > 1u) {
+        f4 q2 = P.pay2[p], q3 = P.pay3[p];
+        f3 hp = xyz(q0), N = xyz(q1), albedo = xyz(q2), em = xyz(q3);
+        if (aov) { P.albedoAOV[pi] = mk4(albedo, 1.0f); P.normalAOV[pi] = mk4(N * 0.5f + mk3(0.5f), 1.0f); }
+        float rough, metal; unpackHitPbr(mk3(q1.w, q2.w, q3.w), rough, metal);
+        f3 F0 = mix(mk3(0.04f), albedo, metal);
+        float curvature = primary ? clampf(q3.w, 0.0f, 1.0f) : 0.0f;
+        if (length(em) > 0.001f) rad += primary ? em : thr * em;
+        // NEE: one call site each for every bounce (bounce 0 differs inside, see ShadeCtx)
+        if (sc.lightCount > 0u) cx.lightNEE(hp, N, d, albedo, F0, rough, metal, curvature, primary, thr);
+        if (cx.envOn) cx.envNEE(hp, N, d, albedo, F0, rough, metal, primary, thr);
+        bool killed = false; float specProb = 1.0f; bool takeSpec = true;
+        if (!primary) {
+            if (bounce > 1u) {   // Russian roulette :834-839 / :1142-1147
                 float pr = maxcomp(thr);
                 float rr = cx.sm.get1D(cx.dimIdx); cx.dimIdx += 1u;
                 if (pr < 0.01f || rr > pr) killed = true; else thr /= pr;
             }
-            if (killed) chainEnds = true;
-            else {
-                float specProb = specProbOf(d, N, F0, rough, metal);
+            if (!killed) {
+                specProb = specProbOf(d, N, F0, rough, metal);
                 float choice = cx.sm.get1D(cx.dimIdx); cx.dimIdx += 1u;
-                if (choice < specProb || rough < 0.05f) {
-                    f3 refl = reflect(d, N);
-                    if (rough > 0.01f) {
-                        f2 ju = cx.sm.get2D(cx.dimIdx); cx.dimIdx += 2u;
-                        refl = normalize(refl + cosineHemisphere(refl, ju) * rough);
-                        if (dot(refl, N) < 0.0f) { f2 fu = cx.sm.get2D(cx.dimIdx); cx.dimIdx += 2u; refl = cosineHemisphere(N, fu); }
-                    }
-                    nextD = refl; nextO = hp + N * 0.01f;
-                    if (specChain || (fr.flags & OHB_FLAG_GOLDEN_COMPAT)) thr *= mix(mk3(1.0f), albedo, metal);   // :864
-                    else                                                   thr *= albedo * (1.0f - metal);          // :1172
-                    thr /= fmaxf(specProb, 0.01f);
-                    if (rough < 0.05f) { lastPdf = 1.0f; lastDelta = true; }
-                    else {
-                        f3 Hs = normalize(-d + nextD);
-                        float NdotH = fmaxf(dot(N, Hs), 0.001f), VdotH = fmaxf(dot(-d, Hs), 0.001f);
-                        float as = rough * rough, as2 = as * as;
-                        float dn = NdotH * NdotH * (as2 - 1.0f) + 1.0f;
-                        float Ds = as2 / (OHB_PI * dn * dn + 1e-4f);
-                        lastPdf = specProb * (Ds * NdotH / (4.0f * VdotH + 1e-4f)); lastDelta = false;
-                    }
-                } else {
-                    f2 du = cx.sm.get2D(cx.dimIdx); cx.dimIdx += 2u;
-                    nextD = cosineHemisphere(N, du); nextO = hp + N * 0.01f;
-                    thr *= albedo;
-                    thr /= fmaxf(1.0f - specProb, 0.01f);
-                    lastPdf = (1.0f - specProb) * fmaxf(dot(nextD, N), 0.0f) / OHB_PI; lastDelta = false;
-                }
-                if (bounce >= fr.maxBounces) chainEnds = true; else bounce += 1u;
+                takeSpec = (choice < specProb || rough < 0.05f);
             }
         }
-        if (chainEnds) {
-            if (specChain) {
-                startC = true;
-                f4 a0 = P.fh0[p], a1 = P.fh1[p], a2 = P.fh2[p];
-                fhPos = xyz(a0); fhN = xyz(a1); fhAlbedo = xyz(a2);
-            } else finished = true;
+        if (killed) chainEnds = true;
+        else {
+            nextO = hp + N * 0.01f;
+            if (takeSpec) {
+                nextD = sampleSpecDir(cx, d, N, rough);
+                if (primary) thr = mix(mk3(1.0f), albedo, metal);                                                          // Stage B set-up :594
+                else {
+                    if (specChain || (fr.flags & OHB_FLAG_GOLDEN_COMPAT)) thr *= mix(mk3(1.0f), albedo, metal);            // :864
+                    else                                                   thr *= albedo * (1.0f - metal);                 // :1172
+                    thr /= fmaxf(specProb, 0.01f);
+                }
+                if (rough < 0.05f) { lastPdf = 1.0f; lastDelta = true; }
+                else {
+                    f3 Hs = normalize(-d + nextD);
+                    float NdotH = fmaxf(dot(N, Hs), 0.001f), VdotH = fmaxf(dot(-d, Hs), 0.001f);
+                    float Ds;
+                    if (primary) Ds = ggxD_anisoOrIso(N, Hs, NdotH, rough, fr.aniso, fr.anisoRot);
+                    else { float as = rough * rough, as2 = as * as; float dn = NdotH * NdotH * (as2 - 1.0f) + 1.0f; Ds = as2 / (OHB_PI * dn * dn + 1e-4f); }
+                    float pdfH = Ds * NdotH / (4.0f * VdotH + 1e-4f);
+                    lastPdf = primary ? pdfH : specProb * pdfH; lastDelta = false;
+                }
+            } else {
+                f2 du = cx.sm.get2D(cx.dimIdx); cx.dimIdx += 2u;
+                nextD = cosineHemisphereShared(N, du);
+                thr *= albedo;
+                thr /= fmaxf(1.0f - specProb, 0.01f);
+                lastPdf = (1.0f - specProb) * fmaxf(dot(nextD, N), 0.0f) / OHB_PI; lastDelta = false;
+            }
+            if (primary) {
+                P.fh0[p] = mk4(hp, rough); P.fh1[p] = mk4(N, metal); P.fh2[p] = mk4(albedo, 0.0f); P.fh3[p] = mk4(d, 0.0f);
+                if (fr.maxBounces >= 1u) { stage = ST_CHAIN_B; bounce = 1u; }
+                else { startC = true; fhPos = hp; fhN = N; fhAlbedo = albedo; stage = ST_CHAIN_B; }
+            } else if (bounce >= fr.maxBounces) chainEnds = true;
+            else bounce += 1u;
         }
+    }
+    if (chainEnds) {
+        if (specChain) {
+            startC = true;
+            f4 a0 = P.fh0[p], a1 = P.fh1[p], a2 = P.fh2[p];
+            fhPos = xyz(a0); fhN = xyz(a1); fhAlbedo = xyz(a2);
+        } else finished = true;
     }
     if (startC) {
         // Stage C set-up (:900-921): cosine direction around the FIRST hit's normal, throughput = albedo
         f2 du = cx.sm.get2D(cx.dimIdx); cx.dimIdx += 2u;
-        nextD = cosineHemisphere(fhN, du);
+        nextD = cosineHemisphereShared(fhN, du);
         nextO = fhPos + fhN * 0.01f;
         thr = fhAlbedo;
         lastPdf = fmaxf(dot(nextD, fhN), 0.0f) / OHB_PI; lastDelta = false;
@@ -474,16 +492,18 @@ OHB_HD bool shadePath(const SceneDev& sc, const FrameParams& fr, const PathArray
     }
     P.rad[p] = mk4(rad, 0.0f);
     uint32_t keep = cx.state & (OHB_ST_PEND_A | OHB_ST_PEND_B);
-    if (finished) {
-        m.w = ST_DONE | keep; m.z = (fr.samplerType == OHB_SAMPLER_PCG) ? cx.sm.pcg : cx.dimIdx; P.meta[p] = m;
-        return false;
-    }
-    m.w = OHB_ST_MAKE(stage, bounce) | keep | (lastDelta ? OHB_ST_DELTA : 0u);
     m.z = (fr.samplerType == OHB_SAMPLER_PCG) ? cx.sm.pcg : cx.dimIdx;
+    if (finished) { m.w = ST_DONE | keep; P.meta[p] = m; return false; }
+    m.w = OHB_ST_MAKE(stage, bounce) | keep | (lastDelta ? OHB_ST_DELTA : 0u);
     P.meta[p] = m;
     P.thr[p] = mk4(thr, lastPdf);
     P.rayO[p] = mk4(nextO, 0.0f); P.rayD[p] = mk4(nextD, 0.0f);
     return true;
+}
+// Both shading stages back to back (host emulator / single-kernel fallback for tests).
+OHB_HD bool shadePath(const SceneDev& sc, const FrameParams& fr, const PathArrays& P, uint32_t p) {
+    surfacePath(sc, fr, P, p);
+    return bouncePath(sc, fr, P, p);
 }
 
 // ---------------------------------------------------------------------------------------------

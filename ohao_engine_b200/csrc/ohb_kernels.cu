@@ -176,7 +176,9 @@ __global__ void k_env_rows(const f4* env, uint32_t W, uint32_t H, float* cond, f
     uint32_t y = blockIdx.x * blockDim.x + threadIdx.x;
     if (y >= H) return;
     const float pi = 3.14159265358979323846f;
-    float sinTheta = sinf(pi * (float(y) + 0.5f) / float(H));
+    // fp32 argument like the reference; the sine itself is evaluated in fp64 and rounded once so it equals a
+    // correctly rounded sinf (glibc's), which CUDA's 1-2 ulp sinf does not guarantee
+    float sinTheta = float(sin(double(__fdiv_rn(__fmul_rn(pi, float(y) + 0.5f), float(H)))));
     float* row = cond + size_t(y) * W;
     float run = 0.0f;
     for (uint32_t x = 0; x < W; x++) {
@@ -213,49 +215,80 @@ void launchEnvSample(const SceneDev& sc, const float* u12, uint32_t n, f4* dirPd
     k_env_sample<<<gridFor(n, 128), 128, 0, st>>>(sc, u12, n, dirPdf, pdfOfDir); (*launches)++;
 }
 
+__global__ void k_env_pdf(SceneDev sc, const float* dirs3, uint32_t n, float* pdf) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pdf[i] = pdfEnvMap(sc, mk3(dirs3[3 * i], dirs3[3 * i + 1], dirs3[3 * i + 2]));
+}
+void launchEnvPdf(const SceneDev& sc, const float* dirs3, uint32_t n, float* pdf, cudaStream_t st, uint64_t* launches) {
+    k_env_pdf<<<gridFor(n, 128), 128, 0, st>>>(sc, dirs3, n, pdf); (*launches)++;
+}
+
 // =============================================================================================
 // Traversal kernels (persistent, warp-granular dynamic fetch)
 // =============================================================================================
 #define TRACE_THREADS 128
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace_closest(SceneDev sc, PathArrays P, uint32_t* work) {
-    const uint32_t n = *P.countIn;
+#define TRACE_MIN_ACTIVE 20     // pause traversal and refill idle lanes when fewer lanes than this still traverse
+// Persistent warp loop shared by every traversal kernel.  Lanes pull rays one by one from a global counter
+// (warp-aggregated atomic); a lane that finishes its ray waits at the reconvergence point of the `have`
+// block until the traversing lanes either finish or drop below TRACE_MIN_ACTIVE, then all idle lanes are
+// refilled together.  IO = { load(i, o, d, tmin, tmax), store(i, Trav&) }.
+template <bool ANY, class IO>
+__device__ __forceinline__ void persistentTrace(const SceneDev& sc, uint32_t n, uint32_t* work, IO& io) {
     const uint32_t lane = threadIdx.x & 31u;
-    uint32_t hits = 0;
+    Trav t; int32_t stack[OHB_STACK_SIZE]; uint32_t idx = 0; bool have = false, exhausted = false;
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(work, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        uint32_t i = base + lane;
-        if (i < n) {
-            uint32_t p = P.queueIn[i];
-            f4 o = P.rayO[p], d = P.rayD[p];
-            ohb_hit h = traceClosest(sc, xyz(o), xyz(d), 0.001f, 10000.0f);
-            reinterpret_cast<float4*>(P.hit)[p] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
-            hits += (h.prim != OHB_MISS);
-        }
-    }
-    hits = __reduce_add_sync(0xffffffffu, hits);
-    if (lane == 0 && hits) atomicAdd(P.counters + 3, (unsigned long long)hits);
-}
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace_shadow(SceneDev sc, PathArrays P, uint32_t* work) {
-    const uint32_t n = *P.shCount;
-    const uint32_t lane = threadIdx.x & 31u;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(work, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        uint32_t i = base + lane;
-        if (i < n) {
-            f4 o = P.shO[i], d = P.shD[i];
-            if (traceAny(sc, xyz(o), xyz(d), 0.001f, o.w)) {
-                uint32_t tag = __float_as_uint(d.w);
-                f4* pend = (tag & 1u) ? P.pendB : P.pendA;
-                pend[tag >> 1] = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+        unsigned need = __ballot_sync(0xffffffffu, !have && !exhausted);
+        if (need) {
+            uint32_t base = 0;
+            if (lane == uint32_t(__ffs(int(need)) - 1)) base = atomicAdd(work, uint32_t(__popc(need)));
+            base = __shfl_sync(0xffffffffu, base, __ffs(int(need)) - 1);
+            if (!have && !exhausted) {
+                idx = base + uint32_t(__popc(need & ((1u << lane) - 1u)));
+                if (idx < n) { f3 o, d; float tmin, tmax; io.load(idx, o, d, tmin, tmax); travInit(t, sc, o, d, tmin, tmax); have = true; }
+                else exhausted = true;
             }
         }
+        if (!__any_sync(0xffffffffu, have)) break;
+        bool done = false;
+        if (have) done = travRun<ANY>(t, stack, sc, TRACE_MIN_ACTIVE);
+        __syncwarp();
+        if (done) { io.store(idx, t); have = false; }
     }
+}
+
+struct PathClosestIO {
+    PathArrays P; uint32_t hits;
+    __device__ __forceinline__ void load(uint32_t i, f3& o, f3& d, float& tmin, float& tmax) {
+        uint32_t p = P.queueIn[i]; o = xyz(P.rayO[p]); d = xyz(P.rayD[p]); tmin = 0.001f; tmax = 10000.0f;
+    }
+    __device__ __forceinline__ void store(uint32_t i, Trav& t) {
+        uint32_t p = P.queueIn[i];
+        bool hit = t.best.prim != OHB_MISS;
+        reinterpret_cast<float4*>(P.hit)[p] = make_float4(hit ? t.best.t : -1.0f, t.best.u, t.best.v, __uint_as_float(t.best.prim));
+        hits += hit;
+    }
+};
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_closest(SceneDev sc, PathArrays P, uint32_t* work) {
+    PathClosestIO io{P, 0u};
+    persistentTrace<false>(sc, *P.countIn, work, io);
+    uint32_t hits = __reduce_add_sync(0xffffffffu, io.hits);
+    if ((threadIdx.x & 31u) == 0 && hits) atomicAdd(P.counters + 3, (unsigned long long)hits);
+}
+struct PathShadowIO {
+    PathArrays P;
+    __device__ __forceinline__ void load(uint32_t i, f3& o, f3& d, float& tmin, float& tmax) {
+        f4 a = P.shO[i], b = P.shD[i]; o = xyz(a); d = xyz(b); tmin = 0.001f; tmax = a.w;
+    }
+    __device__ __forceinline__ void store(uint32_t i, Trav& t) {
+        if (!t.anyHit) return;
+        uint32_t tag = __float_as_uint(P.shD[i].w);
+        f4* pend = (tag & 1u) ? P.pendB : P.pendA;
+        pend[tag >> 1] = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+};
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_shadow(SceneDev sc, PathArrays P, uint32_t* work) {
+    PathShadowIO io{P};
+    persistentTrace<true>(sc, *P.shCount, work, io);
 }
 #define SHADE_THREADS 128
 __global__ void __launch_bounds__(SHADE_THREADS) k_raygen(FrameParams fr, PathArrays P, uint32_t total) {
@@ -264,11 +297,16 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_raygen(FrameParams fr, PathAr
     raygenPath(fr, P, p);
     if (OHB_ST_STAGE(P.meta[p].w) != ST_DONE) { uint32_t q = alloc_slot(P.countIn); P.queueIn[q] = p; }
 }
-__global__ void __launch_bounds__(SHADE_THREADS) k_shade(SceneDev sc, FrameParams fr, PathArrays P) {
+__global__ void __launch_bounds__(SHADE_THREADS) k_surface(SceneDev sc, FrameParams fr, PathArrays P) {
+    const uint32_t n = *P.countIn;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        surfacePath(sc, fr, P, P.queueIn[i]);
+}
+__global__ void __launch_bounds__(SHADE_THREADS) k_bounce(SceneDev sc, FrameParams fr, PathArrays P) {
     const uint32_t n = *P.countIn;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         uint32_t p = P.queueIn[i];
-        if (shadePath(sc, fr, P, p)) { uint32_t q = alloc_slot(P.countOut); P.queueOut[q] = p; }
+        if (bouncePath(sc, fr, P, p)) { uint32_t q = alloc_slot(P.countOut); P.queueOut[q] = p; }
     }
 }
 // Between iterations: account the rays just traced, clear the queues that are about to be refilled.
@@ -307,14 +345,17 @@ void launchOfflineBatch(const SceneDev& sc, const FrameParams& fr, PathArrays P,
         if (th) th->begin(0, st);
         k_trace_closest<<<traceGrid, TRACE_THREADS, 0, st>>>(sc, P, work);
         if (th) th->end(0, st);
+        if (th) th->begin(4, st);
+        k_surface<<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P);
+        if (th) th->end(4, st);
         if (th) th->begin(1, st);
-        k_shade<<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P);
+        k_bounce<<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P);
         if (th) th->end(1, st);
         if (th) th->begin(2, st);
         k_trace_shadow<<<traceGrid, TRACE_THREADS, 0, st>>>(sc, P, work + 1);
         if (th) th->end(2, st);
         k_advance<<<1, 32, 0, st>>>(P, work, 0);
-        *launches += 4;
+        *launches += 5;
         // ping-pong the path queues
         uint32_t* tq = P.queueIn; P.queueIn = P.queueOut; P.queueOut = tq;
         uint32_t* tc = P.countIn; P.countIn = P.countOut; P.countOut = tc;
@@ -328,33 +369,23 @@ void launchResolve(f4* accum, uint32_t* ldr, uint32_t n, int sumMode, cudaStream
 }
 
 // ---- parity hooks: trace caller-supplied rays ---------------------------------------------------
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace_batch(SceneDev sc, const ohb_ray* rays, uint32_t n, ohb_hit* hits, uint32_t* work) {
-    const uint32_t lane = threadIdx.x & 31u;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(work, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        uint32_t i = base + lane;
-        if (i < n) {
-            ohb_ray r = rays[i];
-            hits[i] = traceClosest(sc, mk3(r.origin[0], r.origin[1], r.origin[2]), mk3(r.dir[0], r.dir[1], r.dir[2]), r.tmin, r.tmax);
-        }
+struct HookIO {
+    const ohb_ray* rays; ohb_hit* hits; uint8_t* occ;
+    __device__ __forceinline__ void load(uint32_t i, f3& o, f3& d, float& tmin, float& tmax) {
+        ohb_ray r = rays[i]; o = mk3(r.origin[0], r.origin[1], r.origin[2]); d = mk3(r.dir[0], r.dir[1], r.dir[2]); tmin = r.tmin; tmax = r.tmax;
     }
+    __device__ __forceinline__ void store(uint32_t i, Trav& t) {
+        if (hits) { ohb_hit h = t.best; if (h.prim == OHB_MISS) h.t = -1.0f; hits[i] = h; }
+        else occ[i] = t.anyHit ? 1 : 0;
+    }
+};
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_batch(SceneDev sc, const ohb_ray* rays, uint32_t n, ohb_hit* hits, uint32_t* work) {
+    HookIO io{rays, hits, nullptr};
+    persistentTrace<false>(sc, n, work, io);
 }
 __global__ void __launch_bounds__(TRACE_THREADS) k_occluded_batch(SceneDev sc, const ohb_ray* rays, uint32_t n, uint8_t* occ, uint32_t* work) {
-    const uint32_t lane = threadIdx.x & 31u;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(work, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        uint32_t i = base + lane;
-        if (i < n) {
-            ohb_ray r = rays[i];
-            occ[i] = traceAny(sc, mk3(r.origin[0], r.origin[1], r.origin[2]), mk3(r.dir[0], r.dir[1], r.dir[2]), r.tmin, r.tmax) ? 1 : 0;
-        }
-    }
+    HookIO io{rays, nullptr, occ};
+    persistentTrace<true>(sc, n, work, io);
 }
 void launchTraceBatch(const SceneDev& sc, const ohb_ray* rays, uint32_t n, ohb_hit* hits, uint8_t* occ, uint32_t* work, int numSMs, cudaStream_t st, uint64_t* launches) {
     k_zero_u32<<<1, 32, 0, st>>>(work, 2);

@@ -635,6 +635,10 @@ void orc_env_sample_batch(void* h, const float* u12, uint32_t n, float* dir_pdf,
         if (pdf_of_dir) pdf_of_dir[i] = pdfEnvMap(*s, d);
     }
 }
+void orc_env_pdf_batch(void* h, const float* dirs3, uint32_t n, float* pdf) {
+    Scene* s = (Scene*)h;
+    for (uint32_t i = 0; i < n; i++) pdf[i] = pdfEnvMap(*s, V3{dirs3[3 * i], dirs3[3 * i + 1], dirs3[3 * i + 2]});
+}
 float orc_sampler_1d(uint32_t sampler_type, uint32_t px, uint32_t py, uint32_t sample_idx, uint32_t dim) {
     Sampler sm; sm.init(sampler_type, px, py, sample_idx); return sm.get1D(dim);
 }

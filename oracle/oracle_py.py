@@ -80,6 +80,7 @@ def lib() -> C.CDLL:
         _LIB.orc_env_cdf.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
         _LIB.orc_scene_env_cdf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
         _LIB.orc_env_sample_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        _LIB.orc_env_pdf_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         _LIB.orc_set_ray_recorder.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         _LIB.orc_ray_recorder_count.restype = C.c_uint32
         _LIB.orc_scene_set_materials.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
@@ -187,6 +188,11 @@ class OracleScene:
         dp = np.zeros((n, 4), np.float32); pd = np.zeros(n, np.float32)
         lib().orc_env_sample_batch(self.h, _p(u), n, _p(dp), _p(pd))
         return dp, pd
+
+    def env_pdf(self, dirs):
+        d = np.ascontiguousarray(dirs, np.float32); pd = np.zeros(len(d), np.float32)
+        lib().orc_env_pdf_batch(self.h, _p(d), len(d), _p(pd))
+        return pd
 
     def record_rays(self, view, proj, width, height, nsamples, tile, cap=1 << 20, settings=None, first_sample=0):
         rays = np.zeros(cap, RAY_DTYPE); hits = np.zeros(cap, HIT_DTYPE); kinds = np.zeros(cap, np.uint8)

@@ -178,7 +178,7 @@ int emul_render_offline(void* h, emul_render_args* a) {
     fr.tileX = a->tile_x; fr.tileY = a->tile_y; fr.tileW = a->tile_w ? a->tile_w : a->width; fr.tileH = a->tile_h ? a->tile_h : a->height;
     uint32_t tilesX = (fr.tileW + 7u) / 8u, tilesY = (fr.tileH + 3u) / 4u, numPixels = tilesX * tilesY * 32u;
     uint32_t total = numPixels * a->nsamples;
-    std::vector<f4> rayO(total), rayD(total), thr(total), rad(total), pendA(total), pendB(total), fh0(total), fh1(total), fh2(total), fh3(total), shO(size_t(total) * 2), shD(size_t(total) * 2);
+    std::vector<f4> rayO(total), rayD(total), thr(total), rad(total), pendA(total), pendB(total), fh0(total), fh1(total), fh2(total), fh3(total), pay0(total), pay1(total), pay2(total), pay3(total), shO(size_t(total) * 2), shD(size_t(total) * 2);
     std::vector<ohb_hit> hit(total); std::vector<u4> meta(total); std::vector<uint32_t> qa(total), qb(total);
     uint32_t small[4] = {0, 0, 0, 0}; unsigned long long counters[8] = {0};
     size_t npx = size_t(a->width) * a->height;
@@ -186,7 +186,7 @@ int emul_render_offline(void* h, emul_render_args* a) {
     memcpy(accum.data(), a->accum, npx * 16);
     PathArrays P{};
     P.rayO = rayO.data(); P.rayD = rayD.data(); P.hit = hit.data(); P.thr = thr.data(); P.rad = rad.data(); P.pendA = pendA.data(); P.pendB = pendB.data(); P.meta = meta.data();
-    P.fh0 = fh0.data(); P.fh1 = fh1.data(); P.fh2 = fh2.data(); P.fh3 = fh3.data(); P.shO = shO.data(); P.shD = shD.data();
+    P.fh0 = fh0.data(); P.fh1 = fh1.data(); P.fh2 = fh2.data(); P.fh3 = fh3.data(); P.pay0 = pay0.data(); P.pay1 = pay1.data(); P.pay2 = pay2.data(); P.pay3 = pay3.data(); P.shO = shO.data(); P.shD = shD.data();
     P.queueIn = qa.data(); P.queueOut = qb.data(); P.countIn = &small[0]; P.countOut = &small[1]; P.shCount = &small[2]; P.counters = counters;
     P.albedoAOV = albedo.data(); P.normalAOV = normal.data(); P.numPixels = numPixels; P.samplesInBatch = a->nsamples; P.firstSampleIndex = a->first_sample_index;
     for (uint32_t p = 0; p < total; p++) { raygenPath(fr, P, p); if (OHB_ST_STAGE(P.meta[p].w) != ST_DONE) P.queueIn[(*P.countIn)++] = p; }
@@ -195,7 +195,8 @@ int emul_render_offline(void* h, emul_render_args* a) {
     for (uint32_t it = 0; it < iters; it++) {
         uint32_t n = *P.countIn;
         for (uint32_t i = 0; i < n; i++) { uint32_t p = P.queueIn[i]; P.hit[p] = traceClosest(sc, xyz(P.rayO[p]), xyz(P.rayD[p]), 0.001f, 10000.0f); counters[3] += P.hit[p].prim != OHB_MISS; }
-        for (uint32_t i = 0; i < n; i++) { uint32_t p = P.queueIn[i]; if (shadePath(sc, fr, P, p)) P.queueOut[(*P.countOut)++] = p; }
+        for (uint32_t i = 0; i < n; i++) surfacePath(sc, fr, P, P.queueIn[i]);                                                       // k_surface
+        for (uint32_t i = 0; i < n; i++) { uint32_t p = P.queueIn[i]; if (bouncePath(sc, fr, P, p)) P.queueOut[(*P.countOut)++] = p; }   // k_bounce
         uint32_t ns = *P.shCount;
         for (uint32_t i = 0; i < ns; i++) {
             f4 o = P.shO[i], d = P.shD[i];
