@@ -85,7 +85,7 @@ struct ohb_ctx {
     DevBuf activeTris, wtri, primLo, primHi, boundsBits, keys, vals, keysTmp, valsTmp, sortTemp, left, right, parentInner, parentLeaf,
            rangeFirst, rangeLast, nodeLo, nodeHi, visit, newIndex, emitCounter, sah, nodes, tris;
     // paths (device)
-    DevBuf rayO, rayD, hit, thr, rad, pendA, pendB, meta, fh0, fh1, fh2, fh3, pay0, pay1, pay2, pay3, shO, shD, queueA, queueB, smallCounters, devCounters;
+    DevBuf rayO, rayD, hit, thr, rad, pendA, pendB, meta, fh0, fh1, fh2, fh3, pay0, pay1, pay2, pay3, shO, shD, queueA, queueB, queueS, sobolTab, smallCounters, devCounters;
     uint32_t pathCapacity = 0;
     // film
     DevBuf accum, ldr, albedoAOV, normalAOV, sampleDump;
@@ -163,7 +163,7 @@ void ohb_destroy(ohb_ctx* c) {
                      &c->tex, &c->lights, &c->env, &c->marg, &c->cond, &c->rowTotal, &c->integral, &c->activeTris, &c->wtri, &c->primLo, &c->primHi, &c->boundsBits,
                      &c->keys, &c->vals, &c->keysTmp, &c->valsTmp, &c->sortTemp, &c->left, &c->right, &c->parentInner, &c->parentLeaf, &c->rangeFirst, &c->rangeLast,
                      &c->nodeLo, &c->nodeHi, &c->visit, &c->newIndex, &c->emitCounter, &c->sah, &c->nodes, &c->tris, &c->rayO, &c->rayD, &c->hit, &c->thr, &c->rad,
-                     &c->pendA, &c->pendB, &c->meta, &c->fh0, &c->fh1, &c->fh2, &c->fh3, &c->pay0, &c->pay1, &c->pay2, &c->pay3, &c->shO, &c->shD, &c->queueA, &c->queueB, &c->smallCounters, &c->devCounters,
+                     &c->pendA, &c->pendB, &c->meta, &c->fh0, &c->fh1, &c->fh2, &c->fh3, &c->pay0, &c->pay1, &c->pay2, &c->pay3, &c->shO, &c->shD, &c->queueA, &c->queueB, &c->queueS, &c->sobolTab, &c->smallCounters, &c->devCounters,
                      &c->accum, &c->ldr, &c->albedoAOV, &c->normalAOV, &c->sampleDump, &c->hookRays, &c->hookOut, &c->hookAux};
     for (DevBuf* b : all) b->release();
     if (c->evA) cudaEventDestroy(c->evA);
@@ -433,7 +433,7 @@ static int ensurePaths(ohb_ctx* c, uint32_t cap) {
     CU(c, c->pendA.reserve(n * 16)); CU(c, c->pendB.reserve(n * 16)); CU(c, c->meta.reserve(n * 16));
     CU(c, c->fh0.reserve(n * 16)); CU(c, c->fh1.reserve(n * 16)); CU(c, c->fh2.reserve(n * 16)); CU(c, c->fh3.reserve(n * 16));
     CU(c, c->pay0.reserve(n * 16)); CU(c, c->pay1.reserve(n * 16)); CU(c, c->pay2.reserve(n * 16)); CU(c, c->pay3.reserve(n * 16));
-    CU(c, c->shO.reserve(n * 32)); CU(c, c->shD.reserve(n * 32)); CU(c, c->queueA.reserve(n * 4)); CU(c, c->queueB.reserve(n * 4));
+    CU(c, c->shO.reserve(n * 32)); CU(c, c->shD.reserve(n * 32)); CU(c, c->queueA.reserve(n * 4)); CU(c, c->queueB.reserve(n * 4)); CU(c, c->queueS.reserve(n * 4));
     c->pathCapacity = cap;
     return 0;
 }
@@ -464,6 +464,7 @@ int ohb_render(ohb_ctx* c, const float view[16], const float proj[16], uint32_t 
     static const uint32_t maxPaths = []() { const char* e = getenv("OHB_MAX_PATHS"); uint32_t v = e ? uint32_t(strtoul(e, nullptr, 10)) : 0u; return v ? v : (8u << 20); }();
     uint32_t spb = std::max(1u, std::min(nsamples, maxPaths / std::max(numPixels, 1u)));
     if (ensurePaths(c, numPixels * spb)) return 1;
+    CU(c, c->sobolTab.reserve(size_t(spb) * 16));
     SceneDev s; fillScene(c, s);
     float* dumpDev = nullptr;
     if (c->dumpHost) {
@@ -487,6 +488,7 @@ int ohb_render(ohb_ctx* c, const float view[16], const float proj[16], uint32_t 
         P.counters = c->devCounters.as<unsigned long long>();
         P.albedoAOV = c->albedoAOV.as<f4>(); P.normalAOV = c->normalAOV.as<f4>();
         P.numPixels = numPixels; P.samplesInBatch = k; P.firstSampleIndex = c->sampleIndex;
+        P.sobolTab = c->sobolTab.as<u4>(); P.queueSorted = c->queueS.as<uint32_t>(); P.sortCount = small + 12;
         FilmArrays F{};
         F.accum = c->accum.as<f4>(); F.ldr = c->ldr.as<uint32_t>(); F.historyCount = c->historyCount; F.sumMode = c->sumMode;
         F.sampleDump = dumpDev ? dumpDev + size_t(done) * c->W * c->H * 4u : nullptr;

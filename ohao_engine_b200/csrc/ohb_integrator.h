@@ -38,11 +38,13 @@ struct PathArrays {
     f4* shO; f4* shD;              // visibility-ray queue: (origin, tmax) (dir, bits(path << 1 | slot))
     uint32_t* shCount;
     uint32_t* queueIn; uint32_t* queueOut; uint32_t* countIn; uint32_t* countOut;
+    uint32_t* queueSorted; uint32_t* sortCount;   // k_surface re-emits queueIn two-ended: hits from the front, misses from the back; sortCount[0..1]
     unsigned long long* counters;  // [0] samples [1] closest rays [2] shadow rays [3] closest hits
     f4* albedoAOV; f4* normalAOV;  // W*H images (first hit of the last sample rendered)
     uint32_t numPixels;            // pixels in the tile
     uint32_t samplesInBatch;
     uint32_t firstSampleIndex;     // sample index of s = 0
+    const u4* sobolTab;            // samplesInBatch entries: sobolQuad(firstSampleIndex + s)
 };
 
 struct Payload { f3 color, attenuation, hitPos, hitNormal, hitAlbedo; float hitDist, envPdf; };
@@ -335,7 +337,7 @@ OHB_HD void raygenPath(const FrameParams& fr, const PathArrays& P, uint32_t p) {
     }
     uint32_t px = fr.tileX + lx, py = fr.tileY + ly;
     m.x = px | (py << 16);
-    Sampler sm; sm.init(fr.samplerType, px, py, m.y);
+    Sampler sm; sm.init(fr.samplerType, px, py, m.y, ldu4(P.sobolTab + s));
     f2 j = sm.get2D(0u);
     float uvx = (float(px) + 0.5f + (j.x - 0.5f) + fr.jitX) / float(fr.W), uvy = (float(py) + 0.5f + (j.y - 0.5f) + fr.jitY) / float(fr.H);
     float nx = uvx * 2.0f - 1.0f, ny = uvy * 2.0f - 1.0f;
@@ -348,17 +350,20 @@ OHB_HD void raygenPath(const FrameParams& fr, const PathArrays& P, uint32_t p) {
 }
 
 // k_surface: the closest-hit / miss shader of path p's last query -> payload record.
-OHB_HD void surfacePath(const SceneDev& sc, const FrameParams& fr, const PathArrays& P, uint32_t p) {
+// Returns true for a hit (the caller sorts hits to the front of queueSorted, misses to the back).
+OHB_HD bool surfacePath(const SceneDev& sc, const FrameParams& fr, const PathArrays& P, uint32_t p) {
     f3 o = xyz(P.rayO[p]), d = xyz(P.rayD[p]);
     ohb_hit h = P.hit[p];
     Payload pl;
     if (h.prim == OHB_MISS) {
         missShader(sc, fr, d, pl);
         P.pay0[p] = mk4(pl.color, -1.0f); P.pay1[p] = mk4(pl.envPdf, 0.0f, 0.0f, 0.0f);
+        return false;
     } else {
         closestHitShader(sc, o, d, h, pl);
         P.pay0[p] = mk4(pl.hitPos, pl.hitDist); P.pay1[p] = mk4(pl.hitNormal, pl.attenuation.x);
         P.pay2[p] = mk4(pl.hitAlbedo, pl.attenuation.y); P.pay3[p] = mk4(pl.color, pl.attenuation.z);
+        return true;
     }
 }
 
@@ -379,7 +384,7 @@ OHB_HD bool bouncePath(const SceneDev& sc, const FrameParams& fr, const PathArra
     u4 m = P.meta[p];
     cx.path = p; cx.state = m.w;
     uint32_t px = m.x & 0xFFFFu, py = m.x >> 16;
-    cx.sm.init(fr.samplerType, px, py, m.y);
+    cx.sm.init(fr.samplerType, px, py, m.y, ldu4(P.sobolTab + (m.y - P.firstSampleIndex)));
     if (fr.samplerType == OHB_SAMPLER_PCG) { cx.sm.pcg = m.z; cx.dimIdx = 0u; } else cx.dimIdx = m.z;
     f3 rad = xyz(P.rad[p]);
     if (cx.state & OHB_ST_PEND_A) rad += xyz(P.pendA[p]);

@@ -184,7 +184,11 @@ int emul_render_offline(void* h, emul_render_args* a) {
     size_t npx = size_t(a->width) * a->height;
     std::vector<f4> albedo(npx), normal(npx), accum(npx); std::vector<uint32_t> ldr(npx);
     memcpy(accum.data(), a->accum, npx * 16);
+    std::vector<u4> sobolTab(a->nsamples);
+    for (uint32_t i = 0; i < a->nsamples; i++) sobolTab[i] = sobolQuad(a->first_sample_index + i);
+    std::vector<uint32_t> qs(total); uint32_t sortCount[2] = {0, 0};
     PathArrays P{};
+    P.sobolTab = sobolTab.data(); P.queueSorted = qs.data(); P.sortCount = sortCount;
     P.rayO = rayO.data(); P.rayD = rayD.data(); P.hit = hit.data(); P.thr = thr.data(); P.rad = rad.data(); P.pendA = pendA.data(); P.pendB = pendB.data(); P.meta = meta.data();
     P.fh0 = fh0.data(); P.fh1 = fh1.data(); P.fh2 = fh2.data(); P.fh3 = fh3.data(); P.pay0 = pay0.data(); P.pay1 = pay1.data(); P.pay2 = pay2.data(); P.pay3 = pay3.data(); P.shO = shO.data(); P.shD = shD.data();
     P.queueIn = qa.data(); P.queueOut = qb.data(); P.countIn = &small[0]; P.countOut = &small[1]; P.shCount = &small[2]; P.counters = counters;
@@ -195,8 +199,12 @@ int emul_render_offline(void* h, emul_render_args* a) {
     for (uint32_t it = 0; it < iters; it++) {
         uint32_t n = *P.countIn;
         for (uint32_t i = 0; i < n; i++) { uint32_t p = P.queueIn[i]; P.hit[p] = traceClosest(sc, xyz(P.rayO[p]), xyz(P.rayD[p]), 0.001f, 10000.0f); counters[3] += P.hit[p].prim != OHB_MISS; }
-        for (uint32_t i = 0; i < n; i++) surfacePath(sc, fr, P, P.queueIn[i]);                                                       // k_surface
-        for (uint32_t i = 0; i < n; i++) { uint32_t p = P.queueIn[i]; if (bouncePath(sc, fr, P, p)) P.queueOut[(*P.countOut)++] = p; }   // k_bounce
+        sortCount[0] = sortCount[1] = 0;
+        for (uint32_t i = 0; i < n; i++) {                                                                                               // k_surface
+            uint32_t p = P.queueIn[i];
+            if (surfacePath(sc, fr, P, p)) P.queueSorted[sortCount[0]++] = p; else P.queueSorted[n - 1u - sortCount[1]++] = p;
+        }
+        for (uint32_t i = 0; i < n; i++) { uint32_t p = P.queueSorted[i]; if (bouncePath(sc, fr, P, p)) P.queueOut[(*P.countOut)++] = p; }   // k_bounce
         uint32_t ns = *P.shCount;
         for (uint32_t i = 0; i < ns; i++) {
             f4 o = P.shO[i], d = P.shD[i];
