@@ -44,9 +44,10 @@ enum { OHB_SAMPLER_PCG = 0, OHB_SAMPLER_SOBOL = 1 };
 #define OHB_FLAG_ENABLE_AOVS             (1u << 0)
 #define OHB_FLAG_ENABLE_INTERNAL_DENOISE (1u << 1)
 #define OHB_FLAG_ENABLE_FIREFLY_CLAMP    (1u << 2)
-#define OHB_FLAG_RESTIRGI_LEGACY         (1u << 5)
-#define OHB_FLAG_RESTIRGI_NO_TEMPORAL    (1u << 6)
-#define OHB_FLAG_RESTIRGI_NO_SPATIAL     (1u << 7)
+#define OHB_FLAG_RESTIRGI_OFF            (1u << 5)   /* no temporal / spatial reuse (M = 1 anchor)          */
+#define OHB_FLAG_RESTIRGI_GIONLY         (1u << 6)   /* measurement bit of the reference; affects NRD AOVs only */
+#define OHB_FLAG_RESTIRGI_LEGACY         (1u << 7)   /* reference's multi-bounce Stage C escape hatch: NOT implemented, ohb_render refuses it */
+#define OHB_FLAG_RESTIRGI_NOSPATIAL      (1u << 8)   /* temporal-only                                       */
 /* Not a reference flag: reproduces the integrator revision that rendered the reference's
  * committed golden image tests/golden/cornell_box.png (Stage C spec-lobe continuation uses
  * mix(1,albedo,metallic) like Stage B instead of HEAD's albedo*(1-metallic),
@@ -153,7 +154,8 @@ void     ohb_reset_accumulation(ohb_ctx*);             /* m_sampleIndex = seed, 
 void     ohb_notify_view_changed(ohb_ctx*);
 uint32_t ohb_frame_index(const ohb_ctx*);              /* getFrameIndex(): current sample index   */
 /* One call == `nsamples` consecutive PathTracer::render() calls with this view/proj
- * (offline: sample indices advance by nsamples; realtime: nsamples must be 1 frame).
+ * (offline: sample indices advance by nsamples, one spp each; realtime: nsamples FRAMES of
+ * settings.samples_per_frame spp each — ReSTIR GI temporal + spatial reuse, reprojected EMA, a-trous).
  * Asynchronous w.r.t. the host like vkQueueSubmit; readbacks synchronise. */
 int ohb_render(ohb_ctx*, const float view[16], const float proj[16], uint32_t nsamples);
 /* Restrict offline rendering to a pixel rectangle (multi-GPU tile sharding, §8e). Default: full frame. */
@@ -186,6 +188,13 @@ int ohb_enable_timing(ohb_ctx*, int enable);
 /* Per-category device time and launch count: [0] closest-hit traversal, [1] bounce (raygen body: NEE, MIS,
  * lobe sampling), [2] any-hit traversal, [3] film, [4] surface (closest-hit / miss shaders), [5..7] reserved. */
 int ohb_get_timing_detail(ohb_ctx*, float ms[8], uint64_t launches[8]);
+/* Realtime-profile parity hooks.  ohb_set_realtime_dump: the next ohb_render also copies, per pixel, the N-spp mean
+ * radiance after the x0.75 clamp (pt_raygen_realtime.rgen:1552-1556), the diffuse ReSTIR GI term (:1755-1764) and the
+ * a-trous output (:1850-1912) into the given host buffers (W*H*4 floats each, any may be NULL).
+ * ohb_read_realtime_state: the reservoir planes written by the last frame (bindings 32-34: (x_s, M) (n_s, W) (Lo, valid))
+ * and the surface / shading history (bindings 14/16). */
+int ohb_set_realtime_dump(ohb_ctx*, float* radiance_rgba, float* gi_rgba, float* denoised_rgba);
+int ohb_read_realtime_state(ohb_ctx*, float* res0, float* res1, float* res2, float* surface_history, float* shading_history);
 /* Whole-region device timer: two CUDA events recorded on the context's stream (the stream every
  * kernel of this context is launched on).  ohb_timer_stop synchronises and returns the elapsed ms. */
 int ohb_timer_start(ohb_ctx*);

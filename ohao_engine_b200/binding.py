@@ -81,6 +81,8 @@ ABI = {
     "ohb_get_timing": (_I, [_VP, C.POINTER(_F), C.POINTER(_F), C.POINTER(_F)]),
     "ohb_get_timing_detail": (_I, [_VP, C.POINTER(_F * 8), C.POINTER(C.c_uint64 * 8)]),
     "ohb_enable_timing": (_I, [_VP, _I]),
+    "ohb_set_realtime_dump": (_I, [_VP, _VP, _VP, _VP]),
+    "ohb_read_realtime_state": (_I, [_VP, _VP, _VP, _VP, _VP, _VP]),
     "ohb_timer_start": (_I, [_VP]),
     "ohb_timer_stop": (_I, [_VP, C.POINTER(_F)]),
 }
@@ -255,6 +257,26 @@ class Renderer:
 
     def reset_counters(self): self.lib.ohb_reset_counters(self.h)
     def enable_timing(self, on: bool = True): self._ck(self.lib.ohb_enable_timing(self.h, int(on)), "ohb_enable_timing")
+
+    def render_realtime(self, view, proj, dumps: bool = False):
+        """One realtime frame (profile REALTIME).  With dumps=True also returns the parity dumps."""
+        v = np.ascontiguousarray(view, np.float32); p = np.ascontiguousarray(proj, np.float32)
+        out = {}
+        if dumps:
+            out = {k: np.zeros((self.height, self.width, 4), np.float32) for k in ("radiance", "gi", "denoised")}
+            self._ck(self.lib.ohb_set_realtime_dump(self.h, _p(out["radiance"]), _p(out["gi"]), _p(out["denoised"])), "ohb_set_realtime_dump")
+        try:
+            self._ck(self.lib.ohb_render(self.h, _p(v), _p(p), 1), "ohb_render")
+        finally:
+            if dumps:
+                self.lib.ohb_set_realtime_dump(self.h, None, None, None)
+        return out
+
+    def realtime_state(self):
+        z = lambda: np.zeros((self.height, self.width, 4), np.float32)
+        r0, r1, r2, su, sh = z(), z(), z(), z(), z()
+        self._ck(self.lib.ohb_read_realtime_state(self.h, _p(r0), _p(r1), _p(r2), _p(su), _p(sh)), "ohb_read_realtime_state")
+        return dict(reservoirs=[r0, r1, r2], surf=su, shad=sh)
 
     def timer_start(self): self._ck(self.lib.ohb_timer_start(self.h), "ohb_timer_start")
 

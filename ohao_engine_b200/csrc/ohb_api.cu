@@ -89,6 +89,10 @@ struct ohb_ctx {
     uint32_t pathCapacity = 0;
     // film
     DevBuf accum, ldr, albedoAOV, normalAOV, sampleDump;
+    // realtime profile: ping-ponged history (index rtCur = the images written by the last frame)
+    DevBuf accumPrev, surf[2], shad[2], res[2][3], rtDump[3];
+    int rtCur = 0; float prevViewProj[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    float* rtDumpHost[3] = {nullptr, nullptr, nullptr};
     float* dumpHost = nullptr; size_t dumpCapacity = 0;
     // hooks
     DevBuf hookRays, hookOut, hookAux;
@@ -102,12 +106,23 @@ struct ohb_ctx {
 static int ensureFilm(ohb_ctx* c) {
     size_t n = size_t(c->W) * c->H;
     CU(c, c->accum.reserve(n * 16)); CU(c, c->ldr.reserve(n * 4)); CU(c, c->albedoAOV.reserve(n * 16)); CU(c, c->normalAOV.reserve(n * 16));
+    if (c->profile == OHB_PROFILE_REALTIME) {
+        CU(c, c->accumPrev.reserve(n * 16));
+        for (int i = 0; i < 2; i++) { CU(c, c->surf[i].reserve(n * 16)); CU(c, c->shad[i].reserve(n * 16)); for (int k = 0; k < 3; k++) CU(c, c->res[i][k].reserve(n * 16)); }
+    }
     return 0;
 }
 static int clearFilm(ohb_ctx* c) {
     size_t n = size_t(c->W) * c->H;
     CU(c, cudaMemsetAsync(c->accum.p, 0, n * 16, c->stream)); CU(c, cudaMemsetAsync(c->ldr.p, 0, n * 4, c->stream));
     CU(c, cudaMemsetAsync(c->albedoAOV.p, 0, n * 16, c->stream)); CU(c, cudaMemsetAsync(c->normalAOV.p, 0, n * 16, c->stream));
+    if (c->profile == OHB_PROFILE_REALTIME) {
+        CU(c, cudaMemsetAsync(c->accumPrev.p, 0, n * 16, c->stream));
+        for (int i = 0; i < 2; i++) {
+            CU(c, cudaMemsetAsync(c->surf[i].p, 0, n * 16, c->stream)); CU(c, cudaMemsetAsync(c->shad[i].p, 0, n * 16, c->stream));
+            for (int k = 0; k < 3; k++) CU(c, cudaMemsetAsync(c->res[i][k].p, 0, n * 16, c->stream));
+        }
+    }
     return 0;
 }
 static void defaultSettings(ohb_ctx* c) {
@@ -164,7 +179,9 @@ void ohb_destroy(ohb_ctx* c) {
                      &c->keys, &c->vals, &c->keysTmp, &c->valsTmp, &c->sortTemp, &c->left, &c->right, &c->parentInner, &c->parentLeaf, &c->rangeFirst, &c->rangeLast,
                      &c->nodeLo, &c->nodeHi, &c->visit, &c->newIndex, &c->emitCounter, &c->sah, &c->nodes, &c->tris, &c->rayO, &c->rayD, &c->hit, &c->thr, &c->rad,
                      &c->pendA, &c->pendB, &c->meta, &c->fh0, &c->fh1, &c->fh2, &c->fh3, &c->pay0, &c->pay1, &c->pay2, &c->pay3, &c->shO, &c->shD, &c->queueA, &c->queueB, &c->queueS, &c->sobolTab, &c->smallCounters, &c->devCounters,
-                     &c->accum, &c->ldr, &c->albedoAOV, &c->normalAOV, &c->sampleDump, &c->hookRays, &c->hookOut, &c->hookAux};
+                     &c->accum, &c->ldr, &c->albedoAOV, &c->normalAOV, &c->sampleDump, &c->hookRays, &c->hookOut, &c->hookAux,
+                     &c->accumPrev, &c->surf[0], &c->surf[1], &c->shad[0], &c->shad[1], &c->res[0][0], &c->res[0][1], &c->res[0][2],
+                     &c->res[1][0], &c->res[1][1], &c->res[1][2], &c->rtDump[0], &c->rtDump[1], &c->rtDump[2]};
     for (DevBuf* b : all) b->release();
     if (c->evA) cudaEventDestroy(c->evA);
     if (c->evB) cudaEventDestroy(c->evB);
@@ -405,6 +422,7 @@ int ohb_get_accel_stats(ohb_ctx* c, ohb_accel_stats* s) { if (!c || !s) return 1
 int ohb_set_settings(ohb_ctx* c, const ohb_settings* s) {
     if (!c || !s) return 1;
     if ((s->max_bounces & 0xFFFFu) > 15u) OHB_FAIL(c, "ohb_set_settings: max_bounces > 15");
+    if (s->profile == OHB_PROFILE_REALTIME && c->profile != OHB_PROFILE_REALTIME) OHB_FAIL(c, "ohb_set_settings: realtime settings need a context created with OHB_PROFILE_REALTIME");
     c->settings = *s;
     uint32_t spf = s->samples_per_frame; c->settings.samples_per_frame = spf < 1u ? 1u : (spf > 64u ? 64u : spf);   // clampSamplesPerFrame
     return 0;
@@ -426,7 +444,7 @@ int ohb_set_tile(ohb_ctx* c, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h) {
     return 0;
 }
 
-static int ensurePaths(ohb_ctx* c, uint32_t cap) {
+int ensurePaths(ohb_ctx* c, uint32_t cap) {
     if (cap <= c->pathCapacity) return 0;
     size_t n = cap;
     CU(c, c->rayO.reserve(n * 16)); CU(c, c->rayD.reserve(n * 16)); CU(c, c->hit.reserve(n * 16)); CU(c, c->thr.reserve(n * 16)); CU(c, c->rad.reserve(n * 16));
@@ -438,16 +456,8 @@ static int ensurePaths(ohb_ctx* c, uint32_t cap) {
     return 0;
 }
 
-int ohb_render(ohb_ctx* c, const float view[16], const float proj[16], uint32_t nsamples) {
-    if (!c) return 1;
-    if (!view || !proj) OHB_FAIL(c, "ohb_render: null matrix");
-    if (!c->accelValid) { c->err = "ohb_render: no acceleration structure (call ohb_build_accel)"; return 1; }   // reference: silent return (path_tracer_render.cpp:42)
-    if (!c->nmat) OHB_FAIL(c, "ohb_render: no materials");
-    if (c->settings.profile != OHB_PROFILE_OFFLINE) OHB_FAIL(c, "ohb_render: realtime profile is not available in this build");
-    if (nsamples == 0) return 0;
-    cudaSetDevice(c->device);
+static void fillFrameCommon(ohb_ctx* c, const float* view, const float* proj, FrameParams& fr) {
     M4h iv = inverse4(view), ip = inverse4(proj);
-    FrameParams fr{};
     fr.camPos = mk3(iv.m[12], iv.m[13], iv.m[14]); fr.fwd = mk3(-iv.m[8], -iv.m[9], -iv.m[10]);
     fr.right = mk3(iv.m[0], iv.m[1], iv.m[2]); fr.up = mk3(iv.m[4], iv.m[5], iv.m[6]);
     float aspect = float(c->W) / float(c->H);
@@ -459,6 +469,78 @@ int ohb_render(ohb_ctx* c, const float view[16], const float proj[16], uint32_t 
     fr.aniso = c->settings.anisotropy_strength; fr.anisoRot = c->settings.anisotropy_rotation; fr.jitX = fr.jitY = 0.0f;   // no Halton jitter without NRD/DLSS-RR (Q15)
     fr.samplerType = c->settings.sampler_type;
     fr.tileX = c->tileX; fr.tileY = c->tileY; fr.tileW = c->tileW; fr.tileH = c->tileH;
+}
+static void fillPaths(ohb_ctx* c, PathArrays& P) {
+    uint32_t* small = c->smallCounters.as<uint32_t>();
+    P.rayO = c->rayO.as<f4>(); P.rayD = c->rayD.as<f4>(); P.hit = c->hit.as<ohb_hit>(); P.thr = c->thr.as<f4>(); P.rad = c->rad.as<f4>();
+    P.pendA = c->pendA.as<f4>(); P.pendB = c->pendB.as<f4>(); P.meta = c->meta.as<u4>();
+    P.fh0 = c->fh0.as<f4>(); P.fh1 = c->fh1.as<f4>(); P.fh2 = c->fh2.as<f4>(); P.fh3 = c->fh3.as<f4>();
+    P.pay0 = c->pay0.as<f4>(); P.pay1 = c->pay1.as<f4>(); P.pay2 = c->pay2.as<f4>(); P.pay3 = c->pay3.as<f4>();
+    P.shO = c->shO.as<f4>(); P.shD = c->shD.as<f4>();
+    P.queueIn = c->queueA.as<uint32_t>(); P.queueOut = c->queueB.as<uint32_t>();
+    P.countIn = small + 0; P.countOut = small + 1; P.shCount = small + 2;
+    P.counters = c->devCounters.as<unsigned long long>();
+    P.albedoAOV = c->albedoAOV.as<f4>(); P.normalAOV = c->normalAOV.as<f4>();
+    P.sobolTab = c->sobolTab.as<u4>(); P.queueSorted = c->queueS.as<uint32_t>(); P.sortCount = small + 12;
+}
+int ensurePaths(ohb_ctx* c, uint32_t cap);
+
+// One PathTracer::render() of the realtime profile per frame (path_tracer_render.cpp:686-724, :1274-1280):
+// frame index = m_sampleIndex, history count, view-changed flag, prevViewProj = last frame's proj*view, ping-pong flip.
+static int renderRealtime(ohb_ctx* c, const float* view, const float* proj, uint32_t nframes) {
+    if (c->settings.flags & OHB_FLAG_RESTIRGI_LEGACY) OHB_FAIL(c, "ohb_render: OHB_FLAG_RESTIRGI_LEGACY (multi-bounce Stage C) is not implemented");
+    if (c->tileX || c->tileY || c->tileW != c->W || c->tileH != c->H) OHB_FAIL(c, "ohb_render: the realtime profile renders full frames only (ReSTIR reuse reads neighbours)");
+    uint32_t spf = c->settings.samples_per_frame; spf = spf < 1u ? 1u : (spf > 64u ? 64u : spf);
+    uint32_t tilesX = (c->W + 7u) / 8u, tilesY = (c->H + 3u) / 4u, numPixels = tilesX * tilesY * 32u;
+    if (uint64_t(numPixels) * spf > (64ull << 20)) OHB_FAIL(c, "ohb_render: width*height*samples_per_frame too large");
+    if (ensurePaths(c, numPixels * spf)) return 1;
+    CU(c, c->sobolTab.reserve(size_t(spf) * 16));
+    size_t npx = size_t(c->W) * c->H;
+    for (int k = 0; k < 3; k++) if (c->rtDumpHost[k]) CU(c, c->rtDump[k].reserve(npx * 16));
+    SceneDev s; fillScene(c, s);
+    uint32_t* small = c->smallCounters.as<uint32_t>();
+    for (uint32_t f = 0; f < nframes; f++) {
+        FrameParams fr{}; fillFrameCommon(c, view, proj, fr);
+        memcpy(fr.prevViewProj, c->prevViewProj, 64);
+        fr.frameIdx = c->sampleIndex; fr.historyCount = c->historyCount; fr.viewChanged = c->viewChanged ? 1u : 0u; fr.spf = spf;
+        fr.jitterSobol = sobolQuad(fr.frameIdx);
+        PathArrays P{}; fillPaths(c, P);
+        P.numPixels = numPixels; P.samplesInBatch = spf; P.firstSampleIndex = fr.frameIdx * spf;
+        int prev = c->rtCur, cur = 1 - c->rtCur;
+        std::swap(c->accum, c->accumPrev);            // c->accum = image written by this frame
+        RTImagesDev im{};
+        im.accumPrev = c->accumPrev.as<f4>(); im.accumCurr = c->accum.as<f4>();
+        im.surfPrev = c->surf[prev].as<f4>(); im.surfCurr = c->surf[cur].as<f4>(); im.shadPrev = c->shad[prev].as<f4>(); im.shadCurr = c->shad[cur].as<f4>();
+        im.res0Prev = c->res[prev][0].as<f4>(); im.res1Prev = c->res[prev][1].as<f4>(); im.res2Prev = c->res[prev][2].as<f4>();
+        im.res0Curr = c->res[cur][0].as<f4>(); im.res1Curr = c->res[cur][1].as<f4>(); im.res2Curr = c->res[cur][2].as<f4>();
+        im.radianceDump = c->rtDumpHost[0] ? c->rtDump[0].as<float>() : nullptr; im.giDump = c->rtDumpHost[1] ? c->rtDump[1].as<float>() : nullptr;
+        im.counters = c->devCounters.as<unsigned long long>();
+        launchRealtimeFrame(s, fr, P, im, c->ldr.as<uint32_t>(), c->rtDumpHost[2] ? c->rtDump[2].as<float>() : nullptr, small + 4, c->numSMs, c->stream,
+                            &c->launches, c->timingOn ? &c->timing : nullptr);
+        c->rtCur = cur;
+        // m_prevViewProj = proj * view (column-major)
+        for (int col = 0; col < 4; col++) for (int row = 0; row < 4; row++) {
+            float acc = 0.0f; for (int k = 0; k < 4; k++) acc += proj[k * 4 + row] * view[col * 4 + k];
+            c->prevViewProj[col * 4 + row] = acc;
+        }
+        c->sampleIndex += 1; c->historyCount += 1; c->viewChanged = false;
+    }
+    CU(c, cudaGetLastError());
+    bool any = false;
+    for (int k = 0; k < 3; k++) if (c->rtDumpHost[k]) { CU(c, cudaMemcpyAsync(c->rtDumpHost[k], c->rtDump[k].p, npx * 16, cudaMemcpyDeviceToHost, c->stream)); any = true; }
+    if (any) CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int ohb_render(ohb_ctx* c, const float view[16], const float proj[16], uint32_t nsamples) {
+    if (!c) return 1;
+    if (!view || !proj) OHB_FAIL(c, "ohb_render: null matrix");
+    if (!c->accelValid) { c->err = "ohb_render: no acceleration structure (call ohb_build_accel)"; return 1; }   // reference: silent return (path_tracer_render.cpp:42)
+    if (!c->nmat) OHB_FAIL(c, "ohb_render: no materials");
+    if (nsamples == 0) return 0;
+    cudaSetDevice(c->device);
+    if (c->settings.profile == OHB_PROFILE_REALTIME) return renderRealtime(c, view, proj, nsamples);
+    FrameParams fr{}; fillFrameCommon(c, view, proj, fr);
     uint32_t tilesX = (c->tileW + 7u) / 8u, tilesY = (c->tileH + 3u) / 4u;
     uint32_t numPixels = tilesX * tilesY * 32u;
     static const uint32_t maxPaths = []() { const char* e = getenv("OHB_MAX_PATHS"); uint32_t v = e ? uint32_t(strtoul(e, nullptr, 10)) : 0u; return v ? v : (8u << 20); }();
@@ -477,18 +559,8 @@ int ohb_render(ohb_ctx* c, const float view[16], const float proj[16], uint32_t 
     uint32_t done = 0;
     while (done < nsamples) {
         uint32_t k = std::min(spb, nsamples - done);
-        PathArrays P{};
-        P.rayO = c->rayO.as<f4>(); P.rayD = c->rayD.as<f4>(); P.hit = c->hit.as<ohb_hit>(); P.thr = c->thr.as<f4>(); P.rad = c->rad.as<f4>();
-        P.pendA = c->pendA.as<f4>(); P.pendB = c->pendB.as<f4>(); P.meta = c->meta.as<u4>();
-        P.fh0 = c->fh0.as<f4>(); P.fh1 = c->fh1.as<f4>(); P.fh2 = c->fh2.as<f4>(); P.fh3 = c->fh3.as<f4>();
-        P.pay0 = c->pay0.as<f4>(); P.pay1 = c->pay1.as<f4>(); P.pay2 = c->pay2.as<f4>(); P.pay3 = c->pay3.as<f4>();
-        P.shO = c->shO.as<f4>(); P.shD = c->shD.as<f4>();
-        P.queueIn = c->queueA.as<uint32_t>(); P.queueOut = c->queueB.as<uint32_t>();
-        P.countIn = small + 0; P.countOut = small + 1; P.shCount = small + 2;
-        P.counters = c->devCounters.as<unsigned long long>();
-        P.albedoAOV = c->albedoAOV.as<f4>(); P.normalAOV = c->normalAOV.as<f4>();
+        PathArrays P{}; fillPaths(c, P);
         P.numPixels = numPixels; P.samplesInBatch = k; P.firstSampleIndex = c->sampleIndex;
-        P.sobolTab = c->sobolTab.as<u4>(); P.queueSorted = c->queueS.as<uint32_t>(); P.sortCount = small + 12;
         FilmArrays F{};
         F.accum = c->accum.as<f4>(); F.ldr = c->ldr.as<uint32_t>(); F.historyCount = c->historyCount; F.sumMode = c->sumMode;
         F.sampleDump = dumpDev ? dumpDev + size_t(done) * c->W * c->H * 4u : nullptr;
@@ -593,6 +665,25 @@ int ohb_get_timing_detail(ohb_ctx* c, float ms[8], uint64_t launches[8]) {
     CU(c, cudaStreamSynchronize(c->stream));
     c->timing.collect();
     for (int i = 0; i < 8; i++) { ms[i] = float(c->timing.ms[i]); launches[i] = c->timing.count[i]; }
+    return 0;
+}
+
+int ohb_set_realtime_dump(ohb_ctx* c, float* radiance, float* gi, float* denoised) {
+    if (!c) return 1;
+    c->rtDumpHost[0] = radiance; c->rtDumpHost[1] = gi; c->rtDumpHost[2] = denoised;
+    return 0;
+}
+int ohb_read_realtime_state(ohb_ctx* c, float* res0, float* res1, float* res2, float* surf, float* shad) {
+    if (!c) return 1;
+    if (c->profile != OHB_PROFILE_REALTIME) OHB_FAIL(c, "ohb_read_realtime_state: context was not created with OHB_PROFILE_REALTIME");
+    cudaSetDevice(c->device);
+    size_t bytes = size_t(c->W) * c->H * 16; int k = c->rtCur;
+    if (res0) CU(c, cudaMemcpyAsync(res0, c->res[k][0].p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (res1) CU(c, cudaMemcpyAsync(res1, c->res[k][1].p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (res2) CU(c, cudaMemcpyAsync(res2, c->res[k][2].p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (surf) CU(c, cudaMemcpyAsync(surf, c->surf[k].p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (shad) CU(c, cudaMemcpyAsync(shad, c->shad[k].p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 

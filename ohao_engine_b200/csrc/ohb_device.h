@@ -2,6 +2,7 @@
 #pragma once
 #include "ohb_bvh.h"
 #include "ohb_integrator.h"
+#include "ohb_realtime.h"
 #include <cuda_runtime.h>
 #include <vector>
 
@@ -34,6 +35,8 @@ void launchEnvSample(const SceneDev& sc, const float* u12, uint32_t n, f4* dirPd
 void launchEnvPdf(const SceneDev& sc, const float* dirs3, uint32_t n, float* pdf, cudaStream_t st, uint64_t* launches);
 void launchOfflineBatch(const SceneDev& sc, const FrameParams& fr, PathArrays P, const FilmArrays& F,
                         uint32_t* work, int numSMs, cudaStream_t st, uint64_t* launches, TimingHooks* th);
+void launchRealtimeFrame(const SceneDev& sc, const FrameParams& fr, PathArrays P, const RTImagesDev& im, uint32_t* ldr, float* denoisedDump,
+                         uint32_t* work, int numSMs, cudaStream_t st, uint64_t* launches, TimingHooks* th);
 void launchResolve(f4* accum, uint32_t* ldr, uint32_t n, int sumMode, cudaStream_t st, uint64_t* launches);
 void launchTraceBatch(const SceneDev& sc, const ohb_ray* rays, uint32_t n, ohb_hit* hits, uint8_t* occ, uint32_t* work, int numSMs, cudaStream_t st, uint64_t* launches);
 

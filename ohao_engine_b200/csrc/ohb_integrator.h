@@ -182,7 +182,30 @@ OHB_HD void clampLum(f3& c, float cap) { float l = luminance(c); if (l > cap) c 
 
 // One NEE light sample: pt_raygen_offline.rgen:311-389 (== :653-731 == :961-1039).
 struct LightSample { f3 L, Le; float shadowDist, weight; };
-OHB_HD LightSample sampleLight(const SceneDev& sc, Sampler& sm, uint32_t& dimIdx, f3 hitPos) {
+// pt_raygen_realtime.rgen:150-186 — subtended-cone sampling of a sphere light (realtime profile)
+OHB_HD void sampleSphereLightSolidAngle(f3 p, f3 center, float r, f2 u, f3& L, float& weight, float& shadowDist) {
+    f3 toCenter = center - p;
+    float d2 = dot(toCenter, toCenter);
+    float d = sqrtf(fmaxf(d2, 1e-8f));
+    f3 axis = toCenter / d;
+    float cosThetaMax = sqrtf(fmaxf(0.0f, 1.0f - (r * r) / fmaxf(d2, 1e-8f)));
+    float cosTheta = 1.0f - u.x * (1.0f - cosThetaMax);
+    float sinTheta = sqrtf(fmaxf(0.0f, 1.0f - cosTheta * cosTheta));
+    float phi = 6.2831853f * u.y;
+    f3 up = fabsf(axis.y) < 0.999f ? mk3(0, 1, 0) : mk3(1, 0, 0);
+    f3 T = normalize(cross(up, axis));
+    f3 B = cross(axis, T);
+    L = normalize(T * (sinTheta * ohb_cos(phi)) + B * (sinTheta * ohb_sin(phi)) + axis * cosTheta);
+    weight = 6.2831853f * (1.0f - cosThetaMax);
+    float b = dot(L, -toCenter);
+    float c = d2 - r * r;
+    float disc = b * b - c;
+    float t;
+    if (disc > 0.0f) { float sq = sqrtf(disc); t = -b - sq; if (t < 1e-3f) t = -b + sq; }
+    else t = d;
+    shadowDist = fmaxf(t - 0.02f, 1e-3f);
+}
+OHB_HD LightSample sampleLight(const SceneDev& sc, Sampler& sm, uint32_t& dimIdx, f3 hitPos, bool solidAngle = false) {
     uint32_t sel = uint32_t(sm.get1D(dimIdx) * float(sc.lightCount)); dimIdx += 1u;
     sel = sel < sc.lightCount - 1u ? sel : sc.lightCount - 1u;
     const f4* lp4 = reinterpret_cast<const f4*>(sc.lights + sel);
@@ -195,7 +218,10 @@ OHB_HD LightSample sampleLight(const SceneDev& sc, Sampler& sm, uint32_t& dimIdx
     float area = 4.0f * 3.14159f * r * r;
     LightSample ls;
     ls.Le = xyz(ci) * ci.w / fmaxf(area, 0.01f);
-    if (type < 0.5f || (type >= 1.5f && type < 2.5f)) {
+    if (type < 0.5f && solidAngle) {
+        f2 u = sm.get2D(dimIdx); dimIdx += 2u;
+        sampleSphereLightSolidAngle(hitPos, center, r, u, ls.L, ls.weight, ls.shadowDist);
+    } else if (type < 0.5f || (type >= 1.5f && type < 2.5f)) {
         f2 u = sm.get2D(dimIdx); dimIdx += 2u;
         float cosT = 1.0f - 2.0f * u.x;
         float sinT = sqrtf(fmaxf(0.0f, 1.0f - cosT * cosT));

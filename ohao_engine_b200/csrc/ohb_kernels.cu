@@ -378,6 +378,67 @@ void launchOfflineBatch(const SceneDev& sc, const FrameParams& fr, PathArrays P,
     k_film<<<gridFor(P.numPixels, 128), 128, 0, st>>>(fr, P, F); (*launches)++;
     if (th) th->end(3, st);
 }
+// =============================================================================================
+// Realtime profile: one frame = N-spp wavefront + per-pixel ReSTIR GI / EMA + a-trous (ohb_realtime.h)
+// =============================================================================================
+__global__ void __launch_bounds__(SHADE_THREADS) k_raygen_rt(FrameParams fr, PathArrays P, uint32_t total) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    raygenPathRT(fr, P, p);
+    if (OHB_ST_STAGE(P.meta[p].w) != ST_DONE) { uint32_t q = alloc_slot(P.countIn); P.queueIn[q] = p; }
+}
+__global__ void __launch_bounds__(SHADE_THREADS, 8) k_bounce_rt(SceneDev sc, FrameParams fr, PathArrays P) {
+    const uint32_t n = *P.countIn;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t p = P.queueSorted[i];
+        if (bouncePathRT(sc, fr, P, p)) { uint32_t q = alloc_slot(P.countOut); P.queueOut[q] = p; }
+    }
+}
+__global__ void __launch_bounds__(128) k_rt_pixel(SceneDev sc, FrameParams fr, PathArrays P, RTImagesDev im) {
+    uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix < P.numPixels) pixelRT(sc, fr, P, im, pix);
+}
+__global__ void __launch_bounds__(128) k_rt_denoise(FrameParams fr, const f4* accum, const f4* normalAOV, uint32_t* ldr, float* dump, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) denoiseRT(fr, accum, normalAOV, ldr, dump, i);
+}
+void launchRealtimeFrame(const SceneDev& sc, const FrameParams& fr, PathArrays P, const RTImagesDev& im, uint32_t* ldr, float* denoisedDump,
+                         uint32_t* work, int numSMs, cudaStream_t st, uint64_t* launches, TimingHooks* th) {
+    uint32_t total = P.numPixels * P.samplesInBatch;
+    k_zero_u32<<<1, 32, 0, st>>>(P.countIn, 1); k_zero_u32<<<1, 32, 0, st>>>(P.countOut, 1);
+    k_sobol_tab<<<gridFor(P.samplesInBatch, 64), 64, 0, st>>>(const_cast<u4*>(P.sobolTab), P.firstSampleIndex, P.samplesInBatch);
+    k_raygen_rt<<<gridFor(total, SHADE_THREADS), SHADE_THREADS, 0, st>>>(fr, P, total);
+    k_advance<<<1, 32, 0, st>>>(P, work, 1);
+    *launches += 5;
+    unsigned grid = unsigned(numSMs) * 8u;
+    uint32_t iters = 2u + fr.maxBounces;          // primary + chain B + the ReSTIR GI bounce
+    for (uint32_t it = 0; it < iters; it++) {
+        if (th) th->begin(0, st);
+        k_trace_closest<<<grid, TRACE_THREADS, 0, st>>>(sc, P, work);
+        if (th) th->end(0, st);
+        if (th) th->begin(4, st);
+        k_surface<<<grid, SHADE_THREADS, 0, st>>>(sc, fr, P);
+        if (th) th->end(4, st);
+        if (th) th->begin(1, st);
+        k_bounce_rt<<<grid, SHADE_THREADS, 0, st>>>(sc, fr, P);
+        if (th) th->end(1, st);
+        if (th) th->begin(2, st);
+        k_trace_shadow<<<grid, TRACE_THREADS, 0, st>>>(sc, P, work + 1);
+        if (th) th->end(2, st);
+        k_advance<<<1, 32, 0, st>>>(P, work, 0);
+        *launches += 5;
+        uint32_t* tq = P.queueIn; P.queueIn = P.queueOut; P.queueOut = tq;
+        uint32_t* tc = P.countIn; P.countIn = P.countOut; P.countOut = tc;
+    }
+    if (th) th->begin(5, st);
+    k_rt_pixel<<<gridFor(P.numPixels, 128), 128, 0, st>>>(sc, fr, P, im);
+    if (th) th->end(5, st);
+    if (th) th->begin(3, st);
+    k_rt_denoise<<<gridFor(fr.W * fr.H, 128), 128, 0, st>>>(fr, im.accumCurr, P.normalAOV, ldr, denoisedDump, fr.W * fr.H);
+    if (th) th->end(3, st);
+    *launches += 2;
+}
+
 void launchResolve(f4* accum, uint32_t* ldr, uint32_t n, int sumMode, cudaStream_t st, uint64_t* launches) {
     k_resolve<<<gridFor(n, 256), 256, 0, st>>>(accum, ldr, n, sumMode); (*launches)++;
 }

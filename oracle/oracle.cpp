@@ -220,7 +220,9 @@ static V3 schlick(V3 F0, float c) { return F0 + (v3(1.0f) - F0) * std::pow(1.0f 
 
 // One NEE light sample: pt_raygen_offline.rgen:311-389 (identical text again at :653-731, :961-1039).
 struct LightSample { V3 L, Le; float shadowDist, weight; };
-static LightSample sampleLight(const Scene& sc, Sampler& sm, uint32_t& dimIdx, V3 hitPos) {
+static void sampleSphereLightSolidAngle(V3 p, V3 center, float r, V2 u, V3& L, float& weight, float& shadowDist);   // oracle_realtime.inl
+// `solidAngle` selects the realtime raygen's sphere-light sampler (pt_raygen_realtime.rgen:548-552); everything else is shared text.
+static LightSample sampleLight(const Scene& sc, Sampler& sm, uint32_t& dimIdx, V3 hitPos, bool solidAngle = false) {
     uint32_t sel = uint32_t(sm.get1D(dimIdx) * float(sc.lightCount)); dimIdx += 1u;
     sel = std::min(sel, sc.lightCount - 1u);
     const GPULight& light = sc.lights[sel];
@@ -241,7 +243,10 @@ static LightSample sampleLight(const Scene& sc, Sampler& sm, uint32_t& dimIdx, V
         float phi = 6.2831853f * u.y;
         offset = V3{sinT * std::cos(phi), sinT * std::sin(phi), cosT} * r;
     };
-    if (type < 0.5f) {                       // sphere: uniform surface point
+    if (type < 0.5f && solidAngle) {
+        V2 u = sm.get2D(dimIdx); dimIdx += 2u;
+        sampleSphereLightSolidAngle(hitPos, center, r, u, ls.L, ls.weight, ls.shadowDist);
+    } else if (type < 0.5f) {                // sphere: uniform surface point
         V3 offset; spherePoint(offset);
         V3 lp = center + offset, ln = normalize(offset);
         V3 toL = lp - hitPos; float dist = length(toL);
@@ -528,6 +533,8 @@ static void tonemapStore(V3 acc, uint8_t* px) {   // pt_raygen_offline.rgen:1339
     px[0] = q(ldr.x); px[1] = q(ldr.y); px[2] = q(ldr.z); px[3] = 255;
 }
 
+#include "oracle_realtime.inl"
+
 }  // namespace orc
 
 using namespace orc;
@@ -743,6 +750,61 @@ int orc_render_offline(void* h, orc_render_args* a) {
     };
     std::vector<std::thread> thv; for (int t = 1; t < nthreads; t++) thv.emplace_back(work);
     work(); for (auto& t : thv) t.join();
+    a->counters = ohb_counters{};
+    a->counters.samples = total.samples; a->counters.closest_rays = total.closest; a->counters.shadow_rays = total.shadow; a->counters.closest_hits = total.hits;
+    return 0;
+}
+
+// One realtime frame (pt_raygen_realtime.rgen): pass 1 = everything up to the accumBuffer store, pass 2 = a-trous + tonemap.
+struct orc_rt_args {
+    float view[16], proj[16], prev_view_proj[16];
+    uint32_t width, height, frame_index, history_count, view_changed;
+    ohb_settings settings;
+    const float* accum_prev; float* accum_curr; const float* surf_prev; float* surf_curr; const float* shad_prev; float* shad_curr;
+    const float* res_prev[3]; float* res_curr[3];
+    float* albedo; float* normal; float* radiance_dump; float* gi_dump; float* denoised; uint8_t* ldr;
+    int32_t nthreads; ohb_counters counters;
+};
+int orc_render_realtime(void* h, orc_rt_args* a) {
+    Scene* s = (Scene*)h;
+    Frame fr{};
+    M4 view = toM4(a->view), proj = toM4(a->proj);
+    fr.invView = inverse(view); fr.invProj = inverse(proj); fr.prevViewProj = toM4(a->prev_view_proj);
+    fr.W = a->width; fr.H = a->height; fr.sampleIndex = a->frame_index; fr.maxBounces = a->settings.max_bounces & 0xFFFFu;
+    fr.flags = a->settings.flags; fr.historyCount = a->history_count; fr.viewChanged = a->view_changed;
+    fr.envW = s->hasEnv() ? s->envW : 0u; fr.envH = s->hasEnv() ? float(s->envH) : 0.0f; fr.envIntegral = s->envIntegral;
+    fr.fireflyClamp = a->settings.firefly_clamp_lum; fr.sss = a->settings.subsurface_strength;
+    fr.jitX = fr.jitY = 0.0f; fr.aniso = a->settings.anisotropy_strength; fr.anisoRot = a->settings.anisotropy_rotation;
+    fr.samplerType = a->settings.sampler_type;
+    uint32_t spf = a->settings.samples_per_frame; fr.spf = spf < 1u ? 1u : (spf > 64u ? 64u : spf);
+    RTImages im{a->accum_prev, a->accum_curr, a->surf_prev, a->surf_curr, a->shad_prev, a->shad_curr,
+                {a->res_prev[0], a->res_prev[1], a->res_prev[2]}, {a->res_curr[0], a->res_curr[1], a->res_curr[2]},
+                a->albedo, a->normal, a->radiance_dump, a->gi_dump};
+    int nthreads = std::max(1, a->nthreads);
+    std::atomic<uint32_t> nextRow{0};
+    std::mutex mu; Counters total;
+    auto work = [&]() {
+        Tracer tr(*s, fr);
+        RealtimeIntegrator integ(tr);
+        for (;;) {
+            uint32_t row = nextRow.fetch_add(1); if (row >= a->height) break;
+            for (uint32_t px = 0; px < a->width; px++) integ.pixel(px, row, im);
+        }
+        std::lock_guard<std::mutex> lk(mu);
+        total.samples += tr.cnt.samples; total.closest += tr.cnt.closest; total.shadow += tr.cnt.shadow; total.hits += tr.cnt.hits;
+    };
+    { std::vector<std::thread> thv; for (int t = 1; t < nthreads; t++) thv.emplace_back(work); work(); for (auto& t : thv) t.join(); }
+    nextRow = 0;
+    auto work2 = [&]() {
+        for (;;) {
+            uint32_t row = nextRow.fetch_add(1); if (row >= a->height) break;
+            for (uint32_t px = 0; px < a->width; px++) {
+                size_t pi = size_t(row) * a->width + px;
+                realtimeDenoisePixel(fr, a->accum_curr, a->normal, int(px), int(row), a->ldr ? a->ldr + pi * 4 : nullptr, a->denoised ? a->denoised + pi * 4 : nullptr);
+            }
+        }
+    };
+    { std::vector<std::thread> thv; for (int t = 1; t < nthreads; t++) thv.emplace_back(work2); work2(); for (auto& t : thv) t.join(); }
     a->counters = ohb_counters{};
     a->counters.samples = total.samples; a->counters.closest_rays = total.closest; a->counters.shadow_rays = total.shadow; a->counters.closest_hits = total.hits;
     return 0;

@@ -49,6 +49,16 @@ class RenderArgs(C.Structure):
                 ("nthreads", C.c_int32), ("counters", Counters)]
 
 
+class RTArgs(C.Structure):
+    _fields_ = [("view", C.c_float * 16), ("proj", C.c_float * 16), ("prev_view_proj", C.c_float * 16),
+                ("width", C.c_uint32), ("height", C.c_uint32), ("frame_index", C.c_uint32), ("history_count", C.c_uint32), ("view_changed", C.c_uint32),
+                ("settings", Settings),
+                ("accum_prev", C.c_void_p), ("accum_curr", C.c_void_p), ("surf_prev", C.c_void_p), ("surf_curr", C.c_void_p),
+                ("shad_prev", C.c_void_p), ("shad_curr", C.c_void_p), ("res_prev", C.c_void_p * 3), ("res_curr", C.c_void_p * 3),
+                ("albedo", C.c_void_p), ("normal", C.c_void_p), ("radiance_dump", C.c_void_p), ("gi_dump", C.c_void_p), ("denoised", C.c_void_p), ("ldr", C.c_void_p),
+                ("nthreads", C.c_int32), ("counters", Counters)]
+
+
 def build(force: bool = False) -> str:
     """Compile oracle/liboracle.so (and oracle/_ref when /root/reference exists)."""
     so = os.path.join(_HERE, "liboracle.so")
@@ -68,6 +78,7 @@ def lib() -> C.CDLL:
         _LIB.orc_scene_create.argtypes = [C.POINTER(SceneDesc)]
         _LIB.orc_scene_destroy.argtypes = [C.c_void_p]
         _LIB.orc_render_offline.argtypes = [C.c_void_p, C.POINTER(RenderArgs)]
+        _LIB.orc_render_realtime.argtypes = [C.c_void_p, C.POINTER(RTArgs)]
         _LIB.orc_sampler_1d.restype = C.c_float
         _LIB.orc_sampler_1d.argtypes = [C.c_uint32] * 5
         _LIB.orc_sobol_raw.restype = C.c_float
@@ -112,8 +123,28 @@ def offline_settings(max_bounces=4, flags=1, firefly=0.0, sampler=1) -> Settings
     return s
 
 
+def realtime_settings(max_bounces=2, flags=1 | 2 | 4, firefly=10.0, sampler=1, spf=1) -> Settings:
+    """kRealtimeRTSettings (rt_settings.hpp:37-48) with the sampler the pipeline actually runs (Sobol, quirk Q3)."""
+    s = Settings()
+    s.profile = 1; s.max_bounces = max_bounces; s.flags = flags; s.firefly_clamp_lum = firefly
+    s.sampler_type = sampler; s.samples_per_frame = spf
+    return s
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class RealtimeState:
+    """Host mirror of PathTracer's realtime frame state: ping-ponged history images + frame counters."""
+
+    def __init__(self, width, height):
+        self.W, self.H = width, height
+        z = lambda: np.zeros((height, width, 4), np.float32)
+        self.accum = [z(), z()]; self.surf = [z(), z()]; self.shad = [z(), z()]
+        self.res = [[z(), z(), z()], [z(), z(), z()]]
+        self.albedo = z(); self.normal = z()
+        self.cur = 0; self.frame_index = 0; self.history = 0; self.prev_view_proj = np.eye(4, dtype=np.float32).reshape(16)
 
 
 class OracleScene:
@@ -166,6 +197,30 @@ class OracleScene:
         c = a.counters
         return dict(accum=accum, ldr=ldr, albedo=alb, normal=nrm, samples=sd,
                     counters=dict(samples=c.samples, closest_rays=c.closest_rays, shadow_rays=c.shadow_rays, closest_hits=c.closest_hits))
+
+    def render_realtime(self, st: "RealtimeState", view, proj, settings=None, view_changed=False, nthreads=None, dumps=False):
+        """One realtime frame; flips the ping-pong buffers of `st` and advances its counters like PathTracer::render."""
+        a = RTArgs()
+        a.view[:] = [float(x) for x in view]; a.proj[:] = [float(x) for x in proj]; a.prev_view_proj[:] = [float(x) for x in st.prev_view_proj]
+        a.width, a.height, a.frame_index, a.history_count, a.view_changed = st.W, st.H, st.frame_index, st.history, int(view_changed)
+        a.settings = settings or realtime_settings()
+        p, c = st.cur, 1 - st.cur
+        a.accum_prev, a.accum_curr = _p(st.accum[p]), _p(st.accum[c]); a.surf_prev, a.surf_curr = _p(st.surf[p]), _p(st.surf[c])
+        a.shad_prev, a.shad_curr = _p(st.shad[p]), _p(st.shad[c])
+        for k in range(3):
+            a.res_prev[k] = _p(st.res[p][k]); a.res_curr[k] = _p(st.res[c][k])
+        a.albedo, a.normal = _p(st.albedo), _p(st.normal)
+        rad = np.zeros((st.H, st.W, 4), np.float32) if dumps else None; gi = np.zeros((st.H, st.W, 4), np.float32) if dumps else None
+        den = np.zeros((st.H, st.W, 4), np.float32); ldr = np.zeros((st.H, st.W, 4), np.uint8)
+        a.radiance_dump, a.gi_dump, a.denoised, a.ldr = _p(rad), _p(gi), _p(den), _p(ldr)
+        a.nthreads = nthreads or (os.cpu_count() or 1)
+        lib().orc_render_realtime(self.h, C.byref(a))
+        st.cur = c; st.frame_index += 1; st.history += 1
+        v = np.asarray(view, np.float32).reshape(4, 4); pr = np.asarray(proj, np.float32).reshape(4, 4)    # [col][row]
+        st.prev_view_proj = (v @ pr).reshape(16).astype(np.float32)        # column-major proj*view == (row-vector) view@proj
+        cnt = a.counters
+        return dict(accum=st.accum[c], ldr=ldr, denoised=den, radiance=rad, gi=gi, reservoirs=st.res[c], surf=st.surf[c], shad=st.shad[c],
+                    counters=dict(samples=cnt.samples, closest_rays=cnt.closest_rays, shadow_rays=cnt.shadow_rays, closest_hits=cnt.closest_hits))
 
     def trace(self, rays, brute=False, nthreads=None):
         rays = np.ascontiguousarray(rays, RAY_DTYPE); hits = np.zeros(len(rays), HIT_DTYPE)

@@ -9,6 +9,7 @@
 // radix sort / scan / queue kernels (device-only code) are replaced by std::stable_sort here.
 #include "../../ohao_engine_b200/csrc/ohb_bvh.h"
 #include "../../ohao_engine_b200/csrc/ohb_integrator.h"
+#include "../../ohao_engine_b200/csrc/ohb_realtime.h"
 #include <vector>
 #include <algorithm>
 #include <numeric>
@@ -219,6 +220,76 @@ int emul_render_offline(void* h, emul_render_args* a) {
     if (a->ldr) memcpy(a->ldr, ldr.data(), npx * 4);
     if (a->albedo) memcpy(a->albedo, albedo.data(), npx * 16);
     if (a->normal) memcpy(a->normal, normal.data(), npx * 16);
+    for (int i = 0; i < 4; i++) a->counters[i] = counters[i];
+    return 0;
+}
+
+// Mimics renderRealtime + launchRealtimeFrame for ONE frame (the caller owns the ping-ponged history images).
+struct emul_rt_args {
+    float view[16], proj[16], prev_view_proj[16];
+    uint32_t width, height, frame_index, history_count, view_changed;
+    ohb_settings settings;
+    const float* accum_prev; float* accum_curr; const float* surf_prev; float* surf_curr; const float* shad_prev; float* shad_curr;
+    const float* res_prev[3]; float* res_curr[3];
+    float* albedo; float* normal; float* radiance_dump; float* gi_dump; float* denoised; uint8_t* ldr;
+    uint64_t counters[4];
+};
+int emul_render_realtime(void* h, emul_rt_args* a) {
+    EmulScene* es = (EmulScene*)h; SceneDev sc = es->dev();
+    float iv[16], ip[16]; inv4(a->view, iv); inv4(a->proj, ip);
+    FrameParams fr{};
+    fr.camPos = mk3(iv[12], iv[13], iv[14]); fr.fwd = mk3(-iv[8], -iv[9], -iv[10]); fr.right = mk3(iv[0], iv[1], iv[2]); fr.up = mk3(iv[4], iv[5], iv[6]);
+    fr.tanY = fabsf(ip[5]); fr.tanX = fr.tanY * (float(a->width) / float(a->height));
+    fr.W = a->width; fr.H = a->height; fr.maxBounces = a->settings.max_bounces & 0xFFFFu; fr.flags = a->settings.flags;
+    bool envOn = es->envW && es->envMapTexIdx != 0xFFFFFFFFu;
+    fr.envW = envOn ? es->envW : 0u; fr.envH = envOn ? float(es->envH) : 0.0f;
+    fr.fireflyClamp = a->settings.firefly_clamp_lum; fr.sss = a->settings.subsurface_strength; fr.aniso = a->settings.anisotropy_strength; fr.anisoRot = a->settings.anisotropy_rotation;
+    fr.samplerType = a->settings.sampler_type;
+    fr.tileX = 0; fr.tileY = 0; fr.tileW = a->width; fr.tileH = a->height;
+    memcpy(fr.prevViewProj, a->prev_view_proj, 64);
+    uint32_t spf = a->settings.samples_per_frame; spf = spf < 1u ? 1u : (spf > 64u ? 64u : spf);
+    fr.frameIdx = a->frame_index; fr.historyCount = a->history_count; fr.viewChanged = a->view_changed; fr.spf = spf; fr.jitterSobol = sobolQuad(fr.frameIdx);
+    uint32_t tilesX = (fr.tileW + 7u) / 8u, tilesY = (fr.tileH + 3u) / 4u, numPixels = tilesX * tilesY * 32u, total = numPixels * spf;
+    std::vector<f4> rayO(total), rayD(total), thr(total), rad(total), pendA(total), pendB(total), fh0(total), fh1(total), fh2(total), fh3(total),
+        pay0(total), pay1(total), pay2(total), pay3(total), shO(size_t(total) * 2), shD(size_t(total) * 2);
+    std::vector<ohb_hit> hit(total); std::vector<u4> meta(total); std::vector<uint32_t> qa(total), qb(total), qs(total);
+    uint32_t small[4] = {0, 0, 0, 0}, sortCount[2] = {0, 0}; unsigned long long counters[8] = {0};
+    std::vector<u4> sobolTab(spf); for (uint32_t i = 0; i < spf; i++) sobolTab[i] = sobolQuad(fr.frameIdx * spf + i);
+    size_t npx = size_t(a->width) * a->height;
+    std::vector<uint32_t> ldr(npx);
+    PathArrays P{};
+    P.rayO = rayO.data(); P.rayD = rayD.data(); P.hit = hit.data(); P.thr = thr.data(); P.rad = rad.data(); P.pendA = pendA.data(); P.pendB = pendB.data(); P.meta = meta.data();
+    P.fh0 = fh0.data(); P.fh1 = fh1.data(); P.fh2 = fh2.data(); P.fh3 = fh3.data(); P.pay0 = pay0.data(); P.pay1 = pay1.data(); P.pay2 = pay2.data(); P.pay3 = pay3.data();
+    P.shO = shO.data(); P.shD = shD.data(); P.queueIn = qa.data(); P.queueOut = qb.data(); P.queueSorted = qs.data(); P.sortCount = sortCount;
+    P.countIn = &small[0]; P.countOut = &small[1]; P.shCount = &small[2]; P.counters = counters;
+    P.albedoAOV = reinterpret_cast<f4*>(a->albedo); P.normalAOV = reinterpret_cast<f4*>(a->normal);
+    P.numPixels = numPixels; P.samplesInBatch = spf; P.firstSampleIndex = fr.frameIdx * spf; P.sobolTab = sobolTab.data();
+    for (uint32_t p = 0; p < total; p++) { raygenPathRT(fr, P, p); if (OHB_ST_STAGE(P.meta[p].w) != ST_DONE) P.queueIn[(*P.countIn)++] = p; }
+    counters[0] += *P.countIn;
+    for (uint32_t it = 0; it < 2u + fr.maxBounces; it++) {
+        uint32_t n = *P.countIn;
+        for (uint32_t i = 0; i < n; i++) { uint32_t p = P.queueIn[i]; P.hit[p] = traceClosest(sc, xyz(P.rayO[p]), xyz(P.rayD[p]), 0.001f, 10000.0f); counters[3] += P.hit[p].prim != OHB_MISS; }
+        sortCount[0] = sortCount[1] = 0;
+        for (uint32_t i = 0; i < n; i++) { uint32_t p = P.queueIn[i]; if (surfacePath(sc, fr, P, p)) P.queueSorted[sortCount[0]++] = p; else P.queueSorted[n - 1u - sortCount[1]++] = p; }
+        for (uint32_t i = 0; i < n; i++) { uint32_t p = P.queueSorted[i]; if (bouncePathRT(sc, fr, P, p)) P.queueOut[(*P.countOut)++] = p; }
+        uint32_t ns = *P.shCount;
+        for (uint32_t i = 0; i < ns; i++) {
+            f4 o = P.shO[i], d = P.shD[i];
+            if (traceAny(sc, xyz(o), xyz(d), 0.001f, o.w)) { uint32_t tag = f2u(d.w); ((tag & 1u) ? P.pendB : P.pendA)[tag >> 1] = mk4(0, 0, 0, 0); }
+        }
+        counters[1] += n; counters[2] += ns; *P.countIn = 0; *P.shCount = 0;
+        std::swap(P.queueIn, P.queueOut); std::swap(P.countIn, P.countOut);
+    }
+    RTImagesDev im{};
+    im.accumPrev = reinterpret_cast<const f4*>(a->accum_prev); im.accumCurr = reinterpret_cast<f4*>(a->accum_curr);
+    im.surfPrev = reinterpret_cast<const f4*>(a->surf_prev); im.surfCurr = reinterpret_cast<f4*>(a->surf_curr);
+    im.shadPrev = reinterpret_cast<const f4*>(a->shad_prev); im.shadCurr = reinterpret_cast<f4*>(a->shad_curr);
+    im.res0Prev = reinterpret_cast<const f4*>(a->res_prev[0]); im.res1Prev = reinterpret_cast<const f4*>(a->res_prev[1]); im.res2Prev = reinterpret_cast<const f4*>(a->res_prev[2]);
+    im.res0Curr = reinterpret_cast<f4*>(a->res_curr[0]); im.res1Curr = reinterpret_cast<f4*>(a->res_curr[1]); im.res2Curr = reinterpret_cast<f4*>(a->res_curr[2]);
+    im.radianceDump = a->radiance_dump; im.giDump = a->gi_dump; im.counters = counters;
+    for (uint32_t pix = 0; pix < numPixels; pix++) pixelRT(sc, fr, P, im, pix);
+    for (uint32_t i = 0; i < uint32_t(npx); i++) denoiseRT(fr, im.accumCurr, P.normalAOV, ldr.data(), a->denoised, i);
+    if (a->ldr) memcpy(a->ldr, ldr.data(), npx * 4);
     for (int i = 0; i < 4; i++) a->counters[i] = counters[i];
     return 0;
 }

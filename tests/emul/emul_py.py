@@ -23,6 +23,10 @@ class RenderArgs(C.Structure):
                 ("counters", C.c_uint64 * 4)]
 
 
+class RTArgs(C.Structure):
+    _fields_ = O.RTArgs._fields_[:-2] + [("counters", C.c_uint64 * 4)]
+
+
 def lib():
     global _LIB
     if _LIB is None:
@@ -35,6 +39,7 @@ def lib():
         _LIB.emul_occluded_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         _LIB.emul_env_sample_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         _LIB.emul_render_offline.argtypes = [C.c_void_p, C.POINTER(RenderArgs)]
+        _LIB.emul_render_realtime.argtypes = [C.c_void_p, C.POINTER(RTArgs)]
         _LIB.emul_accel_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
     return _LIB
 
@@ -78,6 +83,29 @@ class EmulScene:
     def env_sample(self, u12):
         u = np.ascontiguousarray(u12, np.float32); n = len(u); dp = np.zeros((n, 4), np.float32); pd = np.zeros(n, np.float32)
         lib().emul_env_sample_batch(self.h, _p(u), n, _p(dp), _p(pd)); return dp, pd
+
+    def render_realtime(self, st, view, proj, settings=None, view_changed=False, dumps=False):
+        """Same contract as OracleScene.render_realtime (st = oracle_py.RealtimeState)."""
+        a = RTArgs()
+        a.view[:] = [float(x) for x in view]; a.proj[:] = [float(x) for x in proj]; a.prev_view_proj[:] = [float(x) for x in st.prev_view_proj]
+        a.width, a.height, a.frame_index, a.history_count, a.view_changed = st.W, st.H, st.frame_index, st.history, int(view_changed)
+        a.settings = settings or O.realtime_settings()
+        p, c = st.cur, 1 - st.cur
+        a.accum_prev, a.accum_curr = _p(st.accum[p]), _p(st.accum[c]); a.surf_prev, a.surf_curr = _p(st.surf[p]), _p(st.surf[c])
+        a.shad_prev, a.shad_curr = _p(st.shad[p]), _p(st.shad[c])
+        for k in range(3):
+            a.res_prev[k] = _p(st.res[p][k]); a.res_curr[k] = _p(st.res[c][k])
+        a.albedo, a.normal = _p(st.albedo), _p(st.normal)
+        rad = np.zeros((st.H, st.W, 4), np.float32) if dumps else None; gi = np.zeros((st.H, st.W, 4), np.float32) if dumps else None
+        den = np.zeros((st.H, st.W, 4), np.float32); ldr = np.zeros((st.H, st.W, 4), np.uint8)
+        a.radiance_dump, a.gi_dump, a.denoised, a.ldr = _p(rad), _p(gi), _p(den), _p(ldr)
+        lib().emul_render_realtime(self.h, C.byref(a))
+        st.cur = c; st.frame_index += 1; st.history += 1
+        v = np.asarray(view, np.float32).reshape(4, 4); pr = np.asarray(proj, np.float32).reshape(4, 4)
+        st.prev_view_proj = (v @ pr).reshape(16).astype(np.float32)
+        cnt = a.counters
+        return dict(accum=st.accum[c], ldr=ldr, denoised=den, radiance=rad, gi=gi, reservoirs=st.res[c], surf=st.surf[c], shad=st.shad[c],
+                    counters=dict(samples=cnt[0], closest_rays=cnt[1], shadow_rays=cnt[2], closest_hits=cnt[3]))
 
     def render_offline(self, view, proj, width, height, nsamples, first_sample=0, history=0, accum=None, settings=None, tile=None, dump=False):
         a = RenderArgs()
