@@ -1,0 +1,63 @@
+"""C++20 host side (host/): builds everywhere; on a GPU box the example binaries render through the C ABI and must agree with the
+Python binding on the same scene (which in turn is parity-checked against the oracle)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+from PIL import Image
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "host")
+
+
+def _build():
+    from ohao_engine_b200 import build
+    build.build_native()
+    subprocess.check_call(["make", "-C", HOST, "all"], stdout=subprocess.DEVNULL)
+
+
+def test_host_examples_build_and_refuse_to_run_without_a_gpu():
+    _build()
+    for b in ("cornell_box", "turntable", "inverse_fit"):
+        assert os.access(os.path.join(HOST, b), os.X_OK)
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = subprocess.run([os.path.join(HOST, "cornell_box"), "/tmp/never.png", "1", "--width", "32", "--height", "18"], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CUDA device" in r.stderr            # no CPU fallback in the host path either
+
+
+@pytest.mark.gpu
+def test_cornell_box_binary_matches_python_binding(tmp_path):
+    _build()
+    from ohao_engine_b200 import binding as B, scenes
+    W, H, spp = 320, 180, 8
+    out = str(tmp_path / "cornell.png")
+    r = subprocess.run([os.path.join(HOST, "cornell_box"), out, str(spp), "--width", str(W), "--height", str(H), "--denoise=none"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Done:" in r.stdout and "Saved" in r.stdout
+    cpp = np.asarray(Image.open(out).convert("RGBA"), np.int16)
+    ps, cam = scenes.cornell_box(), scenes.cornell_camera()
+    rr = B.Renderer(W, H); rr.set_scene(ps)
+    for _ in range(spp):
+        rr.render(cam.view(), cam.proj(W, H), 1)
+    py = rr.get_pixels().astype(np.int16)
+    d = np.abs(cpp - py).max(-1)
+    assert (d > 1).mean() < 0.01, ((d > 1).mean(), d.max())             # same packer, same ABI; libm-vs-numpy sin/cos may move the camera by an ulp
+
+
+@pytest.mark.gpu
+def test_turntable_and_inverse_fit_binaries(tmp_path):
+    _build()
+    out = str(tmp_path / "tt")
+    for mode, extra in (("env", []), ("cornell", ["--realtime"])):
+        r = subprocess.run([os.path.join(HOST, "turntable"), "blob:5000", mode, "4", "3", "--width", "160", "--height", "90", "--outdir", out] + extra, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        frames = sorted(f for f in os.listdir(out) if f.startswith(mode))
+        assert len(frames) == 3
+        im = np.asarray(Image.open(os.path.join(out, frames[1])).convert("RGB"))
+        assert im.shape == (90, 160, 3) and im.mean() > 2
+    r = subprocess.run([os.path.join(HOST, "inverse_fit"), "--backend", "pt", "--preset", "lantern", "--quality", "draft", "--iters", "6", "--tris", "3000"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr                         # exit 0 <=> the fit reduced the loss
+    assert "probes/s" in r.stdout
