@@ -107,6 +107,11 @@ int main(int argc, char** argv) {
     const std::vector<double> truth = {0.80, 0.45, 0.25, 0.35, 0.10, 0.55, 0.50, 0.45, 12.0 / 40.0, 5.0 / 40.0, 8.0 / 40.0, 1.0};
     ParamSpace sp; sp.values = {0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.2, 0.2, 0.2, 0.7};
     sp.lo = {0.02, 0.02, 0.02, 0.05, 0.0, 0.02, 0.02, 0.02, 0.0, 0.0, 0.0, 0.0}; sp.hi = {1, 1, 1, 1, 1, 1, 1, 1, 1.5, 1.5, 1.5, 3.0};
+    // Bind every worker's scene at the SAME theta (the initial guess).  updateRTMaterialParams only rewrites the 3 vec4 per
+    // material (rt_build.cpp:188-389); the 1x1 solid-colour diffuse layer each untextured material received at upload time
+    // (quirk Q1) keeps the colour it was bound with, so the image depends on the theta at bind time — with one renderer the
+    // reference is self-consistent, with G renderers they must all bind alike or their probes disagree.
+    { std::vector<uint8_t> scratch; for (int g = 0; g < G; g++) if (!workers[size_t(g)].render(sp.values, 0, seed, scratch)) { std::cerr << "FATAL: bind render failed on GPU " << g << "\n"; return 1; } }
     // targets: truth rendered with the same budget and seeds (worker 0)
     std::vector<std::vector<uint8_t>> target(static_cast<size_t>(nViews));
     for (int v = 0; v < nViews; v++) if (!workers[0].render(truth, v, seed, target[size_t(v)])) { std::cerr << "FATAL: target render failed\n"; return 1; }
