@@ -83,7 +83,7 @@ struct ohb_ctx {
     DevBuf positions, indices, normals, uvs, matIds, triInst, instXform, instNormalMat, instInv, matColors, tex, lights, env, marg, cond, rowTotal, integral;
     // accel (device)
     DevBuf activeTris, wtri, primLo, primHi, boundsBits, keys, vals, keysTmp, valsTmp, sortTemp, left, right, parentInner, parentLeaf,
-           rangeFirst, rangeLast, nodeLo, nodeHi, visit, newIndex, emitCounter, sah, nodes, tris;
+           nodeFirst, leafPos, nodeLo, nodeHi, visit, newIndex, emitCounter, sah, nodes, tris;
     // paths (device)
     DevBuf rayO, rayD, hit, thr, rad, pendA, pendB, meta, fh0, fh1, fh2, fh3, pay0, pay1, pay2, pay3, shO, shD, queueA, queueB, queueS, sobolTab, smallCounters, devCounters;
     uint32_t pathCapacity = 0;
@@ -176,7 +176,7 @@ void ohb_destroy(ohb_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf* all[] = {&c->positions, &c->indices, &c->normals, &c->uvs, &c->matIds, &c->triInst, &c->instXform, &c->instNormalMat, &c->instInv, &c->matColors,
                      &c->tex, &c->lights, &c->env, &c->marg, &c->cond, &c->rowTotal, &c->integral, &c->activeTris, &c->wtri, &c->primLo, &c->primHi, &c->boundsBits,
-                     &c->keys, &c->vals, &c->keysTmp, &c->valsTmp, &c->sortTemp, &c->left, &c->right, &c->parentInner, &c->parentLeaf, &c->rangeFirst, &c->rangeLast,
+                     &c->keys, &c->vals, &c->keysTmp, &c->valsTmp, &c->sortTemp, &c->left, &c->right, &c->parentInner, &c->parentLeaf, &c->nodeFirst, &c->leafPos,
                      &c->nodeLo, &c->nodeHi, &c->visit, &c->newIndex, &c->emitCounter, &c->sah, &c->nodes, &c->tris, &c->rayO, &c->rayD, &c->hit, &c->thr, &c->rad,
                      &c->pendA, &c->pendB, &c->meta, &c->fh0, &c->fh1, &c->fh2, &c->fh3, &c->pay0, &c->pay1, &c->pay2, &c->pay3, &c->shO, &c->shD, &c->queueA, &c->queueB, &c->queueS, &c->sobolTab, &c->smallCounters, &c->devCounters,
                      &c->accum, &c->ldr, &c->albedoAOV, &c->normalAOV, &c->sampleDump, &c->hookRays, &c->hookOut, &c->hookAux,
@@ -382,7 +382,7 @@ int ohb_build_accel(ohb_ctx* c) {
     CU(c, c->keys.reserve(nn * 8)); CU(c, c->vals.reserve(nn * 4)); CU(c, c->keysTmp.reserve(nn * 8)); CU(c, c->valsTmp.reserve(nn * 4));
     CU(c, c->sortTemp.reserve(size_t(radixSortTempWords(n)) * 4));
     CU(c, c->left.reserve(nn * 4)); CU(c, c->right.reserve(nn * 4)); CU(c, c->parentInner.reserve(nn * 4)); CU(c, c->parentLeaf.reserve(nn * 4));
-    CU(c, c->rangeFirst.reserve(nn * 4)); CU(c, c->rangeLast.reserve(nn * 4)); CU(c, c->nodeLo.reserve(nn * 16)); CU(c, c->nodeHi.reserve(nn * 16));
+    CU(c, c->nodeFirst.reserve(nn * 4)); CU(c, c->leafPos.reserve(nn * 4)); CU(c, c->nodeLo.reserve(nn * 16)); CU(c, c->nodeHi.reserve(nn * 16));
     CU(c, c->visit.reserve(nn * 4)); CU(c, c->newIndex.reserve(nn * 4)); CU(c, c->emitCounter.reserve(4)); CU(c, c->sah.reserve(8));
     CU(c, c->nodes.reserve(nn * 64)); CU(c, c->tris.reserve(nn * 48));
     BuildArrays b{};
@@ -391,11 +391,13 @@ int ohb_build_accel(ohb_ctx* c) {
     b.wtri = c->wtri.as<f4>(); b.primLo = c->primLo.as<f4>(); b.primHi = c->primHi.as<f4>(); b.boundsBits = c->boundsBits.as<uint32_t>();
     b.keys = c->keys.as<uint64_t>(); b.vals = c->vals.as<uint32_t>();
     b.left = c->left.as<int32_t>(); b.right = c->right.as<int32_t>(); b.parentInner = c->parentInner.as<int32_t>(); b.parentLeaf = c->parentLeaf.as<int32_t>();
-    b.rangeFirst = c->rangeFirst.as<uint32_t>(); b.rangeLast = c->rangeLast.as<uint32_t>(); b.nodeLo = c->nodeLo.as<f4>(); b.nodeHi = c->nodeHi.as<f4>();
+    b.nodeFirst = c->nodeFirst.as<uint32_t>(); b.leafPos = c->leafPos.as<uint32_t>(); b.nodeLo = c->nodeLo.as<f4>(); b.nodeHi = c->nodeHi.as<f4>();
     b.visit = c->visit.as<uint32_t>(); b.newIndex = c->newIndex.as<int32_t>(); b.emitCounter = c->emitCounter.as<uint32_t>(); b.sah = c->sah.as<float>();
     b.nodes = c->nodes.as<f4>(); b.tris = c->tris.as<f4>();
     CU(c, cudaEventRecord(c->evA, c->stream));
-    launchBuild(b, c->keysTmp.as<uint64_t>(), c->valsTmp.as<uint32_t>(), c->sortTemp.as<uint32_t>(), c->stream, &c->launches);
+    static const uint32_t treeletPasses = []() { const char* e = getenv("OHB_TREELET_PASSES"); return e ? uint32_t(strtoul(e, nullptr, 10)) : 3u; }();
+    launchBuild(b, c->keysTmp.as<uint64_t>(), c->valsTmp.as<uint32_t>(), c->sortTemp.as<uint32_t>(), treeletPasses, c->stream, &c->launches);
+    c->stats.treelet_passes = treeletPasses;
     CU(c, cudaEventRecord(c->evB, c->stream));
     uint32_t emitted = 1; float sah[2] = {0, 0}; f4 rootLo{}, rootHi{};
     if (n >= 2) {

@@ -9,8 +9,10 @@
 //
 // Pipeline (one kernel each, ohb_kernels.cu):
 //   worldTriangles -> sceneBounds -> morton63 -> radix sort (key u64, val u32) -> karras hierarchy
-//   -> bottom-up AABB refit (atomic visit counters) -> collapse subtrees of <= 4 triangles to leaves
-//   -> emit 64-B nodes + 48-B triangles in leaf order -> (optional) treelet SAH restructuring.
+//   -> bottom-up sweep (atomic visit counters): AABB refit + triangle counts + SAH cost
+//   -> 3 passes of SAH treelet restructuring (7-leaf treelets, gamma = 7, 14, 28; Karras & Aila 2013)
+//   -> collapse subtrees of <= 4 triangles to leaves -> depth-first triangle order
+//   -> emit 64-B nodes + 48-B triangles.
 #pragma once
 #include "ohb_traverse.h"
 
@@ -31,8 +33,9 @@ struct BuildArrays {
     // hierarchy over n-1 internal nodes
     int32_t* left; int32_t* right;           // child: >=0 internal, <0 => ~leafIndex (sorted position)
     int32_t* parentInner; int32_t* parentLeaf;
-    uint32_t* rangeFirst; uint32_t* rangeLast;
-    f4* nodeLo; f4* nodeHi;                  // internal node bounds
+    uint32_t* nodeFirst;                     // n-1 : depth-first position of the node's first triangle
+    uint32_t* leafPos;                       // n   : depth-first position of each sorted leaf
+    f4* nodeLo; f4* nodeHi;                  // internal nodes: (lo, triangle count bits) (hi, SAH cost of the subtree)
     uint32_t* visit;                         // n-1 atomic flags
     int32_t* newIndex;                       // n-1 : index in the emitted array or -1
     uint32_t* emitCounter;                   // 1
@@ -154,30 +157,144 @@ OHB_HD void buildHierarchyNode(const BuildArrays& b, int i) {
     if (lo == gamma) { lc = ~gamma; b.parentLeaf[gamma] = i; } else { lc = gamma; b.parentInner[gamma] = i; }
     if (hi == gamma + 1) { rc = ~(gamma + 1); b.parentLeaf[gamma + 1] = i; } else { rc = gamma + 1; b.parentInner[gamma + 1] = i; }
     b.left[i] = lc; b.right[i] = rc;
-    b.rangeFirst[i] = uint32_t(lo); b.rangeLast[i] = uint32_t(hi);
     if (i == 0) b.parentInner[0] = -1;
 }
 
-// Stage 5: bottom-up refit.  Thread per sorted leaf; the second arrival at a node merges.
-OHB_HD void refitFromLeaf(const BuildArrays& b, uint32_t leaf) {
+// ---- coherent (L2) accesses for arrays that other threads of the same kernel write --------------------------------
+OHB_HD f4 ldcg4(const f4* p) {
+#if OHB_DEVICE_CODE
+    float4 v = __ldcg(reinterpret_cast<const float4*>(p)); return mk4(v.x, v.y, v.z, v.w);
+#else
+    return *p;
+#endif
+}
+OHB_HD int32_t ldcgi(const int32_t* p) {
+#if OHB_DEVICE_CODE
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+OHB_HD float boxArea(f3 lo, f3 hi) { f3 e = hi - lo; return 2.0f * (e.x * e.y + e.y * e.z + e.z * e.x); }
+
+// SAH constants of the optimiser (Karras & Aila 2013): Ci = 1.2 per node visit, Ct = 1 per triangle test.
+#define OHB_SAH_CI 1.2f
+#define OHB_SAH_CT 1.0f
+#define OHB_TREELET_LEAVES 7
+
+// Per-node record kept in nodeLo/nodeHi: (lo, triangle count as bits) and (hi, SAH cost of the subtree).
+struct NodeInfo { f3 lo, hi; uint32_t cnt; float cost; };
+OHB_HD NodeInfo nodeInfo(const BuildArrays& b, int c) {
+    NodeInfo r;
+    if (c < 0) {
+        uint32_t a = b.vals[~c]; r.lo = xyz(b.primLo[a]); r.hi = xyz(b.primHi[a]); r.cnt = 1u; r.cost = OHB_SAH_CT * boxArea(r.lo, r.hi);
+    } else {
+        f4 l = ldcg4(b.nodeLo + c), h = ldcg4(b.nodeHi + c); r.lo = xyz(l); r.hi = xyz(h); r.cnt = f2u(l.w); r.cost = h.w;
+    }
+    return r;
+}
+OHB_HD void writeNode(const BuildArrays& b, int n, f3 lo, f3 hi, uint32_t cnt, float childCost) {
+    float A = boxArea(lo, hi);
+    float cost = (cnt <= OHB_MAX_LEAF) ? OHB_SAH_CT * A * float(cnt) : OHB_SAH_CI * A + childCost;   // <= 4 triangles collapse to one leaf
+    b.nodeLo[n] = mk4(lo, u2f(cnt)); b.nodeHi[n] = mk4(hi, cost);
+}
+
+// Treelet restructuring (Karras & Aila 2013, "Fast parallel construction of high-quality bounding volume
+// hierarchies", §3): the treelet of up to 7 leaves with the largest surface areas below `root` is rebuilt into the
+// SAH-optimal topology by dynamic programming over its 2^7 leaf subsets; the treelet's own internal nodes are
+// reused, subtrees hanging below the treelet leaves are untouched.  One thread per treelet (the DP tables live in
+// local memory); sibling subtrees are processed concurrently by the bottom-up sweep.
+OHB_HD void optimizeTreelet(const BuildArrays& b, int root) {
+    const int NL = OHB_TREELET_LEAVES;
+    int leaves[NL], internal[NL - 1]; int nl = 2, ni = 1;
+    internal[0] = root; leaves[0] = ldcgi(b.left + root); leaves[1] = ldcgi(b.right + root);
+    NodeInfo info[NL];
+    info[0] = nodeInfo(b, leaves[0]); info[1] = nodeInfo(b, leaves[1]);
+    while (nl < NL) {
+        int best = -1; float bestA = -1.0f;
+        for (int k = 0; k < nl; k++) if (leaves[k] >= 0 && info[k].cnt > OHB_MAX_LEAF) { float a = boxArea(info[k].lo, info[k].hi); if (a > bestA) { bestA = a; best = k; } }
+        if (best < 0) break;
+        int c = leaves[best]; internal[ni++] = c;
+        leaves[best] = ldcgi(b.left + c); leaves[nl] = ldcgi(b.right + c);
+        info[best] = nodeInfo(b, leaves[best]); info[nl] = nodeInfo(b, leaves[nl]); nl++;
+    }
+    if (nl < 3) return;
+    const int full = (1 << nl) - 1;
+    float area[1 << NL], copt[1 << NL]; uint8_t part[1 << NL];
+    for (int s = 1; s <= full; s++) {
+        f3 lo = mk3(3.0e38f), hi = mk3(-3.0e38f);
+        for (int k = 0; k < nl; k++) if (s & (1 << k)) { lo = vmin(lo, info[k].lo); hi = vmax(hi, info[k].hi); }
+        area[s] = boxArea(lo, hi);
+    }
+    for (int k = 0; k < nl; k++) copt[1 << k] = info[k].cost;
+    for (int s = 3; s <= full; s++) {
+        if ((s & (s - 1)) == 0) continue;                 // singletons
+        float best = 3.0e38f; int bp = 0;
+        int delta = (s - 1) & s;                          // s without its lowest bit
+        int p = (-delta) & s;
+        do { float c = copt[p] + copt[s ^ p]; if (c < best) { best = c; bp = p; } p = (p - delta) & s; } while (p != 0);
+        copt[s] = OHB_SAH_CI * area[s] + best; part[s] = uint8_t(bp);
+    }
+    float oldCost = ldcg4(b.nodeHi + root).w;
+    if (!(copt[full] < oldCost * 0.99999f)) return;       // keep the current topology unless strictly better
+    // rebuild: the treelet's internal nodes are re-assigned top-down from the full set
+    int stackN[NL], stackS[NL]; int sp = 0, next = 1;
+    stackN[0] = root; stackS[0] = full; sp = 1;
+    while (sp) {
+        sp--; int n = stackN[sp], s = stackS[sp];
+        int sides[2] = {int(part[s]), s ^ int(part[s])}; int child[2];
+        for (int h = 0; h < 2; h++) {
+            int q = sides[h];
+            if ((q & (q - 1)) == 0) {
+                int k = 0; while (!(q & (1 << k))) k++;
+                child[h] = leaves[k];
+                if (child[h] >= 0) b.parentInner[child[h]] = n; else b.parentLeaf[~child[h]] = n;
+            } else {
+                child[h] = internal[next++]; b.parentInner[child[h]] = n;
+                stackN[sp] = child[h]; stackS[sp] = q; sp++;
+            }
+        }
+        b.left[n] = child[0]; b.right[n] = child[1];
+        f3 lo = mk3(3.0e38f), hi = mk3(-3.0e38f); uint32_t cnt = 0u;
+        for (int k = 0; k < nl; k++) if (s & (1 << k)) { lo = vmin(lo, info[k].lo); hi = vmax(hi, info[k].hi); cnt += info[k].cnt; }
+        b.nodeLo[n] = mk4(lo, u2f(cnt)); b.nodeHi[n] = mk4(hi, copt[s]);
+    }
+}
+
+// Stage 5: bottom-up sweep.  Thread per sorted leaf; the second arrival at a node merges its children (box, triangle
+// count, SAH cost) and, when `gamma` > 0 and the subtree holds at least gamma triangles, restructures the treelet
+// rooted there before climbing on.  gamma = 0 is the plain refit.
+OHB_HD void sweepFromLeaf(const BuildArrays& b, uint32_t leaf, uint32_t gamma) {
     int node = b.parentLeaf[leaf];
     while (node >= 0) {
         fenceDevice();
         if (atomicIncU32(b.visit + node) == 0u) return;    // first arrival: sibling not ready
         fenceDevice();
-        int lc = b.left[node], rc = b.right[node];
-        f3 llo, lhi, rlo, rhi;
-        if (lc < 0) { uint32_t a = b.vals[~lc]; llo = xyz(b.primLo[a]); lhi = xyz(b.primHi[a]); } else { llo = xyz(b.nodeLo[lc]); lhi = xyz(b.nodeHi[lc]); }
-        if (rc < 0) { uint32_t a = b.vals[~rc]; rlo = xyz(b.primLo[a]); rhi = xyz(b.primHi[a]); } else { rlo = xyz(b.nodeLo[rc]); rhi = xyz(b.nodeHi[rc]); }
-        b.nodeLo[node] = mk4(vmin(llo, rlo), 0.0f); b.nodeHi[node] = mk4(vmax(lhi, rhi), 0.0f);
-        node = b.parentInner[node];
+        NodeInfo l = nodeInfo(b, ldcgi(b.left + node)), r = nodeInfo(b, ldcgi(b.right + node));
+        uint32_t cnt = l.cnt + r.cnt;
+        writeNode(b, node, vmin(l.lo, r.lo), vmax(l.hi, r.hi), cnt, l.cost + r.cost);
+        if (gamma && cnt >= gamma) optimizeTreelet(b, node);
+        node = ldcgi(b.parentInner + node);
     }
 }
 
-OHB_HD uint32_t nodeCount(const BuildArrays& b, int i) { return b.rangeLast[i] - b.rangeFirst[i] + 1u; }
-OHB_HD float boxArea(f3 lo, f3 hi) { f3 e = hi - lo; return 2.0f * (e.x * e.y + e.y * e.z + e.z * e.x); }
+OHB_HD uint32_t nodeCount(const BuildArrays& b, int i) { return f2u(b.nodeLo[i].w); }
+// Stage 6a: position of a subtree's first triangle in depth-first order = sum, over the ancestors where the path
+// turns right, of the left sibling's triangle count.  (After restructuring, subtrees are no longer contiguous
+// ranges of the Morton order, so triangles are re-emitted in DFS order.)
+OHB_HD uint32_t dfsOffset(const BuildArrays& b, int child, int parent) {
+    uint32_t off = 0u;
+    while (parent >= 0) {
+        int lc = b.left[parent];
+        if (lc != child) off += (lc < 0) ? 1u : nodeCount(b, lc);
+        child = parent; parent = b.parentInner[parent];
+    }
+    return off;
+}
+OHB_HD void computeNodeFirst(const BuildArrays& b, int i) { b.nodeFirst[i] = dfsOffset(b, i, b.parentInner[i]); }
+OHB_HD void computeLeafPos(const BuildArrays& b, uint32_t leaf) { b.leafPos[leaf] = dfsOffset(b, ~int(leaf), b.parentLeaf[leaf]); }
 
-// Stage 6a: which internal nodes survive the collapse (more than OHB_MAX_LEAF triangles below).
+// Stage 6b: which internal nodes survive the collapse (more than OHB_MAX_LEAF triangles below).
 OHB_HD void assignNodeIndex(const BuildArrays& b, int i) {
     if (nodeCount(b, i) <= OHB_MAX_LEAF) { b.newIndex[i] = -1; return; }
     b.newIndex[i] = (i == 0) ? 0 : int32_t(atomicIncU32(b.emitCounter));   // counter starts at 1
@@ -191,14 +308,14 @@ OHB_HD void padBox(f3& lo, f3& hi) {
 OHB_HD void childRefAndBox(const BuildArrays& b, int c, int32_t& ref, f3& lo, f3& hi) {
     if (c < 0) {
         uint32_t pos = uint32_t(~c); uint32_t a = b.vals[pos];
-        ref = makeLeafRef(pos, 1u); lo = xyz(b.primLo[a]); hi = xyz(b.primHi[a]);
+        ref = makeLeafRef(b.leafPos[pos], 1u); lo = xyz(b.primLo[a]); hi = xyz(b.primHi[a]);
     } else {
         lo = xyz(b.nodeLo[c]); hi = xyz(b.nodeHi[c]);
         uint32_t cnt = nodeCount(b, c);
-        ref = (cnt <= OHB_MAX_LEAF) ? makeLeafRef(b.rangeFirst[c], cnt) : b.newIndex[c];
+        ref = (cnt <= OHB_MAX_LEAF) ? makeLeafRef(b.nodeFirst[c], cnt) : b.newIndex[c];
     }
 }
-// Stage 6b: emit the 64-B node of a surviving internal node + SAH bookkeeping.
+// Stage 6c: emit the 64-B node of a surviving internal node + SAH bookkeeping (Ci = Ct = 1 for the reported cost).
 OHB_HD void emitNode(const BuildArrays& b, int i) {
     int32_t ni = b.newIndex[i];
     if (ni < 0) return;
@@ -216,12 +333,12 @@ OHB_HD void emitNode(const BuildArrays& b, int i) {
     np[2] = mk4(lo0.z, hi0.z, lo1.z, hi1.z);
     np[3] = mk4(u2f(uint32_t(r0)), u2f(uint32_t(r1)), 0.0f, 0.0f);
 }
-// Stage 7: triangles into leaf (sorted) order.
+// Stage 7: triangles into depth-first leaf order.
 OHB_HD void emitTri(const BuildArrays& b, uint32_t pos) {
-    uint32_t a = b.vals[pos];
-    b.tris[size_t(pos) * 3 + 0] = b.wtri[size_t(a) * 3 + 0];
-    b.tris[size_t(pos) * 3 + 1] = b.wtri[size_t(a) * 3 + 1];
-    b.tris[size_t(pos) * 3 + 2] = b.wtri[size_t(a) * 3 + 2];
+    uint32_t a = b.vals[pos]; uint32_t dst = b.n >= 2u ? b.leafPos[pos] : pos;
+    b.tris[size_t(dst) * 3 + 0] = b.wtri[size_t(a) * 3 + 0];
+    b.tris[size_t(dst) * 3 + 1] = b.wtri[size_t(a) * 3 + 1];
+    b.tris[size_t(dst) * 3 + 2] = b.wtri[size_t(a) * 3 + 2];
 }
 
 }  // namespace ohb

@@ -24,7 +24,10 @@ static inline unsigned gridFor(uint64_t n, unsigned threads) { return (unsigned)
 __global__ void k_world_tris(BuildArrays b) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < b.n) buildWorldTri(b, i); }
 __global__ void k_morton(BuildArrays b) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < b.n) buildMorton(b, i); }
 __global__ void k_hierarchy(BuildArrays b) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i + 1 < b.n) buildHierarchyNode(b, int(i)); }
-__global__ void k_refit(BuildArrays b) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < b.n) refitFromLeaf(b, i); }
+__global__ void k_sweep(BuildArrays b, uint32_t gamma) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < b.n) sweepFromLeaf(b, i, gamma); }
+__global__ void k_clear_visit(BuildArrays b) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i + 1 < b.n) b.visit[i] = 0u; }
+__global__ void k_node_first(BuildArrays b) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i + 1 < b.n) computeNodeFirst(b, int(i)); }
+__global__ void k_leaf_pos(BuildArrays b) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < b.n) computeLeafPos(b, i); }
 __global__ void k_assign_index(BuildArrays b) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i + 1 < b.n) assignNodeIndex(b, int(i)); }
 __global__ void k_emit_nodes(BuildArrays b) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i + 1 < b.n) emitNode(b, int(i)); }
 __global__ void k_emit_tris(BuildArrays b) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < b.n) emitTri(b, i); }
@@ -152,7 +155,7 @@ void radixSort64(uint64_t* keys, uint32_t* vals, uint64_t* keysTmp, uint32_t* va
     }
 }
 
-void launchBuild(const BuildArrays& b, uint64_t* keysTmp, uint32_t* valsTmp, uint32_t* sortTemp, cudaStream_t st, uint64_t* launches) {
+void launchBuild(const BuildArrays& b, uint64_t* keysTmp, uint32_t* valsTmp, uint32_t* sortTemp, uint32_t treeletPasses, cudaStream_t st, uint64_t* launches) {
     const unsigned T = 256; unsigned g = gridFor(b.n, T);
     k_init_build<<<g, T, 0, st>>>(b);
     k_world_tris<<<g, T, 0, st>>>(b);
@@ -161,7 +164,15 @@ void launchBuild(const BuildArrays& b, uint64_t* keysTmp, uint32_t* valsTmp, uin
     radixSort64(b.keys, b.vals, keysTmp, valsTmp, b.n, sortTemp, st, launches);
     if (b.n >= 2) {
         k_hierarchy<<<g, T, 0, st>>>(b);
-        k_refit<<<g, T, 0, st>>>(b);
+        k_sweep<<<g, T, 0, st>>>(b, 0u);                        // refit + counts + SAH cost
+        *launches += 2;
+        for (uint32_t pass = 0, gamma = OHB_TREELET_LEAVES; pass < treeletPasses; pass++, gamma *= 2u) {
+            k_clear_visit<<<g, T, 0, st>>>(b);
+            k_sweep<<<gridFor(b.n, 64), 64, 0, st>>>(b, gamma);  // treelet restructuring (1.2 KB of DP tables per thread)
+            *launches += 2;
+        }
+        k_node_first<<<g, T, 0, st>>>(b);
+        k_leaf_pos<<<g, T, 0, st>>>(b);
         k_assign_index<<<g, T, 0, st>>>(b);
         k_emit_nodes<<<g, T, 0, st>>>(b);
         *launches += 4;

@@ -15,6 +15,7 @@
 #include <numeric>
 #include <cstring>
 #include <cmath>
+#include <cstdlib>
 
 using namespace ohb;
 
@@ -105,7 +106,7 @@ void* emul_scene_create(const emul_scene_desc* d) {
     b.positions = s->positions.data(); b.posStride = s->stride; b.indices = s->indices.data(); b.triInst = s->triInst.data(); b.instXform = s->instXform.data();
     b.activeTris = s->active.data(); b.n = n; b.wtri = wtri.data(); b.primLo = primLo.data(); b.primHi = primHi.data(); b.boundsBits = bounds.data();
     b.keys = keys.data(); b.vals = vals.data(); b.left = left.data(); b.right = right.data(); b.parentInner = pin.data(); b.parentLeaf = pleaf.data();
-    b.rangeFirst = rf.data(); b.rangeLast = rl.data(); b.nodeLo = nodeLo.data(); b.nodeHi = nodeHi.data(); b.visit = visit.data(); b.newIndex = newIndex.data();
+    b.nodeFirst = rf.data(); b.leafPos = rl.data(); b.nodeLo = nodeLo.data(); b.nodeHi = nodeHi.data(); b.visit = visit.data(); b.newIndex = newIndex.data();
     b.emitCounter = emitCounter.data(); b.sah = sah.data(); b.nodes = s->nodes.data(); b.tris = s->tris.data();
     bounds[0] = bounds[1] = bounds[2] = 0xFFFFFFFFu; bounds[3] = bounds[4] = bounds[5] = 0u;
     for (uint32_t i = 0; i < n; i++) buildWorldTri(b, i);
@@ -119,7 +120,14 @@ void* emul_scene_create(const emul_scene_desc* d) {
     }
     if (n >= 2) {
         for (uint32_t i = 0; i + 1 < n; i++) buildHierarchyNode(b, int(i));
-        for (uint32_t i = 0; i < n; i++) refitFromLeaf(b, i);
+        for (uint32_t i = 0; i < n; i++) sweepFromLeaf(b, i, 0u);
+        const char* tp = getenv("OHB_TREELET_PASSES"); uint32_t passes = tp ? uint32_t(atoi(tp)) : 3u;
+        for (uint32_t pass = 0, gamma = OHB_TREELET_LEAVES; pass < passes; pass++, gamma *= 2u) {
+            std::fill(visit.begin(), visit.end(), 0u);
+            for (uint32_t i = 0; i < n; i++) sweepFromLeaf(b, i, gamma);
+        }
+        for (uint32_t i = 0; i + 1 < n; i++) computeNodeFirst(b, int(i));
+        for (uint32_t i = 0; i < n; i++) computeLeafPos(b, i);
         for (uint32_t i = 0; i + 1 < n; i++) assignNodeIndex(b, int(i));
         for (uint32_t i = 0; i + 1 < n; i++) emitNode(b, int(i));
     }
