@@ -280,7 +280,8 @@ struct PathClosestIO {
         hits += hit;
     }
 };
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace_closest(SceneDev sc, PathArrays P, uint32_t* work) {
+template <int MINB>
+__global__ void __launch_bounds__(TRACE_THREADS, MINB) k_trace_closest(SceneDev sc, PathArrays P, uint32_t* work) {
     PathClosestIO io{P, 0u};
     persistentTrace<false>(sc, *P.countIn, work, io);
     uint32_t hits = __reduce_add_sync(0xffffffffu, io.hits);
@@ -298,9 +299,23 @@ struct PathShadowIO {
         pend[tag >> 1] = mk4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 };
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace_shadow(SceneDev sc, PathArrays P, uint32_t* work) {
+template <int MINB>
+__global__ void __launch_bounds__(TRACE_THREADS, MINB) k_trace_shadow(SceneDev sc, PathArrays P, uint32_t* work) {
     PathShadowIO io{P};
     persistentTrace<true>(sc, *P.shCount, work, io);
+}
+static int traceOcc() { static const int v = []() { const char* e = getenv("OHB_TRACE_OCC"); return e ? atoi(e) : 12; }(); return v; }
+static void launchTraceClosest(unsigned smGrid8, const SceneDev& sc, const PathArrays& P, uint32_t* work, cudaStream_t st) {
+    int o = traceOcc(); unsigned grid = smGrid8 / 8u * unsigned(o >= 16 ? 16 : (o >= 12 ? 12 : 9));
+    if (o >= 16)      k_trace_closest<16><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work);
+    else if (o >= 12) k_trace_closest<12><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work);
+    else              k_trace_closest<9><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work);
+}
+static void launchTraceShadow(unsigned smGrid8, const SceneDev& sc, const PathArrays& P, uint32_t* work, cudaStream_t st) {
+    int o = traceOcc(); unsigned grid = smGrid8 / 8u * unsigned(o >= 16 ? 16 : (o >= 12 ? 12 : 9));
+    if (o >= 16)      k_trace_shadow<16><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work);
+    else if (o >= 12) k_trace_shadow<12><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work);
+    else              k_trace_shadow<9><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work);
 }
 #define SHADE_THREADS 128
 __global__ void __launch_bounds__(SHADE_THREADS) k_raygen(FrameParams fr, PathArrays P, uint32_t total) {
@@ -366,7 +381,7 @@ void launchOfflineBatch(const SceneDev& sc, const FrameParams& fr, PathArrays P,
     static const int bounceOcc = []() { const char* e = getenv("OHB_BOUNCE_OCC"); return e ? atoi(e) : 8; }();
     for (uint32_t it = 0; it < iters; it++) {
         if (th) th->begin(0, st);
-        k_trace_closest<<<traceGrid, TRACE_THREADS, 0, st>>>(sc, P, work);
+        launchTraceClosest(traceGrid, sc, P, work, st);
         if (th) th->end(0, st);
         if (th) th->begin(4, st);
         k_surface<<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P);
@@ -377,7 +392,7 @@ void launchOfflineBatch(const SceneDev& sc, const FrameParams& fr, PathArrays P,
         else                     k_bounce<1><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P);
         if (th) th->end(1, st);
         if (th) th->begin(2, st);
-        k_trace_shadow<<<traceGrid, TRACE_THREADS, 0, st>>>(sc, P, work + 1);
+        launchTraceShadow(traceGrid, sc, P, work + 1, st);
         if (th) th->end(2, st);
         k_advance<<<1, 32, 0, st>>>(P, work, 0);
         *launches += 5;
@@ -425,7 +440,7 @@ void launchRealtimeFrame(const SceneDev& sc, const FrameParams& fr, PathArrays P
     uint32_t iters = 2u + fr.maxBounces;          // primary + chain B + the ReSTIR GI bounce
     for (uint32_t it = 0; it < iters; it++) {
         if (th) th->begin(0, st);
-        k_trace_closest<<<grid, TRACE_THREADS, 0, st>>>(sc, P, work);
+        launchTraceClosest(grid, sc, P, work, st);
         if (th) th->end(0, st);
         if (th) th->begin(4, st);
         k_surface<<<grid, SHADE_THREADS, 0, st>>>(sc, fr, P);
@@ -434,7 +449,7 @@ void launchRealtimeFrame(const SceneDev& sc, const FrameParams& fr, PathArrays P
         k_bounce_rt<<<grid, SHADE_THREADS, 0, st>>>(sc, fr, P);
         if (th) th->end(1, st);
         if (th) th->begin(2, st);
-        k_trace_shadow<<<grid, TRACE_THREADS, 0, st>>>(sc, P, work + 1);
+        launchTraceShadow(grid, sc, P, work + 1, st);
         if (th) th->end(2, st);
         k_advance<<<1, 32, 0, st>>>(P, work, 0);
         *launches += 5;
