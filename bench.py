@@ -62,6 +62,16 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic(workload: str, integrator: str, kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture
+    (profiles/traffic.json, written by tools/ncu_traffic.py); None when no capture exists for this workload."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))[f"{workload}/{integrator}"][kernel]["bytes_per_launch"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -149,11 +159,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="helmet", choices=["helmet", "cornell", "synthetic2m"])
-    ap.add_argument("--spp-step", type=int, default=16, help="samples per pixel per step")
+    ap.add_argument("--spp-step", type=int, default=None, help="samples per pixel per step (default 16 offline, 1 realtime)")
+    ap.add_argument("--integrator", default="offline", choices=["offline", "realtime"],
+                    help="realtime = config 3: one frame per step (ReSTIR GI temporal + spatial, EMA, a-trous), 0.5 deg/frame orbit, N=1 only")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bounded CPU-baseline sample (rank 0, N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.spp_step is None: args.spp_step = 1 if args.integrator == "realtime" else 16
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
@@ -171,8 +184,17 @@ def main():
 
     from ohao_engine_b200 import binding as B
     ps, cam, desc = make_workload(args.workload)
-    r = B.Renderer(W, H, device=local)
+    realtime = args.integrator == "realtime"
+    if realtime and world > 1:
+        raise SystemExit("bench.py: the realtime profile shards by tile + halo only (DESIGN.md §5); its headline is N=1")
+    r = B.Renderer(W, H, profile=B.PROFILE_REALTIME if realtime else B.PROFILE_OFFLINE, device=local)
     r.set_scene(ps)
+    if realtime:
+        desc = desc.replace("offline, 4 bounces", "realtime, 2 bounces + ReSTIR GI temporal/spatial + EMA + a-trous, 0.5 deg/frame orbit")
+        stg = r.get_settings(); stg.samples_per_frame = args.spp_step; r.set_rt_render_settings(stg)
+        import copy, math as _m
+        base_cam = copy.deepcopy(cam); frame_no = [0]
+        radius = _m.hypot(base_cam.position[0], base_cam.position[2]); ang0 = _m.atan2(base_cam.position[2], base_cam.position[0])
     st = r.accel_stats()
     v, p = cam.view(), cam.proj(W, H)
     spp = args.spp_step
@@ -194,9 +216,18 @@ def main():
             dist.barrier()
         r.synchronize(); torch.cuda.synchronize()
 
+    def step():
+        """One pass of the hot path: offline = spp samples per pixel; realtime = one frame of the orbit."""
+        if not realtime:
+            r.render(v, p, spp); return
+        a = ang0 + _m.radians(0.5 * frame_no[0]); frame_no[0] += 1
+        c = copy.deepcopy(base_cam); c.position = (radius * _m.cos(a), base_cam.position[1], radius * _m.sin(a)); c.yaw = _m.degrees(a) + 180.0
+        r.notify_camera_changed()
+        r.render_realtime(c.view(), p)
+
     # ---- warm-up -----------------------------------------------------------------------------------
     for _ in range(args.warmup):
-        r.render(v, p, spp)
+        step()
     barrier()
 
     # ---- timed region: device-resident ---------------------------------------------------------------
@@ -205,7 +236,7 @@ def main():
     barrier()
     r.timer_start()
     for _ in range(args.steps):
-        r.render(v, p, spp)
+        step()
     if world > 1:
         r.synchronize()
         dist.reduce(accum_t, dst=0, op=dist.ReduceOp.SUM)       # NCCL over NVLink: one reduce per image
@@ -230,12 +261,12 @@ def main():
     mat = np.ascontiguousarray(ps.mat_colors, np.float32); lights = np.ascontiguousarray(ps.light_ssbo, np.uint8)
     ldr = np.empty((H, W, 4), np.uint8)
     h2d = mat.nbytes + lights.nbytes + 128; d2h = ldr.nbytes
-    r.reset_accumulation()
+    if not realtime: r.reset_accumulation()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         r.update_rt_material_params(mat); r.update_rt_light_params(lights)      # updateRTMaterialParams / updateRTLightParams
-        r.render(v, p, spp)
+        step()
         if world > 1: r.resolve()
         r.get_pixels(ldr)                                                          # getPixelSpan(): blocking readback
     barrier()
@@ -250,7 +281,8 @@ def main():
         # algorithmic bytes per unit of each kernel (DESIGN.md "Kernels"): rays x B_ray(N) for the traversal kernels,
         # 248 B per path for k_surface (ray 32 + hit 16 + 136 B surface gather + 64 B payload), 304 B per path for k_bounce
         units = {"trace_closest": (cnt["closest_rays"], br), "trace_shadow": (cnt["shadow_rays"], br),
-                 "surface": (cnt["closest_rays"], 248), "bounce": (cnt["closest_rays"], 304), "film": (cnt["samples"], 36)}
+                 "surface": (cnt["closest_rays"], 248), "bounce": (cnt["closest_rays"], 304), "film": (cnt["samples"], 36),
+                 "rt_pixel": (W * H * args.steps, 352 * spp + 416)}     # per pixel: N finished path records + 10 history planes in / 6 out
         kern = {}
         for k, x in tim.items():
             if x["launches"] == 0: continue
@@ -264,7 +296,8 @@ def main():
         out = {
             "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "resolution": [W, H], "spp_per_step": spp, "integrator": "offline", "tris": int(st.num_tris),
+            "config": {"workload": desc, "resolution": [W, H], "spp_per_step": spp, "integrator": args.integrator, "tris": int(st.num_tris),
+                       "frames_per_s": (args.steps / (ms * 1e-3)) if realtime else None, "treelet_passes": int(st.treelet_passes),
                        "bvh_nodes": int(st.num_nodes), "bvh_sah": round(float(st.sah_cost), 2), "bvh_build_ms": round(float(st.build_ms), 3),
                        "parallelism": f"spp-shard x{world}" if world > 1 else "single GPU",
                        "l2": "path-state working set %.1f GB per step >> 126 MB L2 (no explicit flush)" % (W * H * min(spp, 4) * 288 / 1e9)},
@@ -274,7 +307,7 @@ def main():
                      "gsamples_sbe_per_s": (tot["closest_rays"] + tot["shadow_rays"]) / (ms * 1e-3) / 2e9},
             "kernels": kern,
             "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": dk["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dk["frac"],
-                         "traffic": None, "peak_source": peak_src, "bytes_per_unit": dk["bytes_per_unit"], "units_per_launch": dk["units_per_launch"],
+                         "traffic": measured_traffic(args.workload, args.integrator, "k_" + dom), "peak_source": peak_src, "bytes_per_unit": dk["bytes_per_unit"], "units_per_launch": dk["units_per_launch"],
                          "avg_launch_ms": dk["avg_launch_ms"], "share_of_step": dk["share_of_step"]},
             "e2e": {"value": e2e_val, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(cnt["kernel_launches"]),

@@ -286,5 +286,5 @@ class Renderer:
     def timing(self) -> dict:
         ms = (C.c_float * 8)(); cnt = (C.c_uint64 * 8)()
         self._ck(self.lib.ohb_get_timing_detail(self.h, C.byref(ms), C.byref(cnt)), "ohb_get_timing_detail")
-        names = ("trace_closest", "bounce", "trace_shadow", "film", "surface")
+        names = ("trace_closest", "bounce", "trace_shadow", "film", "surface", "rt_pixel")
         return {n: dict(ms=float(ms[i]), launches=int(cnt[i])) for i, n in enumerate(names)}
