@@ -99,7 +99,10 @@ typedef struct ohb_counters {
 
 /* BVH statistics for DESIGN.md / bench (node count, SAH cost, build time). */
 typedef struct ohb_accel_stats {
-    uint32_t num_tris, num_nodes, num_leaves, max_leaf_tris;
+    uint32_t num_tris;       /* triangles the BVH was built over                    */
+    uint32_t num_nodes;      /* 8-wide nodes (80 B each)                            */
+    uint32_t levels;         /* depth of the 8-wide tree                            */
+    uint32_t max_leaf_tris;  /* triangles per leaf child                            */
     float    sah_cost;       /* SAH cost of the final tree (Ct=1, Ci=1)             */
     float    build_ms;       /* device time of the last ohb_build_accel             */
     uint32_t treelet_passes; uint32_t _pad;

@@ -36,7 +36,7 @@ class Counters(C.Structure):
 
 
 class AccelStats(C.Structure):
-    _fields_ = [("num_tris", C.c_uint32), ("num_nodes", C.c_uint32), ("num_leaves", C.c_uint32), ("max_leaf_tris", C.c_uint32),
+    _fields_ = [("num_tris", C.c_uint32), ("num_nodes", C.c_uint32), ("levels", C.c_uint32), ("max_leaf_tris", C.c_uint32),
                 ("sah_cost", C.c_float), ("build_ms", C.c_float), ("treelet_passes", C.c_uint32), ("_pad", C.c_uint32)]
 
 

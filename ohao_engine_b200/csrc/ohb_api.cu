@@ -77,13 +77,13 @@ struct ohb_ctx {
     std::vector<ohb_instance> instances;
     uint32_t lightCount = 0, envMapTexIdx = 0xFFFFFFFFu; float envIntensity = 1.0f;
     uint32_t texW = 0, texH = 0, texLayers = 0, envW = 0, envH = 0; float envIntegral = 0.0f;
-    bool accelValid = false; int32_t rootRef = 0; uint32_t numActive = 0;
+    bool accelValid = false; uint32_t numActive = 0;
     ohb_accel_stats stats{};
     // scene (device)
     DevBuf positions, indices, normals, uvs, matIds, triInst, instXform, instNormalMat, instInv, matColors, tex, lights, env, marg, cond, rowTotal, integral;
     // accel (device)
     DevBuf activeTris, wtri, primLo, primHi, boundsBits, keys, vals, keysTmp, valsTmp, sortTemp, left, right, parentInner, parentLeaf,
-           nodeFirst, leafPos, nodeLo, nodeHi, visit, newIndex, emitCounter, sah, nodes, tris;
+           nodeLo, nodeHi, visit, wideCounters, wideItemsA, wideItemsB, sah, wnodes, tris;
     // paths (device)
     DevBuf rayO, rayD, hit, thr, rad, pendA, pendB, meta, fh0, fh1, fh2, fh3, pay0, pay1, pay2, pay3, shO, shD, queueA, queueB, queueS, sobolTab, smallCounters, devCounters;
     uint32_t pathCapacity = 0;
@@ -176,8 +176,8 @@ void ohb_destroy(ohb_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf* all[] = {&c->positions, &c->indices, &c->normals, &c->uvs, &c->matIds, &c->triInst, &c->instXform, &c->instNormalMat, &c->instInv, &c->matColors,
                      &c->tex, &c->lights, &c->env, &c->marg, &c->cond, &c->rowTotal, &c->integral, &c->activeTris, &c->wtri, &c->primLo, &c->primHi, &c->boundsBits,
-                     &c->keys, &c->vals, &c->keysTmp, &c->valsTmp, &c->sortTemp, &c->left, &c->right, &c->parentInner, &c->parentLeaf, &c->nodeFirst, &c->leafPos,
-                     &c->nodeLo, &c->nodeHi, &c->visit, &c->newIndex, &c->emitCounter, &c->sah, &c->nodes, &c->tris, &c->rayO, &c->rayD, &c->hit, &c->thr, &c->rad,
+                     &c->keys, &c->vals, &c->keysTmp, &c->valsTmp, &c->sortTemp, &c->left, &c->right, &c->parentInner, &c->parentLeaf,
+                     &c->nodeLo, &c->nodeHi, &c->visit, &c->wideCounters, &c->wideItemsA, &c->wideItemsB, &c->sah, &c->wnodes, &c->tris, &c->rayO, &c->rayD, &c->hit, &c->thr, &c->rad,
                      &c->pendA, &c->pendB, &c->meta, &c->fh0, &c->fh1, &c->fh2, &c->fh3, &c->pay0, &c->pay1, &c->pay2, &c->pay3, &c->shO, &c->shD, &c->queueA, &c->queueB, &c->queueS, &c->sobolTab, &c->smallCounters, &c->devCounters,
                      &c->accum, &c->ldr, &c->albedoAOV, &c->normalAOV, &c->sampleDump, &c->hookRays, &c->hookOut, &c->hookAux,
                      &c->accumPrev, &c->surf[0], &c->surf[1], &c->shad[0], &c->shad[1], &c->res[0][0], &c->res[0][1], &c->res[0][2],
@@ -295,7 +295,7 @@ int ohb_get_env_cdf(ohb_ctx* c, float* marg, float* cond, float* integral) {
 
 static void fillScene(ohb_ctx* c, SceneDev& s) {
     memset(&s, 0, sizeof(s));
-    s.nodes = c->nodes.as<f4>(); s.tris = c->tris.as<f4>(); s.rootRef = c->rootRef; s.numTris = c->accelValid ? c->numActive : 0u;
+    s.wnodes = c->wnodes.as<u4>(); s.tris = c->tris.as<f4>(); s.numTris = c->accelValid ? c->numActive : 0u;
     s.indices = c->indices.as<uint32_t>(); s.normals = c->normals.as<f4>(); s.uvs = c->uvs.as<f2>(); s.matIds = c->matIds.as<uint32_t>();
     s.triInst = c->triInst.as<uint32_t>(); s.instNormalMat = c->instNormalMat.as<f4>(); s.instInv = c->instInv.as<f4>();
     s.matColors = c->matColors.as<f4>();
@@ -375,47 +375,49 @@ int ohb_build_accel(ohb_ctx* c) {
     CU(c, cudaMemcpyAsync(c->instInv.p, iv.data(), iv.size() * 4, cudaMemcpyHostToDevice, c->stream));
     memset(&c->stats, 0, sizeof(c->stats));
     c->stats.num_tris = n;
-    if (n == 0) { c->accelValid = true; c->rootRef = 0; CU(c, cudaStreamSynchronize(c->stream)); return 0; }
+    if (n == 0) { c->accelValid = true; CU(c, cudaStreamSynchronize(c->stream)); return 0; }
     size_t nn = n;
     CU(c, c->activeTris.reserve(nn * 4)); CU(c, cudaMemcpyAsync(c->activeTris.p, active.data(), nn * 4, cudaMemcpyHostToDevice, c->stream));
     CU(c, c->wtri.reserve(nn * 48)); CU(c, c->primLo.reserve(nn * 16)); CU(c, c->primHi.reserve(nn * 16)); CU(c, c->boundsBits.reserve(32));
     CU(c, c->keys.reserve(nn * 8)); CU(c, c->vals.reserve(nn * 4)); CU(c, c->keysTmp.reserve(nn * 8)); CU(c, c->valsTmp.reserve(nn * 4));
     CU(c, c->sortTemp.reserve(size_t(radixSortTempWords(n)) * 4));
     CU(c, c->left.reserve(nn * 4)); CU(c, c->right.reserve(nn * 4)); CU(c, c->parentInner.reserve(nn * 4)); CU(c, c->parentLeaf.reserve(nn * 4));
-    CU(c, c->nodeFirst.reserve(nn * 4)); CU(c, c->leafPos.reserve(nn * 4)); CU(c, c->nodeLo.reserve(nn * 16)); CU(c, c->nodeHi.reserve(nn * 16));
-    CU(c, c->visit.reserve(nn * 4)); CU(c, c->newIndex.reserve(nn * 4)); CU(c, c->emitCounter.reserve(4)); CU(c, c->sah.reserve(8));
-    CU(c, c->nodes.reserve(nn * 64)); CU(c, c->tris.reserve(nn * 48));
+    CU(c, c->nodeLo.reserve(nn * 16)); CU(c, c->nodeHi.reserve(nn * 16));
+    CU(c, c->visit.reserve(nn * 4)); CU(c, c->wideCounters.reserve(16)); CU(c, c->sah.reserve(8));
+    CU(c, c->wideItemsA.reserve((nn / 4 + 2) * sizeof(WideItem))); CU(c, c->wideItemsB.reserve((nn / 4 + 2) * sizeof(WideItem)));
+    CU(c, c->wnodes.reserve(nn * 16 * OHB_WNODE_VECS)); CU(c, c->tris.reserve(nn * 48));     // a wide node is a binary node with > 3 triangles: fewer than n
     BuildArrays b{};
     b.positions = c->positions.as<uint8_t>(); b.posStride = c->posStride; b.indices = c->indices.as<uint32_t>(); b.triInst = c->triInst.as<uint32_t>();
     b.instXform = c->instXform.as<f4>(); b.activeTris = c->activeTris.as<uint32_t>(); b.n = n;
     b.wtri = c->wtri.as<f4>(); b.primLo = c->primLo.as<f4>(); b.primHi = c->primHi.as<f4>(); b.boundsBits = c->boundsBits.as<uint32_t>();
     b.keys = c->keys.as<uint64_t>(); b.vals = c->vals.as<uint32_t>();
     b.left = c->left.as<int32_t>(); b.right = c->right.as<int32_t>(); b.parentInner = c->parentInner.as<int32_t>(); b.parentLeaf = c->parentLeaf.as<int32_t>();
-    b.nodeFirst = c->nodeFirst.as<uint32_t>(); b.leafPos = c->leafPos.as<uint32_t>(); b.nodeLo = c->nodeLo.as<f4>(); b.nodeHi = c->nodeHi.as<f4>();
-    b.visit = c->visit.as<uint32_t>(); b.newIndex = c->newIndex.as<int32_t>(); b.emitCounter = c->emitCounter.as<uint32_t>(); b.sah = c->sah.as<float>();
-    b.nodes = c->nodes.as<f4>(); b.tris = c->tris.as<f4>();
+    b.nodeLo = c->nodeLo.as<f4>(); b.nodeHi = c->nodeHi.as<f4>();
+    b.visit = c->visit.as<uint32_t>(); b.wideCounters = c->wideCounters.as<uint32_t>(); b.sah = c->sah.as<float>();
+    b.wnodes = c->wnodes.as<u4>(); b.tris = c->tris.as<f4>();
     CU(c, cudaEventRecord(c->evA, c->stream));
     static const uint32_t treeletPasses = []() { const char* e = getenv("OHB_TREELET_PASSES"); return e ? uint32_t(strtoul(e, nullptr, 10)) : 3u; }();
-    launchBuild(b, c->keysTmp.as<uint64_t>(), c->valsTmp.as<uint32_t>(), c->sortTemp.as<uint32_t>(), treeletPasses, c->stream, &c->launches);
+    launchBuild(b, c->keysTmp.as<uint64_t>(), c->valsTmp.as<uint32_t>(), c->sortTemp.as<uint32_t>(), c->wideItemsA.as<WideItem>(), c->wideItemsB.as<WideItem>(),
+                treeletPasses, c->stream, &c->launches);
     c->stats.treelet_passes = treeletPasses;
     CU(c, cudaEventRecord(c->evB, c->stream));
-    uint32_t emitted = 1; float sah[2] = {0, 0}; f4 rootLo{}, rootHi{};
+    uint32_t wc[4] = {1, 0, 0, 0}; float sah[2] = {0, 0}; f4 rootLo{}, rootHi{};
+    CU(c, cudaMemcpyAsync(wc, c->wideCounters.p, 16, cudaMemcpyDeviceToHost, c->stream));
     if (n >= 2) {
-        CU(c, cudaMemcpyAsync(&emitted, c->emitCounter.p, 4, cudaMemcpyDeviceToHost, c->stream));
-        CU(c, cudaMemcpyAsync(sah, c->sah.p, 8, cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaMemcpyAsync(&rootLo, c->nodeLo.p, 16, cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaMemcpyAsync(&rootHi, c->nodeHi.p, 16, cudaMemcpyDeviceToHost, c->stream));
     }
+    CU(c, cudaMemcpyAsync(sah, c->sah.p, 8, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     CU(c, cudaGetLastError());
-    c->rootRef = (n <= OHB_MAX_LEAF) ? makeLeafRef(0u, n) : 0;
+    if (wc[3] > OHB_MAX_LEVELS) OHB_FAIL(c, "ohb_build_accel: the 8-wide BVH is deeper than OHB_MAX_LEVELS (degenerate geometry: too many coincident triangles)");
     c->accelValid = true;
     cudaEventElapsedTime(&c->stats.build_ms, c->evA, c->evB);
-    c->stats.num_nodes = (n <= OHB_MAX_LEAF) ? 0u : emitted;
+    c->stats.num_nodes = wc[0];
     c->stats.max_leaf_tris = OHB_MAX_LEAF;
+    c->stats.levels = wc[3] + 1u;
     float ra = boxArea(xyz(rootLo), xyz(rootHi));
-    c->stats.sah_cost = (n > OHB_MAX_LEAF && ra > 0.0f) ? (sah[0] + sah[1]) / ra : float(n);
-    c->stats.num_leaves = c->stats.num_nodes ? c->stats.num_nodes + 1u : 1u;
+    c->stats.sah_cost = (n >= 2 && ra > 0.0f) ? (sah[0] + sah[1]) / ra : float(n);
     return 0;
 }
 

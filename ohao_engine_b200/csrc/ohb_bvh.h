@@ -1,5 +1,5 @@
 // ohb_bvh.h — LBVH construction, per-thread stages (Karras 2012 "Maximizing parallelism in the
-// construction of BVHs, octrees and k-d trees") + leaf collapse + 64-B node emission.
+// construction of BVHs, octrees and k-d trees") + SAH treelets + collapse into the compressed 8-wide BVH.
 //
 // Replaces RTAccelerationStructure::{createBLAS, buildTLAS} (rt_acceleration_structure.cpp:205-535),
 // i.e. vkCmdBuildAccelerationStructuresKHR, whose algorithm is inside the Vulkan driver.  The
@@ -11,8 +11,9 @@
 //   worldTriangles -> sceneBounds -> morton63 -> radix sort (key u64, val u32) -> karras hierarchy
 //   -> bottom-up sweep (atomic visit counters): AABB refit + triangle counts + SAH cost
 //   -> 3 passes of SAH treelet restructuring (7-leaf treelets, gamma = 7, 14, 28; Karras & Aila 2013)
-//   -> collapse subtrees of <= 4 triangles to leaves -> depth-first triangle order
-//   -> emit 64-B nodes + 48-B triangles.
+//   -> top-down collapse, one launch per level: greedy 8-wide nodes (subtrees of <= 3 triangles become leaf
+//      children), octant slot assignment, 8-bit outward quantisation -> 80-B nodes + 48-B triangles,
+//      every subtree's triangles contiguous.
 #pragma once
 #include "ohb_traverse.h"
 
@@ -33,15 +34,12 @@ struct BuildArrays {
     // hierarchy over n-1 internal nodes
     int32_t* left; int32_t* right;           // child: >=0 internal, <0 => ~leafIndex (sorted position)
     int32_t* parentInner; int32_t* parentLeaf;
-    uint32_t* nodeFirst;                     // n-1 : depth-first position of the node's first triangle
-    uint32_t* leafPos;                       // n   : depth-first position of each sorted leaf
     f4* nodeLo; f4* nodeHi;                  // internal nodes: (lo, triangle count bits) (hi, SAH cost of the subtree)
     uint32_t* visit;                         // n-1 atomic flags
-    int32_t* newIndex;                       // n-1 : index in the emitted array or -1
-    uint32_t* emitCounter;                   // 1
-    float* sah;                              // 2 : {inner area sum, leaf area*count sum}
+    uint32_t* wideCounters;                  // 4 : {wide nodes allocated, items of level A, items of level B, -}
+    float* sah;                              // 2 : {wide-node area sum, leaf area*count sum}
     // outputs
-    f4* nodes; f4* tris;
+    u4* wnodes; f4* tris;                    // 5 x u4 per wide node (ohb_traverse.h), 3 x f4 per triangle
 };
 
 OHB_HD uint32_t floatOrdered(float f) { uint32_t u = f2u(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
@@ -66,6 +64,13 @@ OHB_HD uint32_t atomicIncU32(uint32_t* p) {
     return atomicAdd(p, 1u);
 #else
     return (*p)++;
+#endif
+}
+OHB_HD uint32_t atomicIncU32N(uint32_t* p, uint32_t n) {
+#if OHB_DEVICE_CODE
+    return atomicAdd(p, n);
+#else
+    uint32_t r = *p; *p += n; return r;
 #endif
 }
 OHB_HD void atomicAddF32(float* p, float v) {
@@ -195,7 +200,7 @@ OHB_HD NodeInfo nodeInfo(const BuildArrays& b, int c) {
 }
 OHB_HD void writeNode(const BuildArrays& b, int n, f3 lo, f3 hi, uint32_t cnt, float childCost) {
     float A = boxArea(lo, hi);
-    float cost = (cnt <= OHB_MAX_LEAF) ? OHB_SAH_CT * A * float(cnt) : OHB_SAH_CI * A + childCost;   // <= 4 triangles collapse to one leaf
+    float cost = (cnt <= OHB_MAX_LEAF) ? OHB_SAH_CT * A * float(cnt) : OHB_SAH_CI * A + childCost;   // <= OHB_MAX_LEAF triangles collapse to one leaf
     b.nodeLo[n] = mk4(lo, u2f(cnt)); b.nodeHi[n] = mk4(hi, cost);
 }
 
@@ -279,66 +284,145 @@ OHB_HD void sweepFromLeaf(const BuildArrays& b, uint32_t leaf, uint32_t gamma) {
 }
 
 OHB_HD uint32_t nodeCount(const BuildArrays& b, int i) { return f2u(b.nodeLo[i].w); }
-// Stage 6a: position of a subtree's first triangle in depth-first order = sum, over the ancestors where the path
-// turns right, of the left sibling's triangle count.  (After restructuring, subtrees are no longer contiguous
-// ranges of the Morton order, so triangles are re-emitted in DFS order.)
-OHB_HD uint32_t dfsOffset(const BuildArrays& b, int child, int parent) {
-    uint32_t off = 0u;
-    while (parent >= 0) {
-        int lc = b.left[parent];
-        if (lc != child) off += (lc < 0) ? 1u : nodeCount(b, lc);
-        child = parent; parent = b.parentInner[parent];
-    }
-    return off;
-}
-OHB_HD void computeNodeFirst(const BuildArrays& b, int i) { b.nodeFirst[i] = dfsOffset(b, i, b.parentInner[i]); }
-OHB_HD void computeLeafPos(const BuildArrays& b, uint32_t leaf) { b.leafPos[leaf] = dfsOffset(b, ~int(leaf), b.parentLeaf[leaf]); }
-
-// Stage 6b: which internal nodes survive the collapse (more than OHB_MAX_LEAF triangles below).
-OHB_HD void assignNodeIndex(const BuildArrays& b, int i) {
-    if (nodeCount(b, i) <= OHB_MAX_LEAF) { b.newIndex[i] = -1; return; }
-    b.newIndex[i] = (i == 0) ? 0 : int32_t(atomicIncU32(b.emitCounter));   // counter starts at 1
-}
 // Conservative outward padding of stored boxes (DESIGN.md "Robustness").
 OHB_HD void padBox(f3& lo, f3& hi) {
     const float k = 9.5367431640625e-7f;   // 2^-20
     lo = mk3(lo.x - fabsf(lo.x) * k - 1e-30f, lo.y - fabsf(lo.y) * k - 1e-30f, lo.z - fabsf(lo.z) * k - 1e-30f);
     hi = mk3(hi.x + fabsf(hi.x) * k + 1e-30f, hi.y + fabsf(hi.y) * k + 1e-30f, hi.z + fabsf(hi.z) * k + 1e-30f);
 }
-OHB_HD void childRefAndBox(const BuildArrays& b, int c, int32_t& ref, f3& lo, f3& hi) {
-    if (c < 0) {
-        uint32_t pos = uint32_t(~c); uint32_t a = b.vals[pos];
-        ref = makeLeafRef(b.leafPos[pos], 1u); lo = xyz(b.primLo[a]); hi = xyz(b.primHi[a]);
-    } else {
-        lo = xyz(b.nodeLo[c]); hi = xyz(b.nodeHi[c]);
-        uint32_t cnt = nodeCount(b, c);
-        ref = (cnt <= OHB_MAX_LEAF) ? makeLeafRef(b.nodeFirst[c], cnt) : b.newIndex[c];
+
+// ---------------------------------------------------------------------------------------------
+// Stage 6: collapse the optimised binary tree into the compressed 8-wide BVH (node format: ohb_traverse.h).
+// Top-down, one level per launch, one thread per wide node (WideItem).  A wide node is grown greedily from
+// a binary node: the child with the largest surface area that still holds more than OHB_MAX_LEAF triangles
+// is replaced by its two children until 8 children exist or only leaf-sized subtrees remain.  Children are
+// placed in the 8 slots so that (slot ^ ray octant) approximates a front-to-back order (greedy assignment on
+// dot(child centre - node centre, octant sign), Ylitie et al. 2017 §3.2).  Child boxes are quantised outward
+// to 8 bits on the node's own power-of-two grid; the rounding is verified in fp64.
+// Triangle layout: a node's leaf triangles first (<= 24, slot order), then the block of each inner child in
+// slot order — every subtree is one contiguous range, computed top-down from the subtree triangle counts.
+// ---------------------------------------------------------------------------------------------
+struct WideItem { int32_t bvh2; uint32_t wide, triStart, pad; };
+
+OHB_HD float exp2i(int e) { return u2f(uint32_t(e + 127) << 23); }     // -126 <= e <= 127
+// smallest-ish e with 255 * 2^e >= ext (any e that satisfies the fp64 check of the caller is valid)
+OHB_HD int gridExponent(float ext) {
+    float v = ext / 255.0f;
+    int e = int((f2u(v) >> 23) & 0xFFu) - 127 + 1;
+    if (!(v > 0.0f) || e < -100) e = -100;
+    if (e > 126) e = 126;
+    return e;
+}
+// append the triangles of the leaf-sized binary subtree `c` to the triangle array, returns how many
+OHB_HD uint32_t emitLeafTris(const BuildArrays& b, int c, uint32_t dst) {
+    int st[4]; int sp = 0; st[sp++] = c; uint32_t k = 0;
+    while (sp) {
+        int x = st[--sp];
+        if (x < 0) {
+            uint32_t a = b.vals[~x];
+            b.tris[size_t(dst + k) * 3 + 0] = b.wtri[size_t(a) * 3 + 0];
+            b.tris[size_t(dst + k) * 3 + 1] = b.wtri[size_t(a) * 3 + 1];
+            b.tris[size_t(dst + k) * 3 + 2] = b.wtri[size_t(a) * 3 + 2];
+            k++;
+        } else { st[sp++] = b.right[x]; st[sp++] = b.left[x]; }
     }
+    return k;
 }
-// Stage 6c: emit the 64-B node of a surviving internal node + SAH bookkeeping (Ci = Ct = 1 for the reported cost).
-OHB_HD void emitNode(const BuildArrays& b, int i) {
-    int32_t ni = b.newIndex[i];
-    if (ni < 0) return;
-    int32_t r0, r1; f3 lo0, hi0, lo1, hi1;
-    childRefAndBox(b, b.left[i], r0, lo0, hi0);
-    childRefAndBox(b, b.right[i], r1, lo1, hi1);
-    float a0 = boxArea(lo0, hi0), a1 = boxArea(lo1, hi1);
-    float inner = (i == 0 ? boxArea(xyz(b.nodeLo[0]), xyz(b.nodeHi[0])) : 0.0f) + (r0 >= 0 ? a0 : 0.0f) + (r1 >= 0 ? a1 : 0.0f);
-    float leaf = (r0 < 0 ? a0 * float(leafCount(r0)) : 0.0f) + (r1 < 0 ? a1 * float(leafCount(r1)) : 0.0f);
-    atomicAddF32(b.sah + 0, inner); atomicAddF32(b.sah + 1, leaf);
-    padBox(lo0, hi0); padBox(lo1, hi1);
-    f4* np = b.nodes + size_t(ni) * 4u;
-    np[0] = mk4(lo0.x, hi0.x, lo0.y, hi0.y);
-    np[1] = mk4(lo1.x, hi1.x, lo1.y, hi1.y);
-    np[2] = mk4(lo0.z, hi0.z, lo1.z, hi1.z);
-    np[3] = mk4(u2f(uint32_t(r0)), u2f(uint32_t(r1)), 0.0f, 0.0f);
-}
-// Stage 7: triangles into depth-first leaf order.
-OHB_HD void emitTri(const BuildArrays& b, uint32_t pos) {
-    uint32_t a = b.vals[pos]; uint32_t dst = b.n >= 2u ? b.leafPos[pos] : pos;
-    b.tris[size_t(dst) * 3 + 0] = b.wtri[size_t(a) * 3 + 0];
-    b.tris[size_t(dst) * 3 + 1] = b.wtri[size_t(a) * 3 + 1];
-    b.tris[size_t(dst) * 3 + 2] = b.wtri[size_t(a) * 3 + 2];
+OHB_HD void emitWideNode(const BuildArrays& b, const WideItem& it, WideItem* outItems, uint32_t* outCount) {
+    int child[8]; f3 lo[8], hi[8]; uint32_t cnt[8]; int nc;
+    auto fetch = [&](int k, int c) { NodeInfo r = nodeInfo(b, c); child[k] = c; lo[k] = r.lo; hi[k] = r.hi; cnt[k] = r.cnt; };
+    if (b.n == 1u) { fetch(0, ~0); nc = 1; }
+    else { fetch(0, b.left[it.bvh2]); fetch(1, b.right[it.bvh2]); nc = 2; }
+    while (nc < 8) {
+        int best = -1; float bestA = -1.0f;
+        for (int k = 0; k < nc; k++) if (cnt[k] > OHB_MAX_LEAF) { float a = boxArea(lo[k], hi[k]); if (a > bestA) { bestA = a; best = k; } }
+        if (best < 0) break;
+        int c = child[best];
+        fetch(best, b.left[c]); fetch(nc, b.right[c]); nc++;
+    }
+    // node box = union of the padded child boxes
+    f3 nlo = mk3(3.0e38f), nhi = mk3(-3.0e38f);
+    float leafArea = 0.0f;
+    for (int k = 0; k < nc; k++) {
+        if (cnt[k] <= OHB_MAX_LEAF) leafArea += boxArea(lo[k], hi[k]) * float(cnt[k]);
+        padBox(lo[k], hi[k]); nlo = vmin(nlo, lo[k]); nhi = vmax(nhi, hi[k]);
+    }
+    atomicAddF32(b.sah + 0, boxArea(nlo, nhi)); atomicAddF32(b.sah + 1, leafArea);
+    // slot assignment
+    int slotOf[8], childAt[8];
+    for (int k = 0; k < 8; k++) { slotOf[k] = -1; childAt[k] = -1; }
+    f3 nc2 = nlo + nhi;                                    // 2 x node centre
+    for (int round = 0; round < nc; round++) {
+        float bestC = 3.0e38f; int bk = -1, bs = -1;
+        for (int k = 0; k < nc; k++) {
+            if (slotOf[k] >= 0) continue;
+            f3 dc = (lo[k] + hi[k]) - nc2;
+            for (int s = 0; s < 8; s++) {
+                if (childAt[s] >= 0) continue;
+                float c = ((s & 4) ? -dc.x : dc.x) + ((s & 2) ? -dc.y : dc.y) + ((s & 1) ? -dc.z : dc.z);
+                if (c < bestC) { bestC = c; bk = k; bs = s; }
+            }
+        }
+        slotOf[bk] = bs; childAt[bs] = bk;
+    }
+    // quantisation grid
+    int e[3] = {gridExponent(nhi.x - nlo.x), gridExponent(nhi.y - nlo.y), gridExponent(nhi.z - nlo.z)};
+    uint32_t qlo[3][8], qhi[3][8];
+    for (int ax = 0; ax < 3; ax++) {
+        const double p = double(comp(nlo, ax));
+        for (;;) {
+            bool ok = true; const double step = double(exp2i(e[ax]));
+            for (int s = 0; s < 8; s++) {
+                int k = childAt[s];
+                if (k < 0) { qlo[ax][s] = 255u; qhi[ax][s] = 0u; continue; }
+                const double l = double(comp(lo[k], ax)), h = double(comp(hi[k], ax));
+                double ql = floor((l - p) / step), qh = ceil((h - p) / step);
+                while (ql > 0.0 && p + ql * step > l) ql -= 1.0;
+                while (p + qh * step < h) qh += 1.0;
+                if (ql < 0.0) ql = 0.0;
+                if (qh > 255.0) { ok = false; break; }
+                qlo[ax][s] = uint32_t(ql); qhi[ax][s] = uint32_t(qh);
+            }
+            if (ok) break;
+            e[ax]++;
+        }
+    }
+    // children: inner ones get consecutive wide-node indices in slot order, leaves their triangle offsets
+    uint32_t imask = 0u, numInner = 0u;
+    for (int s = 0; s < 8; s++) { int k = childAt[s]; if (k >= 0 && cnt[k] > OHB_MAX_LEAF) { imask |= 1u << s; numInner++; } }
+    uint32_t childBase = 0u, itemBase = 0u;
+    if (numInner) {
+        childBase = atomicIncU32N(b.wideCounters + 0, numInner);
+        itemBase = atomicIncU32N(outCount, numInner);
+    }
+    uint32_t meta[8]; uint32_t triOff = 0u, rank = 0u;
+    for (int s = 0; s < 8; s++) {
+        int k = childAt[s];
+        if (k < 0) { meta[s] = 0u; continue; }
+        if (cnt[k] > OHB_MAX_LEAF) continue;
+        uint32_t m = emitLeafTris(b, child[k], it.triStart + triOff);
+        meta[s] = (((1u << m) - 1u) << 5) | triOff;
+        triOff += m;
+    }
+    uint32_t sub = it.triStart + triOff;
+    for (int s = 0; s < 8; s++) {
+        int k = childAt[s];
+        if (k < 0 || cnt[k] <= OHB_MAX_LEAF) continue;
+        meta[s] = (1u << 5) | (24u + uint32_t(s));
+        WideItem w; w.bvh2 = child[k]; w.wide = childBase + rank; w.triStart = sub; w.pad = 0u;
+        outItems[itemBase + rank] = w;
+        rank++; sub += cnt[k];
+    }
+    auto pack4 = [](const uint32_t* v) { return v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24); };
+    u4 w0, w1, w2, w3, w4;
+    w0.x = f2u(nlo.x); w0.y = f2u(nlo.y); w0.z = f2u(nlo.z);
+    w0.w = uint32_t(e[0] + 127) | (uint32_t(e[1] + 127) << 8) | (uint32_t(e[2] + 127) << 16) | (imask << 24);
+    w1.x = childBase; w1.y = it.triStart; w1.z = pack4(meta); w1.w = pack4(meta + 4);
+    w2.x = pack4(qlo[0]); w2.y = pack4(qlo[0] + 4); w2.z = pack4(qlo[1]); w2.w = pack4(qlo[1] + 4);
+    w3.x = pack4(qlo[2]); w3.y = pack4(qlo[2] + 4); w3.z = pack4(qhi[0]); w3.w = pack4(qhi[0] + 4);
+    w4.x = pack4(qhi[1]); w4.y = pack4(qhi[1] + 4); w4.z = pack4(qhi[2]); w4.w = pack4(qhi[2] + 4);
+    u4* np = b.wnodes + size_t(it.wide) * OHB_WNODE_VECS;
+    np[0] = w0; np[1] = w1; np[2] = w2; np[3] = w3; np[4] = w4;
 }
 
 }  // namespace ohb

@@ -29,7 +29,8 @@ struct TimingHooks {
 
 cudaError_t uploadConstants();
 uint32_t radixSortTempWords(uint32_t n);
-void launchBuild(const BuildArrays& b, uint64_t* keysTmp, uint32_t* valsTmp, uint32_t* sortTemp, uint32_t treeletPasses, cudaStream_t st, uint64_t* launches);
+void launchBuild(const BuildArrays& b, uint64_t* keysTmp, uint32_t* valsTmp, uint32_t* sortTemp, WideItem* itemsA, WideItem* itemsB,
+                 uint32_t treeletPasses, cudaStream_t st, uint64_t* launches);
 void launchEnvCdf(const f4* env, uint32_t W, uint32_t H, float* cond, float* marg, float* rowTotal, float* integral, cudaStream_t st, uint64_t* launches);
 void launchEnvSample(const SceneDev& sc, const float* u12, uint32_t n, f4* dirPdf, float* pdfOfDir, cudaStream_t st, uint64_t* launches);
 void launchEnvPdf(const SceneDev& sc, const float* dirs3, uint32_t n, float* pdf, cudaStream_t st, uint64_t* launches);

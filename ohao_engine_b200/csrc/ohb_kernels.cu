@@ -26,18 +26,28 @@ __global__ void k_morton(BuildArrays b) { uint32_t i = blockIdx.x * blockDim.x +
 __global__ void k_hierarchy(BuildArrays b) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i + 1 < b.n) buildHierarchyNode(b, int(i)); }
 __global__ void k_sweep(BuildArrays b, uint32_t gamma) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < b.n) sweepFromLeaf(b, i, gamma); }
 __global__ void k_clear_visit(BuildArrays b) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i + 1 < b.n) b.visit[i] = 0u; }
-__global__ void k_node_first(BuildArrays b) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i + 1 < b.n) computeNodeFirst(b, int(i)); }
-__global__ void k_leaf_pos(BuildArrays b) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < b.n) computeLeafPos(b, i); }
-__global__ void k_assign_index(BuildArrays b) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i + 1 < b.n) assignNodeIndex(b, int(i)); }
-__global__ void k_emit_nodes(BuildArrays b) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i + 1 < b.n) emitNode(b, int(i)); }
-__global__ void k_emit_tris(BuildArrays b) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < b.n) emitTri(b, i); }
+// One level of the 8-wide collapse: thread i expands item i of `in` (count read from the device) and appends the
+// items of its inner children to `out`.  The grid is sized for the worst case of the level; surplus threads exit.
+__global__ void __launch_bounds__(64) k_wide_level(BuildArrays b, const WideItem* in, const uint32_t* inCount, WideItem* out, uint32_t* outCount) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < *inCount) emitWideNode(b, in[i], out, outCount);
+}
+__global__ void k_wide_begin(BuildArrays b, WideItem* items) {
+    if (blockIdx.x || threadIdx.x) return;
+    WideItem r; r.bvh2 = 0; r.wide = 0u; r.triStart = 0u; r.pad = 0u; items[0] = r;
+    b.wideCounters[0] = 1u; b.wideCounters[1] = 1u; b.wideCounters[2] = 0u; b.wideCounters[3] = 0u;
+}
+__global__ void k_wide_next(uint32_t* consumed, uint32_t* levels, const uint32_t* produced) {
+    if (blockIdx.x || threadIdx.x) return;
+    *consumed = 0u; if (*produced) (*levels)++;
+}
 __global__ void k_init_build(BuildArrays b) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i + 1 < b.n) b.visit[i] = 0u;
     if (i == 0) {
         b.boundsBits[0] = b.boundsBits[1] = b.boundsBits[2] = 0xFFFFFFFFu;
         b.boundsBits[3] = b.boundsBits[4] = b.boundsBits[5] = 0u;
-        *b.emitCounter = 1u; b.sah[0] = 0.0f; b.sah[1] = 0.0f;
+        b.sah[0] = 0.0f; b.sah[1] = 0.0f;
     }
 }
 
@@ -155,7 +165,8 @@ void radixSort64(uint64_t* keys, uint32_t* vals, uint64_t* keysTmp, uint32_t* va
     }
 }
 
-void launchBuild(const BuildArrays& b, uint64_t* keysTmp, uint32_t* valsTmp, uint32_t* sortTemp, uint32_t treeletPasses, cudaStream_t st, uint64_t* launches) {
+void launchBuild(const BuildArrays& b, uint64_t* keysTmp, uint32_t* valsTmp, uint32_t* sortTemp, WideItem* itemsA, WideItem* itemsB,
+                 uint32_t treeletPasses, cudaStream_t st, uint64_t* launches) {
     const unsigned T = 256; unsigned g = gridFor(b.n, T);
     k_init_build<<<g, T, 0, st>>>(b);
     k_world_tris<<<g, T, 0, st>>>(b);
@@ -171,13 +182,21 @@ void launchBuild(const BuildArrays& b, uint64_t* keysTmp, uint32_t* valsTmp, uin
             k_sweep<<<gridFor(b.n, 64), 64, 0, st>>>(b, gamma);  // treelet restructuring (1.2 KB of DP tables per thread)
             *launches += 2;
         }
-        k_node_first<<<g, T, 0, st>>>(b);
-        k_leaf_pos<<<g, T, 0, st>>>(b);
-        k_assign_index<<<g, T, 0, st>>>(b);
-        k_emit_nodes<<<g, T, 0, st>>>(b);
-        *launches += 4;
     }
-    k_emit_tris<<<g, T, 0, st>>>(b); (*launches)++;
+    // 8-wide collapse, level by level.  Level l holds at most min(8^l, n / 4) nodes (every inner child owns > 3
+    // triangles); the loop runs OHB_MAX_LEVELS + 1 times so that wideCounters[3] (levels that produced
+    // children) exceeds OHB_MAX_LEVELS exactly when the tree is too deep for the traversal stack.
+    k_wide_begin<<<1, 32, 0, st>>>(b, itemsA); (*launches)++;
+    WideItem* in = itemsA; WideItem* out = itemsB; uint32_t* cin = b.wideCounters + 1; uint32_t* cout = b.wideCounters + 2;
+    uint64_t cap = 1;
+    for (int level = 0; level <= OHB_MAX_LEVELS; level++) {
+        uint64_t bound = cap < uint64_t(b.n / 4u + 1u) ? cap : uint64_t(b.n / 4u + 1u);
+        k_wide_level<<<gridFor(bound, 64), 64, 0, st>>>(b, in, cin, out, cout);
+        k_wide_next<<<1, 32, 0, st>>>(cin, b.wideCounters + 3, cout);
+        *launches += 2;
+        WideItem* ti = in; in = out; out = ti; uint32_t* tc = cin; cin = cout; cout = tc;
+        if (cap < (uint64_t(1) << 40)) cap *= 8;
+    }
 }
 
 // =============================================================================================
@@ -247,7 +266,7 @@ void launchEnvPdf(const SceneDev& sc, const float* dirs3, uint32_t n, float* pdf
 template <bool ANY, class IO>
 __device__ __forceinline__ void persistentTrace(const SceneDev& sc, uint32_t n, uint32_t* work, IO& io) {
     const uint32_t lane = threadIdx.x & 31u;
-    Trav t; int32_t stack[OHB_STACK_SIZE]; uint32_t idx = 0; bool have = false, exhausted = false;
+    Trav t; TravStackEntry stack[OHB_STACK_SIZE]; uint32_t idx = 0; bool have = false, exhausted = false;
     for (;;) {
         unsigned need = __ballot_sync(0xffffffffu, !have && !exhausted);
         if (need) {

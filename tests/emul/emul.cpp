@@ -7,6 +7,19 @@
 // traversal and the wavefront state machine against the oracle before any GPU minute is spent.
 // It is NOT a fallback: nothing in ohao_engine_b200/ links or loads this file, it is slow, and the
 // radix sort / scan / queue kernels (device-only code) are replaced by std::stable_sort here.
+// Host stand-in for the warp's active-lane count: with EMUL_WARP_NOISE set the traversal sees a pseudo-random
+// number of active lanes, which drives the triangle-postponing and pause/resume paths that a single host
+// thread would otherwise never take.
+static unsigned g_emulWarpNoise = 0, g_emulWarpState = 12345u;
+static inline int emulWarpActive() {
+    if (!g_emulWarpNoise) return 32;
+    g_emulWarpState = g_emulWarpState * 1664525u + 1013904223u;
+    return int(g_emulWarpState >> 27) + 1;
+}
+#define OHB_WARP_ACTIVE() emulWarpActive()
+static unsigned long long g_statNodes = 0, g_statTris = 0;
+#define OHB_STAT_NODE() (g_statNodes++)
+#define OHB_STAT_TRI() (g_statTris++)
 #include "../../ohao_engine_b200/csrc/ohb_bvh.h"
 #include "../../ohao_engine_b200/csrc/ohb_integrator.h"
 #include "../../ohao_engine_b200/csrc/ohb_realtime.h"
@@ -27,10 +40,10 @@ struct EmulScene {
     std::vector<uint8_t> tex; uint32_t texW = 0, texH = 0, texLayers = 0;
     std::vector<GPULight> lights; uint32_t lightCount = 0, envMapTexIdx = 0xFFFFFFFFu; float envIntensity = 1.0f;
     uint32_t envW = 0, envH = 0; std::vector<float> marg, cond; float envIntegral = 0;
-    std::vector<f4> nodes, tris; int32_t rootRef = 0; uint32_t numActive = 0, numNodes = 0; float sah = 0;
+    std::vector<u4> wnodes; std::vector<f4> tris; uint32_t numActive = 0, numNodes = 0, levels = 0; float sah = 0;
     SceneDev dev() const {
         SceneDev s; memset(&s, 0, sizeof(s));
-        s.nodes = nodes.data(); s.tris = tris.data(); s.rootRef = rootRef; s.numTris = numActive;
+        s.wnodes = wnodes.data(); s.tris = tris.data(); s.numTris = numActive;
         s.indices = indices.data(); s.normals = normals.data(); s.uvs = uvs.data(); s.matIds = matIds.data(); s.triInst = triInst.data();
         s.instNormalMat = instNormalMat.data(); s.instInv = instInv.data(); s.matColors = matColors.data();
         s.tex = tex.data(); s.texW = texW; s.texH = texH; s.texLayers = texLayers;
@@ -97,17 +110,17 @@ void* emul_scene_create(const emul_scene_desc* d) {
     uint32_t n = uint32_t(s->active.size()); s->numActive = n;
     if (n == 0) return s;
     std::vector<f4> wtri(size_t(n) * 3), primLo(n), primHi(n), nodeLo(n), nodeHi(n);
-    std::vector<uint32_t> bounds(6), vals(n), rf(n), rl(n), visit(n, 0), emitCounter(1, 1);
+    std::vector<uint32_t> bounds(6), vals(n), visit(n, 0), wideCounters(4, 0);
     std::vector<uint64_t> keys(n);
-    std::vector<int32_t> left(n), right(n), pin(n, -1), pleaf(n, -1), newIndex(n, -1);
+    std::vector<int32_t> left(n), right(n), pin(n, -1), pleaf(n, -1);
     std::vector<float> sah(2, 0.0f);
-    s->nodes.assign(size_t(n) * 4, f4{0, 0, 0, 0}); s->tris.resize(size_t(n) * 3);
+    s->wnodes.assign(size_t(n) * OHB_WNODE_VECS, u4{0, 0, 0, 0}); s->tris.resize(size_t(n) * 3);
     BuildArrays b{};
     b.positions = s->positions.data(); b.posStride = s->stride; b.indices = s->indices.data(); b.triInst = s->triInst.data(); b.instXform = s->instXform.data();
     b.activeTris = s->active.data(); b.n = n; b.wtri = wtri.data(); b.primLo = primLo.data(); b.primHi = primHi.data(); b.boundsBits = bounds.data();
     b.keys = keys.data(); b.vals = vals.data(); b.left = left.data(); b.right = right.data(); b.parentInner = pin.data(); b.parentLeaf = pleaf.data();
-    b.nodeFirst = rf.data(); b.leafPos = rl.data(); b.nodeLo = nodeLo.data(); b.nodeHi = nodeHi.data(); b.visit = visit.data(); b.newIndex = newIndex.data();
-    b.emitCounter = emitCounter.data(); b.sah = sah.data(); b.nodes = s->nodes.data(); b.tris = s->tris.data();
+    b.nodeLo = nodeLo.data(); b.nodeHi = nodeHi.data(); b.visit = visit.data();
+    b.wideCounters = wideCounters.data(); b.sah = sah.data(); b.wnodes = s->wnodes.data(); b.tris = s->tris.data();
     bounds[0] = bounds[1] = bounds[2] = 0xFFFFFFFFu; bounds[3] = bounds[4] = bounds[5] = 0u;
     for (uint32_t i = 0; i < n; i++) buildWorldTri(b, i);
     for (uint32_t i = 0; i < n; i++) buildMorton(b, i);
@@ -126,20 +139,27 @@ void* emul_scene_create(const emul_scene_desc* d) {
             std::fill(visit.begin(), visit.end(), 0u);
             for (uint32_t i = 0; i < n; i++) sweepFromLeaf(b, i, gamma);
         }
-        for (uint32_t i = 0; i + 1 < n; i++) computeNodeFirst(b, int(i));
-        for (uint32_t i = 0; i < n; i++) computeLeafPos(b, i);
-        for (uint32_t i = 0; i + 1 < n; i++) assignNodeIndex(b, int(i));
-        for (uint32_t i = 0; i + 1 < n; i++) emitNode(b, int(i));
     }
-    for (uint32_t i = 0; i < n; i++) emitTri(b, i);
-    s->rootRef = (n <= OHB_MAX_LEAF) ? makeLeafRef(0u, n) : 0;
-    s->numNodes = (n <= OHB_MAX_LEAF) ? 0u : emitCounter[0];
+    {   // emulate the level loop of launchBuild
+        std::vector<WideItem> qa(n / 4 + 2), qb(n / 4 + 2);
+        qa[0] = WideItem{0, 0u, 0u, 0u}; wideCounters[0] = 1; wideCounters[1] = 1; wideCounters[2] = 0; wideCounters[3] = 0;
+        WideItem* in = qa.data(); WideItem* out = qb.data(); uint32_t* cin = &wideCounters[1]; uint32_t* cout = &wideCounters[2];
+        for (int level = 0; level <= OHB_MAX_LEVELS; level++) {
+            for (uint32_t i = 0; i < *cin; i++) emitWideNode(b, in[i], out, cout);
+            *cin = 0; if (*cout) wideCounters[3]++;
+            std::swap(in, out); std::swap(cin, cout);
+        }
+    }
+    s->numNodes = wideCounters[0]; s->levels = wideCounters[3] + 1;
     float ra = n >= 2 ? boxArea(xyz(nodeLo[0]), xyz(nodeHi[0])) : 0.0f;
     s->sah = ra > 0 ? (sah[0] + sah[1]) / ra : float(n);
     return s;
 }
 void emul_scene_destroy(void* h) { delete (EmulScene*)h; }
 void emul_accel_stats(void* h, uint32_t* numNodes, float* sah) { EmulScene* s = (EmulScene*)h; *numNodes = s->numNodes; *sah = s->sah; }
+uint32_t emul_accel_levels(void* h) { return ((EmulScene*)h)->levels; }
+void emul_trav_stats(unsigned long long* nodes, unsigned long long* tris, int reset) { *nodes = g_statNodes; *tris = g_statTris; if (reset) { g_statNodes = 0; g_statTris = 0; } }
+void emul_set_warp_noise(unsigned on) { g_emulWarpNoise = on; g_emulWarpState = 12345u; }
 
 void emul_trace_batch(void* h, const ohb_ray* rays, uint32_t n, ohb_hit* hits) {
     SceneDev sc = ((EmulScene*)h)->dev();

@@ -41,6 +41,9 @@ def lib():
         _LIB.emul_render_offline.argtypes = [C.c_void_p, C.POINTER(RenderArgs)]
         _LIB.emul_render_realtime.argtypes = [C.c_void_p, C.POINTER(RTArgs)]
         _LIB.emul_accel_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
+        _LIB.emul_accel_levels.argtypes = [C.c_void_p]; _LIB.emul_accel_levels.restype = C.c_uint32
+        _LIB.emul_set_warp_noise.argtypes = [C.c_uint]
+        _LIB.emul_trav_stats.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.c_int]
     return _LIB
 
 
@@ -71,6 +74,9 @@ class EmulScene:
 
     def stats(self):
         n = C.c_uint32(); s = C.c_float(); lib().emul_accel_stats(self.h, C.byref(n), C.byref(s)); return n.value, s.value
+
+    def levels(self):
+        return lib().emul_accel_levels(self.h)
 
     def trace(self, rays):
         rays = np.ascontiguousarray(rays, O.RAY_DTYPE); hits = np.zeros(len(rays), O.HIT_DTYPE)
@@ -121,3 +127,13 @@ class EmulScene:
         c = a.counters
         return dict(accum=accum, ldr=ldr, albedo=alb, normal=nrm, samples=sd,
                     counters=dict(samples=c[0], closest_rays=c[1], shadow_rays=c[2], closest_hits=c[3]))
+
+
+def set_warp_noise(on: bool):
+    """Pseudo-random active-lane counts: drives triangle postponing and pause/resume in the host emulator."""
+    lib().emul_set_warp_noise(1 if on else 0)
+
+
+def trav_stats(reset=True):
+    """(node visits, triangle tests) since the last reset."""
+    a = C.c_ulonglong(); b = C.c_ulonglong(); lib().emul_trav_stats(C.byref(a), C.byref(b), 1 if reset else 0); return a.value, b.value
