@@ -26,6 +26,16 @@ enum { ST_PRIMARY = 0u, ST_CHAIN_B = 1u, ST_CHAIN_C = 2u, ST_DONE = 3u };
 #define OHB_ST_PEND_B     (1u << 8)
 #define OHB_ST_MAKE(stage, bounce) ((stage) | ((bounce) << 2))
 
+// Queue entries carry the path index (OHB_MAX_PATHS <= 2^24) plus what the NEXT shading kernel needs to know to
+// issue all of its path-state loads at once instead of chasing meta -> pend -> payload (k_bounce was stalled on
+// that dependent chain: 60 % of its samples on the first uses of meta / pendA / pay0, profile r1d).
+#define OHB_Q_PATH(e)   ((e) & 0x00FFFFFFu)
+#define OHB_Q_MISS      0x80000000u      // set by k_surface: the last closest-hit query missed
+#define OHB_Q_PEND_A    0x40000000u      // set by k_bounce: a light-NEE contribution is parked in pendA
+#define OHB_Q_PEND_B    0x20000000u      //                  an env-NEE contribution is parked in pendB
+#define OHB_Q_PRIMARY   0x10000000u      // set by k_raygen: the path is at its camera ray
+#define OHB_Q_NONE      0xFFFFFFFFu      // bouncePath: the path traces no further closest-hit ray
+
 struct PathArrays {
     f4* rayO; f4* rayD;            // next closest-hit ray (origin.xyz | dir.xyz)
     ohb_hit* hit;                  // answer of k_trace_closest
@@ -404,26 +414,32 @@ OHB_HD f3 sampleSpecDir(ShadeCtx& cx, f3 d, f3 N, float rough) {
     return refl;
 }
 
-// k_bounce: the raygen's per-bounce body for path p, after k_surface.  Returns true if the path traces again.
-OHB_HD bool bouncePath(const SceneDev& sc, const FrameParams& fr, const PathArrays& P, uint32_t p) {
+// k_bounce: the raygen's per-bounce body for the path of queue entry e, after k_surface.
+// Returns the path's next queue entry, or OHB_Q_NONE if it traces no further closest-hit ray.
+OHB_HD uint32_t bouncePath(const SceneDev& sc, const FrameParams& fr, const PathArrays& P, uint32_t e) {
+    const uint32_t p = OHB_Q_PATH(e);
+    const bool isMiss = (e & OHB_Q_MISS) != 0u, primary = (e & OHB_Q_PRIMARY) != 0u;
+    // every load of the path record is issued here, before the first use
+    const u4 m = P.meta[p];
+    const f4 rad4 = P.rad[p], q0 = P.pay0[p], q1 = P.pay1[p], d4 = P.rayD[p];
+    const f4 zero4 = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+    const f4 pa4 = (e & OHB_Q_PEND_A) ? P.pendA[p] : zero4, pb4 = (e & OHB_Q_PEND_B) ? P.pendB[p] : zero4;
+    const f4 t4 = primary ? mk4(1.0f, 1.0f, 1.0f, 0.0f) : P.thr[p];
+    const f4 q2 = isMiss ? zero4 : P.pay2[p], q3 = isMiss ? zero4 : P.pay3[p];
     ShadeCtx cx(sc, fr, P);
-    u4 m = P.meta[p];
     cx.path = p; cx.state = m.w;
     uint32_t px = m.x & 0xFFFFu, py = m.x >> 16;
     cx.sm.init(fr.samplerType, px, py, m.y, ldu4(P.sobolTab + (m.y - P.firstSampleIndex)));
     if (fr.samplerType == OHB_SAMPLER_PCG) { cx.sm.pcg = m.z; cx.dimIdx = 0u; } else cx.dimIdx = m.z;
-    f3 rad = xyz(P.rad[p]);
-    if (cx.state & OHB_ST_PEND_A) rad += xyz(P.pendA[p]);
-    if (cx.state & OHB_ST_PEND_B) rad += xyz(P.pendB[p]);
+    f3 rad = xyz(rad4);
+    if (e & OHB_Q_PEND_A) rad += xyz(pa4);
+    if (e & OHB_Q_PEND_B) rad += xyz(pb4);
     cx.state &= ~(OHB_ST_PEND_A | OHB_ST_PEND_B);
     uint32_t stage = OHB_ST_STAGE(cx.state), bounce = OHB_ST_BOUNCE(cx.state);
-    const bool primary = (stage == ST_PRIMARY), specChain = (stage == ST_CHAIN_B);
-    f3 d = xyz(P.rayD[p]);
-    f4 q0 = P.pay0[p], q1 = P.pay1[p];
-    const bool isMiss = q0.w < 0.0f;
+    const bool specChain = (stage == ST_CHAIN_B);
+    f3 d = xyz(d4);
 
-    f3 nextO = mk3(0.0f), nextD = mk3(0.0f), thr = mk3(1.0f); float lastPdf = 0.0f; bool lastDelta = false;
-    if (!primary) { f4 t4 = P.thr[p]; thr = xyz(t4); lastPdf = t4.w; lastDelta = (cx.state & OHB_ST_DELTA) != 0u; }
+    f3 nextO = mk3(0.0f), nextD = mk3(0.0f), thr = xyz(t4); float lastPdf = t4.w; bool lastDelta = !primary && (cx.state & OHB_ST_DELTA) != 0u;
     bool startC = false, finished = false, chainEnds = false;
     f3 fhPos = mk3(0.0f), fhN = mk3(0.0f), fhAlbedo = mk3(0.0f);   // first-hit data for the Stage C set-up
 
@@ -446,7 +462,6 @@ OHB_HD bool bouncePath(const SceneDev& sc, const FrameParams& fr, const PathArra
             chainEnds = true;
         }
     } else {
-        f4 q2 = P.pay2[p], q3 = P.pay3[p];
         f3 hp = xyz(q0), N = xyz(q1), albedo = xyz(q2), em = xyz(q3);
         if (aov) { P.albedoAOV[pi] = mk4(albedo, 1.0f); P.normalAOV[pi] = mk4(N * 0.5f + mk3(0.5f), 1.0f); }
         float rough, metal; unpackHitPbr(mk3(q1.w, q2.w, q3.w), rough, metal);
@@ -523,18 +538,19 @@ OHB_HD bool bouncePath(const SceneDev& sc, const FrameParams& fr, const PathArra
     }
     P.rad[p] = mk4(rad, 0.0f);
     uint32_t keep = cx.state & (OHB_ST_PEND_A | OHB_ST_PEND_B);
-    m.z = (fr.samplerType == OHB_SAMPLER_PCG) ? cx.sm.pcg : cx.dimIdx;
-    if (finished) { m.w = ST_DONE | keep; P.meta[p] = m; return false; }
-    m.w = OHB_ST_MAKE(stage, bounce) | keep | (lastDelta ? OHB_ST_DELTA : 0u);
-    P.meta[p] = m;
+    u4 mo = m;
+    mo.z = (fr.samplerType == OHB_SAMPLER_PCG) ? cx.sm.pcg : cx.dimIdx;
+    if (finished) { mo.w = ST_DONE | keep; P.meta[p] = mo; return OHB_Q_NONE; }
+    mo.w = OHB_ST_MAKE(stage, bounce) | keep | (lastDelta ? OHB_ST_DELTA : 0u);
+    P.meta[p] = mo;
     P.thr[p] = mk4(thr, lastPdf);
     P.rayO[p] = mk4(nextO, 0.0f); P.rayD[p] = mk4(nextD, 0.0f);
-    return true;
+    return p | ((keep & OHB_ST_PEND_A) ? OHB_Q_PEND_A : 0u) | ((keep & OHB_ST_PEND_B) ? OHB_Q_PEND_B : 0u);
 }
 // Both shading stages back to back (host emulator / single-kernel fallback for tests).
-OHB_HD bool shadePath(const SceneDev& sc, const FrameParams& fr, const PathArrays& P, uint32_t p) {
-    surfacePath(sc, fr, P, p);
-    return bouncePath(sc, fr, P, p);
+OHB_HD uint32_t shadePath(const SceneDev& sc, const FrameParams& fr, const PathArrays& P, uint32_t e) {
+    const bool hit = surfacePath(sc, fr, P, OHB_Q_PATH(e));
+    return bouncePath(sc, fr, P, hit ? e : (e | OHB_Q_MISS));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -258,13 +258,25 @@ void launchEnvPdf(const SceneDev& sc, const float* dirs3, uint32_t n, float* pdf
 // Traversal kernels (persistent, warp-granular dynamic fetch)
 // =============================================================================================
 #define TRACE_THREADS 128
-#define TRACE_MIN_ACTIVE 20     // pause traversal and refill idle lanes when fewer lanes than this still traverse
+// Scheduling knobs of the traversal kernels (env overrides are for A/B measurements on the GPU box):
+//   minActive : pause traversal and refill idle lanes when fewer lanes than this still traverse   (OHB_TRACE_MIN_ACTIVE)
+//   mode      : 0 = travRun (triangles right after the node visit), 1 = travRunVote (warp-voted triangle steps) (OHB_TRAV_MODE)
+//   triNum    : mode 1 fires a triangle step when >= triNum/8 of the traversing lanes want one        (OHB_TRI_NUM)
+struct TraceKnobs { int minActive, mode, triNum; };
+static TraceKnobs traceKnobs() {
+    static const TraceKnobs k = []() {
+        auto geti = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
+        TraceKnobs r; r.minActive = geti("OHB_TRACE_MIN_ACTIVE", 20); r.mode = geti("OHB_TRAV_MODE", 1); r.triNum = geti("OHB_TRI_NUM", OHB_TRI_NUM_DEFAULT);
+        return r;
+    }();
+    return k;
+}
 // Persistent warp loop shared by every traversal kernel.  Lanes pull rays one by one from a global counter
 // (warp-aggregated atomic); a lane that finishes its ray waits at the reconvergence point of the `have`
 // block until the traversing lanes either finish or drop below TRACE_MIN_ACTIVE, then all idle lanes are
 // refilled together.  IO = { load(i, o, d, tmin, tmax), store(i, Trav&) }.
-template <bool ANY, class IO>
-__device__ __forceinline__ void persistentTrace(const SceneDev& sc, uint32_t n, uint32_t* work, IO& io) {
+template <bool ANY, int MODE, class IO>
+__device__ __forceinline__ void persistentTrace(const SceneDev& sc, uint32_t n, uint32_t* work, IO& io, int minActive, int triNum) {
     const uint32_t lane = threadIdx.x & 31u;
     Trav t; TravStackEntry stack[OHB_STACK_SIZE]; uint32_t idx = 0; bool have = false, exhausted = false;
     for (;;) {
@@ -281,7 +293,7 @@ __device__ __forceinline__ void persistentTrace(const SceneDev& sc, uint32_t n, 
         }
         if (!__any_sync(0xffffffffu, have)) break;
         bool done = false;
-        if (have) done = travRun<ANY>(t, stack, sc, TRACE_MIN_ACTIVE);
+        if (have) done = MODE ? travRunVote<ANY>(t, stack, sc, minActive, triNum) : travRun<ANY>(t, stack, sc, minActive);
         __syncwarp();
         if (done) { io.store(idx, t); have = false; }
     }
@@ -290,19 +302,19 @@ __device__ __forceinline__ void persistentTrace(const SceneDev& sc, uint32_t n, 
 struct PathClosestIO {
     PathArrays P; uint32_t hits;
     __device__ __forceinline__ void load(uint32_t i, f3& o, f3& d, float& tmin, float& tmax) {
-        uint32_t p = P.queueIn[i]; o = xyz(P.rayO[p]); d = xyz(P.rayD[p]); tmin = 0.001f; tmax = 10000.0f;
+        uint32_t p = OHB_Q_PATH(P.queueIn[i]); o = xyz(P.rayO[p]); d = xyz(P.rayD[p]); tmin = 0.001f; tmax = 10000.0f;
     }
     __device__ __forceinline__ void store(uint32_t i, Trav& t) {
-        uint32_t p = P.queueIn[i];
+        uint32_t p = OHB_Q_PATH(P.queueIn[i]);
         bool hit = t.best.prim != OHB_MISS;
         reinterpret_cast<float4*>(P.hit)[p] = make_float4(hit ? t.best.t : -1.0f, t.best.u, t.best.v, __uint_as_float(t.best.prim));
         hits += hit;
     }
 };
-template <int MINB>
-__global__ void __launch_bounds__(TRACE_THREADS, MINB) k_trace_closest(SceneDev sc, PathArrays P, uint32_t* work) {
+template <int MINB, int MODE>
+__global__ void __launch_bounds__(TRACE_THREADS, MINB) k_trace_closest(SceneDev sc, PathArrays P, uint32_t* work, int minActive, int triNum) {
     PathClosestIO io{P, 0u};
-    persistentTrace<false>(sc, *P.countIn, work, io);
+    persistentTrace<false, MODE>(sc, *P.countIn, work, io, minActive, triNum);
     uint32_t hits = __reduce_add_sync(0xffffffffu, io.hits);
     if ((threadIdx.x & 31u) == 0 && hits) atomicAdd(P.counters + 3, (unsigned long long)hits);
 }
@@ -318,46 +330,50 @@ struct PathShadowIO {
         pend[tag >> 1] = mk4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 };
-template <int MINB>
-__global__ void __launch_bounds__(TRACE_THREADS, MINB) k_trace_shadow(SceneDev sc, PathArrays P, uint32_t* work) {
+template <int MINB, int MODE>
+__global__ void __launch_bounds__(TRACE_THREADS, MINB) k_trace_shadow(SceneDev sc, PathArrays P, uint32_t* work, int minActive, int triNum) {
     PathShadowIO io{P};
-    persistentTrace<true>(sc, *P.shCount, work, io);
+    persistentTrace<true, MODE>(sc, *P.shCount, work, io, minActive, triNum);
 }
 static int traceOcc() { static const int v = []() { const char* e = getenv("OHB_TRACE_OCC"); return e ? atoi(e) : 12; }(); return v; }
 static void launchTraceClosest(unsigned smGrid8, const SceneDev& sc, const PathArrays& P, uint32_t* work, cudaStream_t st) {
     int o = traceOcc(); unsigned grid = smGrid8 / 8u * unsigned(o >= 16 ? 16 : (o >= 12 ? 12 : 9));
-    if (o >= 16)      k_trace_closest<16><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work);
-    else if (o >= 12) k_trace_closest<12><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work);
-    else              k_trace_closest<9><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work);
+    const TraceKnobs k = traceKnobs();
+#define OHB_LAUNCH_TC(OCC) do { if (k.mode) k_trace_closest<OCC, 1><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work, k.minActive, k.triNum); \
+                                else        k_trace_closest<OCC, 0><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work, k.minActive, k.triNum); } while (0)
+    if (o >= 16) OHB_LAUNCH_TC(16); else if (o >= 12) OHB_LAUNCH_TC(12); else OHB_LAUNCH_TC(9);
+#undef OHB_LAUNCH_TC
 }
 static void launchTraceShadow(unsigned smGrid8, const SceneDev& sc, const PathArrays& P, uint32_t* work, cudaStream_t st) {
     int o = traceOcc(); unsigned grid = smGrid8 / 8u * unsigned(o >= 16 ? 16 : (o >= 12 ? 12 : 9));
-    if (o >= 16)      k_trace_shadow<16><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work);
-    else if (o >= 12) k_trace_shadow<12><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work);
-    else              k_trace_shadow<9><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work);
+    const TraceKnobs k = traceKnobs();
+#define OHB_LAUNCH_TS(OCC) do { if (k.mode) k_trace_shadow<OCC, 1><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work, k.minActive, k.triNum); \
+                                else        k_trace_shadow<OCC, 0><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work, k.minActive, k.triNum); } while (0)
+    if (o >= 16) OHB_LAUNCH_TS(16); else if (o >= 12) OHB_LAUNCH_TS(12); else OHB_LAUNCH_TS(9);
+#undef OHB_LAUNCH_TS
 }
 #define SHADE_THREADS 128
 __global__ void __launch_bounds__(SHADE_THREADS) k_raygen(FrameParams fr, PathArrays P, uint32_t total) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= total) return;
     raygenPath(fr, P, p);
-    if (OHB_ST_STAGE(P.meta[p].w) != ST_DONE) { uint32_t q = alloc_slot(P.countIn); P.queueIn[q] = p; }
+    if (OHB_ST_STAGE(P.meta[p].w) != ST_DONE) { uint32_t q = alloc_slot(P.countIn); P.queueIn[q] = p | OHB_Q_PRIMARY; }
 }
 __global__ void __launch_bounds__(SHADE_THREADS) k_surface(SceneDev sc, FrameParams fr, PathArrays P) {
     const uint32_t n = *P.countIn;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint32_t p = P.queueIn[i];
+        uint32_t e = P.queueIn[i];
         // two-ended re-emit: k_bounce then runs hit-only and miss-only warps (35 % of bounce rays miss on the helmet scene)
-        if (surfacePath(sc, fr, P, p)) P.queueSorted[alloc_slot(P.sortCount)] = p;
-        else                           P.queueSorted[n - 1u - alloc_slot(P.sortCount + 1)] = p;
+        if (surfacePath(sc, fr, P, OHB_Q_PATH(e))) P.queueSorted[alloc_slot(P.sortCount)] = e;
+        else                                       P.queueSorted[n - 1u - alloc_slot(P.sortCount + 1)] = e | OHB_Q_MISS;
     }
 }
 template <int MINB>
 __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_bounce(SceneDev sc, FrameParams fr, PathArrays P) {
     const uint32_t n = *P.countIn;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint32_t p = P.queueSorted[i];
-        if (bouncePath(sc, fr, P, p)) { uint32_t q = alloc_slot(P.countOut); P.queueOut[q] = p; }
+        uint32_t e = bouncePath(sc, fr, P, P.queueSorted[i]);
+        if (e != OHB_Q_NONE) { uint32_t q = alloc_slot(P.countOut); P.queueOut[q] = e; }
     }
 }
 // Between iterations: account the rays just traced, clear the queues that are about to be refilled.
@@ -435,7 +451,7 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_raygen_rt(FrameParams fr, Pat
 __global__ void __launch_bounds__(SHADE_THREADS, 8) k_bounce_rt(SceneDev sc, FrameParams fr, PathArrays P) {
     const uint32_t n = *P.countIn;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint32_t p = P.queueSorted[i];
+        uint32_t p = OHB_Q_PATH(P.queueSorted[i]);
         if (bouncePathRT(sc, fr, P, p)) { uint32_t q = alloc_slot(P.countOut); P.queueOut[q] = p; }
     }
 }
@@ -499,18 +515,19 @@ struct HookIO {
         else occ[i] = t.anyHit ? 1 : 0;
     }
 };
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace_batch(SceneDev sc, const ohb_ray* rays, uint32_t n, ohb_hit* hits, uint32_t* work) {
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_batch(SceneDev sc, const ohb_ray* rays, uint32_t n, ohb_hit* hits, uint32_t* work, int mode, int minActive, int triNum) {
     HookIO io{rays, hits, nullptr};
-    persistentTrace<false>(sc, n, work, io);
+    if (mode) persistentTrace<false, 1>(sc, n, work, io, minActive, triNum); else persistentTrace<false, 0>(sc, n, work, io, minActive, triNum);
 }
-__global__ void __launch_bounds__(TRACE_THREADS) k_occluded_batch(SceneDev sc, const ohb_ray* rays, uint32_t n, uint8_t* occ, uint32_t* work) {
+__global__ void __launch_bounds__(TRACE_THREADS) k_occluded_batch(SceneDev sc, const ohb_ray* rays, uint32_t n, uint8_t* occ, uint32_t* work, int mode, int minActive, int triNum) {
     HookIO io{rays, nullptr, occ};
-    persistentTrace<true>(sc, n, work, io);
+    if (mode) persistentTrace<true, 1>(sc, n, work, io, minActive, triNum); else persistentTrace<true, 0>(sc, n, work, io, minActive, triNum);
 }
 void launchTraceBatch(const SceneDev& sc, const ohb_ray* rays, uint32_t n, ohb_hit* hits, uint8_t* occ, uint32_t* work, int numSMs, cudaStream_t st, uint64_t* launches) {
     k_zero_u32<<<1, 32, 0, st>>>(work, 2);
-    if (hits) k_trace_batch<<<numSMs * 8, TRACE_THREADS, 0, st>>>(sc, rays, n, hits, work);
-    else      k_occluded_batch<<<numSMs * 8, TRACE_THREADS, 0, st>>>(sc, rays, n, occ, work);
+    const TraceKnobs k = traceKnobs();
+    if (hits) k_trace_batch<<<numSMs * 8, TRACE_THREADS, 0, st>>>(sc, rays, n, hits, work, k.mode, k.minActive, k.triNum);
+    else      k_occluded_batch<<<numSMs * 8, TRACE_THREADS, 0, st>>>(sc, rays, n, occ, work, k.mode, k.minActive, k.triNum);
     *launches += 2;
 }
 

@@ -17,6 +17,15 @@ static inline int emulWarpActive() {
     return int(g_emulWarpState >> 27) + 1;
 }
 #define OHB_WARP_ACTIVE() emulWarpActive()
+// votes of travRunVote: this lane's own predicate plus a pseudo-random number of other lanes
+static inline int emulWarpCount(bool pred) {
+    if (!g_emulWarpNoise) return pred ? 32 : 0;
+    g_emulWarpState = g_emulWarpState * 1664525u + 1013904223u;
+    return (pred ? 1 : 0) + int((g_emulWarpState >> 27) % 24u) * int((g_emulWarpState >> 20) & 1u);
+}
+#define OHB_WARP_COUNT(pred) emulWarpCount(pred)
+static int g_emulTravMode = 1;
+#define OHB_TRAV_MODE() g_emulTravMode
 static unsigned long long g_statNodes = 0, g_statTris = 0;
 #define OHB_STAT_NODE() (g_statNodes++)
 #define OHB_STAT_TRI() (g_statTris++)
@@ -158,6 +167,7 @@ void* emul_scene_create(const emul_scene_desc* d) {
 void emul_scene_destroy(void* h) { delete (EmulScene*)h; }
 void emul_accel_stats(void* h, uint32_t* numNodes, float* sah) { EmulScene* s = (EmulScene*)h; *numNodes = s->numNodes; *sah = s->sah; }
 uint32_t emul_accel_levels(void* h) { return ((EmulScene*)h)->levels; }
+void emul_set_trav_mode(int m) { g_emulTravMode = m; }
 void emul_trav_stats(unsigned long long* nodes, unsigned long long* tris, int reset) { *nodes = g_statNodes; *tris = g_statTris; if (reset) { g_statNodes = 0; g_statTris = 0; } }
 void emul_set_warp_noise(unsigned on) { g_emulWarpNoise = on; g_emulWarpState = 12345u; }
 
@@ -222,18 +232,18 @@ int emul_render_offline(void* h, emul_render_args* a) {
     P.fh0 = fh0.data(); P.fh1 = fh1.data(); P.fh2 = fh2.data(); P.fh3 = fh3.data(); P.pay0 = pay0.data(); P.pay1 = pay1.data(); P.pay2 = pay2.data(); P.pay3 = pay3.data(); P.shO = shO.data(); P.shD = shD.data();
     P.queueIn = qa.data(); P.queueOut = qb.data(); P.countIn = &small[0]; P.countOut = &small[1]; P.shCount = &small[2]; P.counters = counters;
     P.albedoAOV = albedo.data(); P.normalAOV = normal.data(); P.numPixels = numPixels; P.samplesInBatch = a->nsamples; P.firstSampleIndex = a->first_sample_index;
-    for (uint32_t p = 0; p < total; p++) { raygenPath(fr, P, p); if (OHB_ST_STAGE(P.meta[p].w) != ST_DONE) P.queueIn[(*P.countIn)++] = p; }
+    for (uint32_t p = 0; p < total; p++) { raygenPath(fr, P, p); if (OHB_ST_STAGE(P.meta[p].w) != ST_DONE) P.queueIn[(*P.countIn)++] = p | OHB_Q_PRIMARY; }
     counters[0] += *P.countIn;
     uint32_t iters = 1u + 2u * fr.maxBounces;
     for (uint32_t it = 0; it < iters; it++) {
         uint32_t n = *P.countIn;
-        for (uint32_t i = 0; i < n; i++) { uint32_t p = P.queueIn[i]; P.hit[p] = traceClosest(sc, xyz(P.rayO[p]), xyz(P.rayD[p]), 0.001f, 10000.0f); counters[3] += P.hit[p].prim != OHB_MISS; }
+        for (uint32_t i = 0; i < n; i++) { uint32_t p = OHB_Q_PATH(P.queueIn[i]); P.hit[p] = traceClosest(sc, xyz(P.rayO[p]), xyz(P.rayD[p]), 0.001f, 10000.0f); counters[3] += P.hit[p].prim != OHB_MISS; }
         sortCount[0] = sortCount[1] = 0;
         for (uint32_t i = 0; i < n; i++) {                                                                                               // k_surface
-            uint32_t p = P.queueIn[i];
-            if (surfacePath(sc, fr, P, p)) P.queueSorted[sortCount[0]++] = p; else P.queueSorted[n - 1u - sortCount[1]++] = p;
+            uint32_t e = P.queueIn[i];
+            if (surfacePath(sc, fr, P, OHB_Q_PATH(e))) P.queueSorted[sortCount[0]++] = e; else P.queueSorted[n - 1u - sortCount[1]++] = e | OHB_Q_MISS;
         }
-        for (uint32_t i = 0; i < n; i++) { uint32_t p = P.queueSorted[i]; if (bouncePath(sc, fr, P, p)) P.queueOut[(*P.countOut)++] = p; }   // k_bounce
+        for (uint32_t i = 0; i < n; i++) { uint32_t e = bouncePath(sc, fr, P, P.queueSorted[i]); if (e != OHB_Q_NONE) P.queueOut[(*P.countOut)++] = e; }   // k_bounce
         uint32_t ns = *P.shCount;
         for (uint32_t i = 0; i < ns; i++) {
             f4 o = P.shO[i], d = P.shD[i];

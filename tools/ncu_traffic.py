@@ -8,12 +8,12 @@ rows = list(csv.reader(io.StringIO(out))); hdr, units = rows[0], rows[1]
 sc = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 agg = collections.defaultdict(lambda: [0, 0.0])
 for r in rows[2:]:
-    name = r[hdr.index("Kernel Name")].split("(")[0].split("<")[0].split("::")[-1]
+    name = r[hdr.index("Kernel Name")].split("(")[0].split("<")[0].split("::")[-1].replace("void ", "").strip()
     b = 0.0
     for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
         i = hdr.index(m); b += float(r[i]) * sc.get(units[i], 1)
     agg[name][0] += 1; agg[name][1] += b
-path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+path = os.environ.get("OHB_TRAFFIC_JSON") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
 data = json.load(open(path)) if os.path.exists(path) else {}
 data[key] = {k: {"launches_profiled": n, "bytes_per_launch": tot / n, "source": os.path.basename(rep)} for k, (n, tot) in agg.items()}
 json.dump(data, open(path, "w"), indent=1, sort_keys=True)
