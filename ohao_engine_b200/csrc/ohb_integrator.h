@@ -26,10 +26,10 @@ enum { ST_PRIMARY = 0u, ST_CHAIN_B = 1u, ST_CHAIN_C = 2u, ST_DONE = 3u };
 #define OHB_ST_PEND_B     (1u << 8)
 #define OHB_ST_MAKE(stage, bounce) ((stage) | ((bounce) << 2))
 
-// Queue entries carry the path index (OHB_MAX_PATHS <= 2^24) plus what the NEXT shading kernel needs to know to
+// Queue entries carry the path index (OHB_MAX_PATHS <= 2^28) plus what the NEXT shading kernel needs to know to
 // issue all of its path-state loads at once instead of chasing meta -> pend -> payload (k_bounce was stalled on
 // that dependent chain: 60 % of its samples on the first uses of meta / pendA / pay0, profile r1d).
-#define OHB_Q_PATH(e)   ((e) & 0x00FFFFFFu)
+#define OHB_Q_PATH(e)   ((e) & 0x0FFFFFFFu)
 #define OHB_Q_MISS      0x80000000u      // set by k_surface: the last closest-hit query missed
 #define OHB_Q_PEND_A    0x40000000u      // set by k_bounce: a light-NEE contribution is parked in pendA
 #define OHB_Q_PEND_B    0x20000000u      //                  an env-NEE contribution is parked in pendB

@@ -258,15 +258,15 @@ void launchEnvPdf(const SceneDev& sc, const float* dirs3, uint32_t n, float* pdf
 // Traversal kernels (persistent, warp-granular dynamic fetch)
 // =============================================================================================
 #define TRACE_THREADS 128
-// Scheduling knobs of the traversal kernels (env overrides are for A/B measurements on the GPU box):
-//   minActive : pause traversal and refill idle lanes when fewer lanes than this still traverse   (OHB_TRACE_MIN_ACTIVE)
-//   mode      : 0 = travRun (triangles right after the node visit), 1 = travRunVote (warp-voted triangle steps) (OHB_TRAV_MODE)
-//   triNum    : mode 1 fires a triangle step when >= triNum/8 of the traversing lanes want one        (OHB_TRI_NUM)
-struct TraceKnobs { int minActive, mode, triNum; };
+// Scheduling knobs of the traversal kernels (the env overrides exist for A/B measurements on the GPU box):
+//   minActive   : pause traversal and refill idle lanes when fewer lanes than this still traverse   (OHB_TRACE_MIN_ACTIVE)
+//   postponeDen : travRun's triangle-postponing threshold                                            (OHB_POSTPONE_DEN)
+struct TraceKnobs { int minActive, postponeDen; };
 static TraceKnobs traceKnobs() {
     static const TraceKnobs k = []() {
         auto geti = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
-        TraceKnobs r; r.minActive = geti("OHB_TRACE_MIN_ACTIVE", 20); r.mode = geti("OHB_TRAV_MODE", 1); r.triNum = geti("OHB_TRI_NUM", OHB_TRI_NUM_DEFAULT);
+        TraceKnobs r; r.minActive = geti("OHB_TRACE_MIN_ACTIVE", 20); r.postponeDen = geti("OHB_POSTPONE_DEN", OHB_POSTPONE_DEN_DEFAULT);
+        if (r.postponeDen < 2) r.postponeDen = 2;      // 0 or 1 would postpone every triangle forever
         return r;
     }();
     return k;
@@ -275,8 +275,8 @@ static TraceKnobs traceKnobs() {
 // (warp-aggregated atomic); a lane that finishes its ray waits at the reconvergence point of the `have`
 // block until the traversing lanes either finish or drop below TRACE_MIN_ACTIVE, then all idle lanes are
 // refilled together.  IO = { load(i, o, d, tmin, tmax), store(i, Trav&) }.
-template <bool ANY, int MODE, class IO>
-__device__ __forceinline__ void persistentTrace(const SceneDev& sc, uint32_t n, uint32_t* work, IO& io, int minActive, int triNum) {
+template <bool ANY, class IO>
+__device__ __forceinline__ void persistentTrace(const SceneDev& sc, uint32_t n, uint32_t* work, IO& io, int minActive, int postponeDen) {
     const uint32_t lane = threadIdx.x & 31u;
     Trav t; TravStackEntry stack[OHB_STACK_SIZE]; uint32_t idx = 0; bool have = false, exhausted = false;
     for (;;) {
@@ -293,7 +293,7 @@ __device__ __forceinline__ void persistentTrace(const SceneDev& sc, uint32_t n, 
         }
         if (!__any_sync(0xffffffffu, have)) break;
         bool done = false;
-        if (have) done = MODE ? travRunVote<ANY>(t, stack, sc, minActive, triNum) : travRun<ANY>(t, stack, sc, minActive);
+        if (have) done = travRun<ANY>(t, stack, sc, minActive, postponeDen);
         __syncwarp();
         if (done) { io.store(idx, t); have = false; }
     }
@@ -311,10 +311,10 @@ struct PathClosestIO {
         hits += hit;
     }
 };
-template <int MINB, int MODE>
-__global__ void __launch_bounds__(TRACE_THREADS, MINB) k_trace_closest(SceneDev sc, PathArrays P, uint32_t* work, int minActive, int triNum) {
+template <int MINB>
+__global__ void __launch_bounds__(TRACE_THREADS, MINB) k_trace_closest(SceneDev sc, PathArrays P, uint32_t* work, int minActive, int postponeDen) {
     PathClosestIO io{P, 0u};
-    persistentTrace<false, MODE>(sc, *P.countIn, work, io, minActive, triNum);
+    persistentTrace<false>(sc, *P.countIn, work, io, minActive, postponeDen);
     uint32_t hits = __reduce_add_sync(0xffffffffu, io.hits);
     if ((threadIdx.x & 31u) == 0 && hits) atomicAdd(P.counters + 3, (unsigned long long)hits);
 }
@@ -330,26 +330,29 @@ struct PathShadowIO {
         pend[tag >> 1] = mk4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 };
-template <int MINB, int MODE>
-__global__ void __launch_bounds__(TRACE_THREADS, MINB) k_trace_shadow(SceneDev sc, PathArrays P, uint32_t* work, int minActive, int triNum) {
+template <int MINB>
+__global__ void __launch_bounds__(TRACE_THREADS, MINB) k_trace_shadow(SceneDev sc, PathArrays P, uint32_t* work, int minActive, int postponeDen) {
     PathShadowIO io{P};
-    persistentTrace<true, MODE>(sc, *P.shCount, work, io, minActive, triNum);
+    persistentTrace<true>(sc, *P.shCount, work, io, minActive, postponeDen);
 }
-static int traceOcc() { static const int v = []() { const char* e = getenv("OHB_TRACE_OCC"); return e ? atoi(e) : 12; }(); return v; }
+// resident CTAs per SM the traversal kernels are compiled for: 8 -> 64 registers, 9 -> 56, 10 -> 48, 12 -> 40, 16 -> 32.
+// 9 is the measured optimum with the 8-wide BVH (profiles/r1f_sweep.txt, r1g_sweep.txt).
+static int traceOcc() {
+    static const int v = []() { const char* e = getenv("OHB_TRACE_OCC"); int o = e ? atoi(e) : 9; return o >= 16 ? 16 : (o >= 12 ? 12 : (o >= 10 ? 10 : (o >= 9 ? 9 : 8))); }();
+    return v;
+}
 static void launchTraceClosest(unsigned smGrid8, const SceneDev& sc, const PathArrays& P, uint32_t* work, cudaStream_t st) {
-    int o = traceOcc(); unsigned grid = smGrid8 / 8u * unsigned(o >= 16 ? 16 : (o >= 12 ? 12 : 9));
+    const int o = traceOcc(); const unsigned grid = smGrid8 / 8u * unsigned(o);
     const TraceKnobs k = traceKnobs();
-#define OHB_LAUNCH_TC(OCC) do { if (k.mode) k_trace_closest<OCC, 1><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work, k.minActive, k.triNum); \
-                                else        k_trace_closest<OCC, 0><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work, k.minActive, k.triNum); } while (0)
-    if (o >= 16) OHB_LAUNCH_TC(16); else if (o >= 12) OHB_LAUNCH_TC(12); else OHB_LAUNCH_TC(9);
+#define OHB_LAUNCH_TC(OCC) k_trace_closest<OCC><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work, k.minActive, k.postponeDen)
+    if (o == 16) OHB_LAUNCH_TC(16); else if (o == 12) OHB_LAUNCH_TC(12); else if (o == 10) OHB_LAUNCH_TC(10); else if (o == 9) OHB_LAUNCH_TC(9); else OHB_LAUNCH_TC(8);
 #undef OHB_LAUNCH_TC
 }
 static void launchTraceShadow(unsigned smGrid8, const SceneDev& sc, const PathArrays& P, uint32_t* work, cudaStream_t st) {
-    int o = traceOcc(); unsigned grid = smGrid8 / 8u * unsigned(o >= 16 ? 16 : (o >= 12 ? 12 : 9));
+    const int o = traceOcc(); const unsigned grid = smGrid8 / 8u * unsigned(o);
     const TraceKnobs k = traceKnobs();
-#define OHB_LAUNCH_TS(OCC) do { if (k.mode) k_trace_shadow<OCC, 1><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work, k.minActive, k.triNum); \
-                                else        k_trace_shadow<OCC, 0><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work, k.minActive, k.triNum); } while (0)
-    if (o >= 16) OHB_LAUNCH_TS(16); else if (o >= 12) OHB_LAUNCH_TS(12); else OHB_LAUNCH_TS(9);
+#define OHB_LAUNCH_TS(OCC) k_trace_shadow<OCC><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work, k.minActive, k.postponeDen)
+    if (o == 16) OHB_LAUNCH_TS(16); else if (o == 12) OHB_LAUNCH_TS(12); else if (o == 10) OHB_LAUNCH_TS(10); else if (o == 9) OHB_LAUNCH_TS(9); else OHB_LAUNCH_TS(8);
 #undef OHB_LAUNCH_TS
 }
 #define SHADE_THREADS 128
@@ -363,7 +366,9 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_surface(SceneDev sc, FramePar
     const uint32_t n = *P.countIn;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         uint32_t e = P.queueIn[i];
-        // two-ended re-emit: k_bounce then runs hit-only and miss-only warps (35 % of bounce rays miss on the helmet scene)
+        // two-ended re-emit: k_bounce then runs hit-only and miss-only warps (35 % of bounce rays miss on the helmet scene).
+        // It has to happen HERE, in queue order: emitting from k_trace_closest's store (rays finish in arbitrary order)
+        // scatters the path indices and made k_surface + k_bounce 60 % slower (sector-inefficient path records, r1i).
         if (surfacePath(sc, fr, P, OHB_Q_PATH(e))) P.queueSorted[alloc_slot(P.sortCount)] = e;
         else                                       P.queueSorted[n - 1u - alloc_slot(P.sortCount + 1)] = e | OHB_Q_MISS;
     }
@@ -515,19 +520,19 @@ struct HookIO {
         else occ[i] = t.anyHit ? 1 : 0;
     }
 };
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace_batch(SceneDev sc, const ohb_ray* rays, uint32_t n, ohb_hit* hits, uint32_t* work, int mode, int minActive, int triNum) {
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_batch(SceneDev sc, const ohb_ray* rays, uint32_t n, ohb_hit* hits, uint32_t* work, int minActive, int postponeDen) {
     HookIO io{rays, hits, nullptr};
-    if (mode) persistentTrace<false, 1>(sc, n, work, io, minActive, triNum); else persistentTrace<false, 0>(sc, n, work, io, minActive, triNum);
+    persistentTrace<false>(sc, n, work, io, minActive, postponeDen);
 }
-__global__ void __launch_bounds__(TRACE_THREADS) k_occluded_batch(SceneDev sc, const ohb_ray* rays, uint32_t n, uint8_t* occ, uint32_t* work, int mode, int minActive, int triNum) {
+__global__ void __launch_bounds__(TRACE_THREADS) k_occluded_batch(SceneDev sc, const ohb_ray* rays, uint32_t n, uint8_t* occ, uint32_t* work, int minActive, int postponeDen) {
     HookIO io{rays, nullptr, occ};
-    if (mode) persistentTrace<true, 1>(sc, n, work, io, minActive, triNum); else persistentTrace<true, 0>(sc, n, work, io, minActive, triNum);
+    persistentTrace<true>(sc, n, work, io, minActive, postponeDen);
 }
 void launchTraceBatch(const SceneDev& sc, const ohb_ray* rays, uint32_t n, ohb_hit* hits, uint8_t* occ, uint32_t* work, int numSMs, cudaStream_t st, uint64_t* launches) {
     k_zero_u32<<<1, 32, 0, st>>>(work, 2);
     const TraceKnobs k = traceKnobs();
-    if (hits) k_trace_batch<<<numSMs * 8, TRACE_THREADS, 0, st>>>(sc, rays, n, hits, work, k.mode, k.minActive, k.triNum);
-    else      k_occluded_batch<<<numSMs * 8, TRACE_THREADS, 0, st>>>(sc, rays, n, occ, work, k.mode, k.minActive, k.triNum);
+    if (hits) k_trace_batch<<<numSMs * 8, TRACE_THREADS, 0, st>>>(sc, rays, n, hits, work, k.minActive, k.postponeDen);
+    else      k_occluded_batch<<<numSMs * 8, TRACE_THREADS, 0, st>>>(sc, rays, n, occ, work, k.minActive, k.postponeDen);
     *launches += 2;
 }
 

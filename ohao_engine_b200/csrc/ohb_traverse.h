@@ -142,14 +142,14 @@ OHB_HD bool intersectTri(const RayPrep& r, f3 p0, f3 p1, f3 p2, float tmax, floa
 
 struct Trav {
     RayPrep r; float tmax; ohb_hit best;
-    u2 G, Gt; int sp, tc; uint32_t octinv; bool anyHit;     // tc: parked triangle groups (travRunVote), stored top-down in the stack array
+    u2 G, Gt; int sp; uint32_t octinv; bool anyHit;
 };
 typedef u2 TravStackEntry;
 
 OHB_HD void travInit(Trav& t, const SceneDev& s, f3 o, f3 d, float tmin, float tmax) {
     t.r = prepRay(o, d, tmin); t.tmax = tmax;
     t.best.t = tmax; t.best.u = 0.0f; t.best.v = 0.0f; t.best.prim = OHB_MISS;
-    t.sp = 0; t.tc = 0; t.anyHit = false;
+    t.sp = 0; t.anyHit = false;
     // bit 2/1/0 set = the ray travels toward +x/+y/+z: slot ^ octinv is then the visit priority (7 first)
     uint32_t octinv = (t.r.idir.x < 0.0f ? 0u : 4u) | (t.r.idir.y < 0.0f ? 0u : 2u) | (t.r.idir.z < 0.0f ? 0u : 1u);
     t.octinv = octinv;
@@ -226,9 +226,14 @@ OHB_HD uint32_t intersectWideNode(const Trav& t, const u4* np, float thi, uint32
 }
 
 // Runs until the query is finished (returns true) or fewer than `minActive` lanes of the warp are still
-// traversing (returns false; call again later).  ANY = TerminateOnFirstHit.
+// traversing (returns false; call again later).  ANY = TerminateOnFirstHit.  Lanes postpone their remaining leaf
+// triangles when fewer than 1/postponeDen of the lanes that entered the triangle loop are still in it (>= 2).
+// (A variant that parked triangle groups and tested them in warp-voted steps to raise the SIMT efficiency of the
+// triangle test was measured 17 % SLOWER on both workloads, profiles/r1e_sweep.txt: a closest hit that is found
+// late stops culling the nodes behind it.  Triangles are therefore tested right after the node visit.)
+#define OHB_POSTPONE_DEN_DEFAULT 5
 template <bool ANY>
-OHB_HD bool travRun(Trav& t, TravStackEntry* stack, const SceneDev& s, int minActive) {
+OHB_HD bool travRun(Trav& t, TravStackEntry* stack, const SceneDev& s, int minActive, int postponeDen) {
     for (;;) {
         if (t.G.y & 0xFF000000u) {
             // next inner child of the current group, front to back
@@ -247,7 +252,7 @@ OHB_HD bool travRun(Trav& t, TravStackEntry* stack, const SceneDev& s, int minAc
         // leaf triangles; when most lanes of the warp have none left, the rest postpone theirs (Ylitie et al. §4.3)
         const int entered = OHB_WARP_ACTIVE();
         while (t.Gt.y) {
-            if (OHB_WARP_ACTIVE() * 5 < entered && t.sp < OHB_POSTPONE_SLOTS) { stack[t.sp++] = t.Gt; t.Gt.y = 0u; break; }
+            if (OHB_WARP_ACTIVE() * postponeDen < entered && t.sp < OHB_POSTPONE_SLOTS) { stack[t.sp++] = t.Gt; t.Gt.y = 0u; break; }
             const uint32_t k = bfind32(t.Gt.y);
             t.Gt.y &= ~(1u << k);
             const f4* tp = s.tris + size_t(t.Gt.x + k) * 3u;
@@ -268,83 +273,17 @@ OHB_HD bool travRun(Trav& t, TravStackEntry* stack, const SceneDev& s, int minAc
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Vote-scheduled variant ("if-if" with warp votes).  travRun above tests a node's leaf triangles right after the
-// node visit, so the triangle code runs with the few lanes (measured: ~6 of 32, profile r1d) that happen to have
-// hit a leaf in the same step.  Here hit triangle groups are parked (current group Gt + a queue of up to
-// OHB_POSTPONE_SLOTS groups at the top of the stack array) while the lane keeps visiting nodes, and ONE triangle
-// per wanting lane is tested whenever at least triNum/8 of the traversing lanes want a test or no lane has node
-// work left.  A lane whose node work is exhausted simply waits for the vote (it would idle until the next refill
-// anyway).  The order in which triangles are tested does not change the result (tree-independent hits, header).
-// ---------------------------------------------------------------------------------------------
-#if OHB_DEVICE_CODE
-#define OHB_WARP_COUNT(pred) (__popc(__ballot_sync(__activemask(), (pred))))
-#elif !defined(OHB_WARP_COUNT)
-#define OHB_WARP_COUNT(pred) ((pred) ? 32 : 0)
-#endif
-#define OHB_INNER_BITS 0xFF000000u
-
-template <bool ANY>
-OHB_HD bool travRunVote(Trav& t, TravStackEntry* stack, const SceneDev& s, int minActive, int triNum) {
-    for (;;) {
-        // node step: at most one visit; the node stack holds only groups that still have inner children to visit
-        if (!(t.G.y & OHB_INNER_BITS) && t.sp > 0) t.G = stack[--t.sp];
-        bool busy = (t.G.y & OHB_INNER_BITS) != 0u && t.tc < OHB_POSTPONE_SLOTS;
-        if (busy) {
-            const uint32_t bit = bfind32(t.G.y);
-            const uint32_t slot = (bit - 24u) ^ t.octinv;
-            t.G.y &= ~(1u << bit);
-            const uint32_t idx = t.G.x + popc32(t.G.y & 0xFFu & ((1u << slot) - 1u));
-            if (t.G.y & OHB_INNER_BITS) stack[t.sp++] = t.G;
-            uint32_t childBase, triBase, imask, triMask;
-            const uint32_t hits = intersectWideNode(t, s.wnodes + size_t(idx) * OHB_WNODE_VECS, ANY ? t.tmax : t.best.t, childBase, triBase, imask, triMask);
-            t.G.x = childBase; t.G.y = hits | imask;
-            if (triMask) {
-                u2 g; g.x = triBase; g.y = triMask;
-                if (!t.Gt.y) t.Gt = g; else { t.tc++; stack[OHB_STACK_SIZE - t.tc] = g; }
-            }
-        }
-        // triangle step
-        const bool want = t.Gt.y != 0u;
-        const bool more = (t.G.y & OHB_INNER_BITS) != 0u || t.sp > 0;          // node work left for a later iteration
-        if (!want && !more) return true;
-        const int nAct = OHB_WARP_ACTIVE(), nWant = OHB_WARP_COUNT(want), nBusy = OHB_WARP_COUNT(more && t.tc < OHB_POSTPONE_SLOTS);
-        if (want && (nWant * 8 >= nAct * triNum || nBusy == 0)) {
-            const uint32_t k = bfind32(t.Gt.y);
-            t.Gt.y &= ~(1u << k);
-            const f4* tp = s.tris + size_t(t.Gt.x + k) * 3u;
-            f4 v0 = ld4(tp), v1 = ld4(tp + 1), v2 = ld4(tp + 2);
-            float tt, bu, bv;
-            OHB_STAT_TRI();
-            if (intersectTri(t.r, xyz(v0), xyz(v1), xyz(v2), t.tmax, tt, bu, bv)) {
-                if (ANY) { t.anyHit = true; t.G.y = 0u; t.Gt.y = 0u; t.sp = 0; t.tc = 0; return true; }
-                uint32_t id = f2u(v0.w);
-                if (t.best.prim == OHB_MISS || tt < t.best.t || (tt == t.best.t && id < t.best.prim)) { t.best.t = tt; t.best.u = bu; t.best.v = bv; t.best.prim = id; }
-            }
-            if (!t.Gt.y && t.tc > 0) { t.Gt = stack[OHB_STACK_SIZE - t.tc]; t.tc--; }
-            if (!t.Gt.y && !more) return true;
-        }
-        if (OHB_WARP_ACTIVE() < minActive) return false;
-    }
-}
-
-// Scheduling variant used by the stand-alone queries below (and by the emulator): 0 = travRun, 1 = travRunVote.
-#ifndef OHB_TRAV_MODE
-#define OHB_TRAV_MODE() 1
-#endif
-#define OHB_TRI_NUM_DEFAULT 4
-
 // Closest hit.  Returns prim == OHB_MISS and t = -1 on miss.
 OHB_HD ohb_hit traceClosest(const SceneDev& s, f3 o, f3 d, float tmin, float tmax) {
     Trav t; TravStackEntry stack[OHB_STACK_SIZE]; travInit(t, s, o, d, tmin, tmax);
-    if (t.G.y) { if (OHB_TRAV_MODE()) while (!travRunVote<false>(t, stack, s, 0, OHB_TRI_NUM_DEFAULT)) {} else while (!travRun<false>(t, stack, s, 0)) {} }
+    if (t.G.y) while (!travRun<false>(t, stack, s, 0, OHB_POSTPONE_DEN_DEFAULT)) {}
     if (t.best.prim == OHB_MISS) t.best.t = -1.0f;
     return t.best;
 }
 // Any hit in (tmin, tmax): TerminateOnFirstHit | SkipClosestHit.
 OHB_HD bool traceAny(const SceneDev& s, f3 o, f3 d, float tmin, float tmax) {
     Trav t; TravStackEntry stack[OHB_STACK_SIZE]; travInit(t, s, o, d, tmin, tmax);
-    if (t.G.y) { if (OHB_TRAV_MODE()) while (!travRunVote<true>(t, stack, s, 0, OHB_TRI_NUM_DEFAULT)) {} else while (!travRun<true>(t, stack, s, 0)) {} }
+    if (t.G.y) while (!travRun<true>(t, stack, s, 0, OHB_POSTPONE_DEN_DEFAULT)) {}
     return t.anyHit;
 }
 

@@ -17,15 +17,6 @@ static inline int emulWarpActive() {
     return int(g_emulWarpState >> 27) + 1;
 }
 #define OHB_WARP_ACTIVE() emulWarpActive()
-// votes of travRunVote: this lane's own predicate plus a pseudo-random number of other lanes
-static inline int emulWarpCount(bool pred) {
-    if (!g_emulWarpNoise) return pred ? 32 : 0;
-    g_emulWarpState = g_emulWarpState * 1664525u + 1013904223u;
-    return (pred ? 1 : 0) + int((g_emulWarpState >> 27) % 24u) * int((g_emulWarpState >> 20) & 1u);
-}
-#define OHB_WARP_COUNT(pred) emulWarpCount(pred)
-static int g_emulTravMode = 1;
-#define OHB_TRAV_MODE() g_emulTravMode
 static unsigned long long g_statNodes = 0, g_statTris = 0;
 #define OHB_STAT_NODE() (g_statNodes++)
 #define OHB_STAT_TRI() (g_statTris++)
@@ -167,7 +158,6 @@ void* emul_scene_create(const emul_scene_desc* d) {
 void emul_scene_destroy(void* h) { delete (EmulScene*)h; }
 void emul_accel_stats(void* h, uint32_t* numNodes, float* sah) { EmulScene* s = (EmulScene*)h; *numNodes = s->numNodes; *sah = s->sah; }
 uint32_t emul_accel_levels(void* h) { return ((EmulScene*)h)->levels; }
-void emul_set_trav_mode(int m) { g_emulTravMode = m; }
 void emul_trav_stats(unsigned long long* nodes, unsigned long long* tris, int reset) { *nodes = g_statNodes; *tris = g_statTris; if (reset) { g_statNodes = 0; g_statTris = 0; } }
 void emul_set_warp_noise(unsigned on) { g_emulWarpNoise = on; g_emulWarpState = 12345u; }
 

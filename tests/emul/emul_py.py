@@ -43,7 +43,6 @@ def lib():
         _LIB.emul_accel_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
         _LIB.emul_accel_levels.argtypes = [C.c_void_p]; _LIB.emul_accel_levels.restype = C.c_uint32
         _LIB.emul_set_warp_noise.argtypes = [C.c_uint]
-        _LIB.emul_set_trav_mode.argtypes = [C.c_int]
         _LIB.emul_trav_stats.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.c_int]
     return _LIB
 
@@ -133,11 +132,6 @@ class EmulScene:
 def set_warp_noise(on: bool):
     """Pseudo-random active-lane counts: drives triangle postponing and pause/resume in the host emulator."""
     lib().emul_set_warp_noise(1 if on else 0)
-
-
-def set_trav_mode(mode: int):
-    """0 = travRun (triangles tested right after the node visit), 1 = travRunVote (warp-voted triangle steps)."""
-    lib().emul_set_trav_mode(int(mode))
 
 
 def trav_stats(reset=True):
