@@ -62,12 +62,14 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def measured_traffic(workload: str, integrator: str, kernel: str):
+def measured_traffic(workload: str, integrator: str, kernel: str, units_per_launch: float):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture
-    (profiles/traffic.json, written by tools/ncu_traffic.py); None when no capture exists for this workload."""
+    (profiles/traffic.json, written by tools/ncu_traffic.py), scaled from the units (rays / paths) per launch of the
+    profiled run to the units per launch of THIS run; None when no capture exists for this workload."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return json.load(open(p))[f"{workload}/{integrator}"][kernel]["bytes_per_launch"]
+        e = json.load(open(p))[f"{workload}/{integrator}"][kernel]
+        return e["bytes_per_launch"] / e["units_per_launch"] * units_per_launch if e.get("units_per_launch") else e["bytes_per_launch"]
     except Exception:
         return None
 
@@ -162,6 +164,8 @@ def main():
     ap.add_argument("--spp-step", type=int, default=None, help="samples per pixel per step (default 16 offline, 1 realtime)")
     ap.add_argument("--integrator", default="offline", choices=["offline", "realtime"],
                     help="realtime = config 3: one frame per step (ReSTIR GI temporal + spatial, EMA, a-trous), 0.5 deg/frame orbit, N=1 only")
+    ap.add_argument("--denoise", default="none", choices=["none", "svgf"],
+                    help="realtime only: svgf = DenoiseMode::Atrous (fresh-sample frames + the SVGF denoiser, SURVEY 8f row 2)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bounded CPU-baseline sample (rank 0, N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -191,7 +195,11 @@ def main():
     r.set_scene(ps)
     if realtime:
         desc = desc.replace("offline, 4 bounces", "realtime, 2 bounces + ReSTIR GI temporal/spatial + EMA + a-trous, 0.5 deg/frame orbit")
-        stg = r.get_settings(); stg.samples_per_frame = args.spp_step; r.set_rt_render_settings(stg)
+        stg = r.get_settings(); stg.samples_per_frame = args.spp_step
+        if args.denoise == "svgf":
+            stg.denoise_mode = B.DENOISE_ATROUS
+            desc = desc.replace("EMA + a-trous", "a-trous, fresh-sample frames + SVGF denoiser (DenoiseMode::Atrous)")
+        r.set_rt_render_settings(stg)
         import copy, math as _m
         base_cam = copy.deepcopy(cam); frame_no = [0]
         radius = _m.hypot(base_cam.position[0], base_cam.position[2]); ang0 = _m.atan2(base_cam.position[2], base_cam.position[0])
@@ -282,7 +290,8 @@ def main():
         # 248 B per path for k_surface (ray 32 + hit 16 + 136 B surface gather + 64 B payload), 304 B per path for k_bounce
         units = {"trace_closest": (cnt["closest_rays"], br), "trace_shadow": (cnt["shadow_rays"], br),
                  "surface": (cnt["closest_rays"], 248), "bounce": (cnt["closest_rays"], 304), "film": (cnt["samples"], 36),
-                 "rt_pixel": (W * H * args.steps, 352 * spp + 416)}     # per pixel: N finished path records + 10 history planes in / 6 out
+                 "rt_pixel": (W * H * args.steps, 352 * spp + 416),     # per pixel: N finished path records + 10 history planes in / 6 out
+                 "svgf": (W * H * args.steps, 278)}                      # per pixel: temporal pass 78 B + 5 a-trous iterations x 40 B
         kern = {}
         for k, x in tim.items():
             if x["launches"] == 0: continue
@@ -300,14 +309,14 @@ def main():
                        "frames_per_s": (args.steps / (ms * 1e-3)) if realtime else None, "treelet_passes": int(st.treelet_passes),
                        "bvh_nodes": int(st.num_nodes), "bvh_sah": round(float(st.sah_cost), 2), "bvh_build_ms": round(float(st.build_ms), 3),
                        "parallelism": f"spp-shard x{world}" if world > 1 else "single GPU",
-                       "l2": "path-state working set %.1f GB per step >> 126 MB L2 (no explicit flush)" % (W * H * min(spp, 4) * 288 / 1e9)},
+                       "l2": "path-state working set %.1f GB per step >> 126 MB L2 (no explicit flush)" % (W * H * min(spp, 16) * 352 / 1e9)},
             "rays": {"per_sample": (tot["closest_rays"] + tot["shadow_rays"]) / max(tot["samples"], 1),
                      "closest_per_sample": tot["closest_rays"] / max(tot["samples"], 1), "shadow_per_sample": tot["shadow_rays"] / max(tot["samples"], 1),
                      "mrays_per_s": (tot["closest_rays"] + tot["shadow_rays"]) / (ms * 1e-3) / 1e6,
                      "gsamples_sbe_per_s": (tot["closest_rays"] + tot["shadow_rays"]) / (ms * 1e-3) / 2e9},
             "kernels": kern,
             "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": dk["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dk["frac"],
-                         "traffic": measured_traffic(args.workload, args.integrator, "k_" + dom), "peak_source": peak_src, "bytes_per_unit": dk["bytes_per_unit"], "units_per_launch": dk["units_per_launch"],
+                         "traffic": measured_traffic(args.workload, args.integrator, "k_" + dom, dk["units_per_launch"]), "peak_source": peak_src, "bytes_per_unit": dk["bytes_per_unit"], "units_per_launch": dk["units_per_launch"],
                          "avg_launch_ms": dk["avg_launch_ms"], "share_of_step": dk["share_of_step"]},
             "e2e": {"value": e2e_val, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(cnt["kernel_launches"]),

@@ -38,6 +38,10 @@ typedef struct ohb_ctx ohb_ctx;
 enum { OHB_PROFILE_OFFLINE = 0, OHB_PROFILE_REALTIME = 1 };
 /* SamplerType (sampler_types.hpp) ; GLSL SAMPLER_PCG=0 / SAMPLER_SOBOL=1 (sampler_api.glsl:12-13) */
 enum { OHB_SAMPLER_PCG = 0, OHB_SAMPLER_SOBOL = 1 };
+/* DenoiseMode (denoise/denoise_types.hpp:13-19), same numeric values.  Implemented: NONE and ATROUS (the SVGF
+ * denoiser of atrous_denoise.cpp, realtime profile only); ohb_set_settings refuses the others (OIDN / NRD /
+ * DLSS-RR are third-party libraries). */
+enum { OHB_DENOISE_NONE = 0, OHB_DENOISE_OIDN = 1, OHB_DENOISE_NRD = 3, OHB_DENOISE_ATROUS = 4, OHB_DENOISE_DLSSRR = 5 };
 
 /* Control-flag bits, identical to the raygen's PT_FLAG_* (pt_raygen_offline.rgen:59-63,
  * pt_raygen_realtime.rgen flag block) so a push-constant dump can be replayed. */
@@ -78,7 +82,8 @@ typedef struct ohb_settings {
     float    anisotropy_rotation; /* pc.jitter.w                                     */
     float    subsurface_strength; /* pc.tuning.w                                     */
     uint32_t samples_per_frame;   /* realtime N-spp loop, clamped to [1,64]          */
-    uint32_t _pad[3];
+    uint32_t denoise_mode;        /* OHB_DENOISE_* (RTRenderSettings::denoiseMode)   */
+    uint32_t _pad[2];
 } ohb_settings;
 
 /* Ray / hit records of the parity hook (north_star: closest-hit primitive IDs
@@ -189,7 +194,8 @@ void ohb_reset_counters(ohb_ctx*);
 int ohb_get_timing(ohb_ctx*, float* trace_ms, float* shade_ms, float* total_ms);
 int ohb_enable_timing(ohb_ctx*, int enable);
 /* Per-category device time and launch count: [0] closest-hit traversal, [1] bounce (raygen body: NEE, MIS,
- * lobe sampling), [2] any-hit traversal, [3] film, [4] surface (closest-hit / miss shaders), [5..7] reserved. */
+ * lobe sampling), [2] any-hit traversal, [3] film, [4] surface (closest-hit / miss shaders), [5] realtime per-pixel pass
+ * (ReSTIR GI + EMA), [6] SVGF denoiser, [7] reserved. */
 int ohb_get_timing_detail(ohb_ctx*, float ms[8], uint64_t launches[8]);
 /* Realtime-profile parity hooks.  ohb_set_realtime_dump: the next ohb_render also copies, per pixel, the N-spp mean
  * radiance after the x0.75 clamp (pt_raygen_realtime.rgen:1552-1556), the diffuse ReSTIR GI term (:1755-1764) and the
@@ -198,6 +204,17 @@ int ohb_get_timing_detail(ohb_ctx*, float ms[8], uint64_t launches[8]);
  * and the surface / shading history (bindings 14/16). */
 int ohb_set_realtime_dump(ohb_ctx*, float* radiance_rgba, float* gi_rgba, float* denoised_rgba);
 int ohb_read_realtime_state(ohb_ctx*, float* res0, float* res1, float* res2, float* surface_history, float* shading_history);
+/* AtrousDenoiser::dispatch (atrous_denoise.hpp:19-61, atrous_denoise.cpp:392-537) on caller-supplied images of the
+ * context's resolution (realtime-profile context): RGBA8 beauty in / denoised out, RGBA32F normal AOV (N*0.5+0.5),
+ * R32F linear view Z (1e30 = background), RG16F motion vectors packed x | y << 16 (pixel units, current - previous).
+ * The denoiser's history lives in the context and ping-pongs like AtrousDenoiser's; reset != 0 discards it.
+ * ohb_render runs the same kernels on its own images when settings.denoise_mode == OHB_DENOISE_ATROUS. */
+int ohb_svgf_dispatch(ohb_ctx*, uint8_t* beauty_rgba8, const float* normal_rgba, const float* depth, const uint32_t* motion_rg16f, int reset);
+/* SVGF denoiser parity hook (DenoiseMode::Atrous, AtrousDenoiser history images of atrous_denoise.cpp:79-121): the
+ * history written by the last frame as raw fp16 bits — colour RGBA16F, moments (m1, m2, len, 0) RGBA16F, geometry
+ * (viewZ, n) RGBA16F, W*H*4 uint16 each — and the guide AOVs of that frame: motion vectors RG16F packed x | y << 16
+ * (binding 19) and linear view Z R32F (binding 20).  Any pointer may be NULL. */
+int ohb_read_denoise_state(ohb_ctx*, uint16_t* color, uint16_t* moments, uint16_t* geom, uint32_t* motion, float* depth);
 /* Whole-region device timer: two CUDA events recorded on the context's stream (the stream every
  * kernel of this context is launched on).  ohb_timer_stop synchronises and returns the elapsed ms. */
 int ohb_timer_start(ohb_ctx*);

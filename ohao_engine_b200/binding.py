@@ -17,6 +17,7 @@ import numpy as np
 from . import build as _build
 
 PROFILE_OFFLINE, PROFILE_REALTIME = 0, 1
+DENOISE_NONE, DENOISE_ATROUS = 0, 4      # DenoiseMode values (denoise_types.hpp:13-19)
 FLAG_AOVS, FLAG_INTERNAL_DENOISE, FLAG_FIREFLY = 1, 2, 4
 FLAG_GOLDEN_COMPAT = 1 << 16
 
@@ -27,7 +28,7 @@ HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4")]
 class Settings(C.Structure):
     _fields_ = [("profile", C.c_uint32), ("max_bounces", C.c_uint32), ("flags", C.c_uint32), ("firefly_clamp_lum", C.c_float),
                 ("sampler_type", C.c_uint32), ("anisotropy_strength", C.c_float), ("anisotropy_rotation", C.c_float),
-                ("subsurface_strength", C.c_float), ("samples_per_frame", C.c_uint32), ("_pad", C.c_uint32 * 3)]
+                ("subsurface_strength", C.c_float), ("samples_per_frame", C.c_uint32), ("denoise_mode", C.c_uint32), ("_pad", C.c_uint32 * 2)]
 
 
 class Counters(C.Structure):
@@ -83,6 +84,8 @@ ABI = {
     "ohb_enable_timing": (_I, [_VP, _I]),
     "ohb_set_realtime_dump": (_I, [_VP, _VP, _VP, _VP]),
     "ohb_read_realtime_state": (_I, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    "ohb_svgf_dispatch": (_I, [_VP, _VP, _VP, _VP, _VP, _I]),
+    "ohb_read_denoise_state": (_I, [_VP, _VP, _VP, _VP, _VP, _VP]),
     "ohb_timer_start": (_I, [_VP]),
     "ohb_timer_stop": (_I, [_VP, C.POINTER(_F)]),
 }
@@ -278,6 +281,21 @@ class Renderer:
         self._ck(self.lib.ohb_read_realtime_state(self.h, _p(r0), _p(r1), _p(r2), _p(su), _p(sh)), "ohb_read_realtime_state")
         return dict(reservoirs=[r0, r1, r2], surf=su, shad=sh)
 
+    def svgf_dispatch(self, beauty, normal, depth, motion, reset: bool) -> np.ndarray:
+        """AtrousDenoiser::dispatch on host images (RGBA8, RGBA32F N*0.5+0.5, R32F view Z, RG16F bits): returns the denoised RGBA8."""
+        out = np.ascontiguousarray(beauty, np.uint8).copy()
+        n = np.ascontiguousarray(normal, np.float32); d = np.ascontiguousarray(depth, np.float32); m = np.ascontiguousarray(motion, np.uint32)
+        assert out.shape == (self.height, self.width, 4) and n.shape == (self.height, self.width, 4) and d.shape == (self.height, self.width) and m.shape == (self.height, self.width)
+        self._ck(self.lib.ohb_svgf_dispatch(self.h, _p(out), _p(n), _p(d), _p(m), int(bool(reset))), "ohb_svgf_dispatch")
+        return out
+
+    def read_denoise_state(self) -> dict:
+        """History written by the last SVGF dispatch (raw fp16 bits) and the guide AOVs of the last frame."""
+        z = lambda: np.zeros((self.height, self.width, 4), np.uint16)
+        col, mom, geo = z(), z(), z(); mot = np.zeros((self.height, self.width), np.uint32); dep = np.zeros((self.height, self.width), np.float32)
+        self._ck(self.lib.ohb_read_denoise_state(self.h, _p(col), _p(mom), _p(geo), _p(mot), _p(dep)), "ohb_read_denoise_state")
+        return dict(color=col, moments=mom, geom=geo, motion=mot, depth=dep)
+
     def timer_start(self): self._ck(self.lib.ohb_timer_start(self.h), "ohb_timer_start")
 
     def timer_stop(self) -> float:
@@ -286,5 +304,5 @@ class Renderer:
     def timing(self) -> dict:
         ms = (C.c_float * 8)(); cnt = (C.c_uint64 * 8)()
         self._ck(self.lib.ohb_get_timing_detail(self.h, C.byref(ms), C.byref(cnt)), "ohb_get_timing_detail")
-        names = ("trace_closest", "bounce", "trace_shadow", "film", "surface", "rt_pixel")
+        names = ("trace_closest", "bounce", "trace_shadow", "film", "surface", "rt_pixel", "svgf")
         return {n: dict(ms=float(ms[i]), launches=int(cnt[i])) for i, n in enumerate(names)}

@@ -91,6 +91,9 @@ struct ohb_ctx {
     DevBuf accum, ldr, albedoAOV, normalAOV, sampleDump;
     // realtime profile: ping-ponged history (index rtCur = the images written by the last frame)
     DevBuf accumPrev, surf[2], shad[2], res[2][3], rtDump[3];
+    // SVGF denoiser (DenoiseMode::Atrous): guide AOVs, ping-ponged history, scratch; svgfCur = history written by the last frame
+    DevBuf motionAOV, depthAOV, svgfHistColor[2], svgfHistMoments[2], svgfHistGeom[2], svgfColor[2], svgfVar[2];
+    int svgfCur = 0;
     int rtCur = 0; float prevViewProj[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
     float* rtDumpHost[3] = {nullptr, nullptr, nullptr};
     float* dumpHost = nullptr; size_t dumpCapacity = 0;
@@ -181,7 +184,9 @@ void ohb_destroy(ohb_ctx* c) {
                      &c->pendA, &c->pendB, &c->meta, &c->fh0, &c->fh1, &c->fh2, &c->fh3, &c->pay0, &c->pay1, &c->pay2, &c->pay3, &c->shO, &c->shD, &c->queueA, &c->queueB, &c->queueS, &c->sobolTab, &c->smallCounters, &c->devCounters,
                      &c->accum, &c->ldr, &c->albedoAOV, &c->normalAOV, &c->sampleDump, &c->hookRays, &c->hookOut, &c->hookAux,
                      &c->accumPrev, &c->surf[0], &c->surf[1], &c->shad[0], &c->shad[1], &c->res[0][0], &c->res[0][1], &c->res[0][2],
-                     &c->res[1][0], &c->res[1][1], &c->res[1][2], &c->rtDump[0], &c->rtDump[1], &c->rtDump[2]};
+                     &c->res[1][0], &c->res[1][1], &c->res[1][2], &c->rtDump[0], &c->rtDump[1], &c->rtDump[2],
+                     &c->motionAOV, &c->depthAOV, &c->svgfHistColor[0], &c->svgfHistColor[1], &c->svgfHistMoments[0], &c->svgfHistMoments[1],
+                     &c->svgfHistGeom[0], &c->svgfHistGeom[1], &c->svgfColor[0], &c->svgfColor[1], &c->svgfVar[0], &c->svgfVar[1]};
     for (DevBuf* b : all) b->release();
     if (c->evA) cudaEventDestroy(c->evA);
     if (c->evB) cudaEventDestroy(c->evB);
@@ -427,6 +432,8 @@ int ohb_set_settings(ohb_ctx* c, const ohb_settings* s) {
     if (!c || !s) return 1;
     if ((s->max_bounces & 0xFFFFu) > 15u) OHB_FAIL(c, "ohb_set_settings: max_bounces > 15");
     if (s->profile == OHB_PROFILE_REALTIME && c->profile != OHB_PROFILE_REALTIME) OHB_FAIL(c, "ohb_set_settings: realtime settings need a context created with OHB_PROFILE_REALTIME");
+    if (s->denoise_mode != OHB_DENOISE_NONE && s->denoise_mode != OHB_DENOISE_ATROUS) OHB_FAIL(c, "ohb_set_settings: denoise_mode must be OHB_DENOISE_NONE or OHB_DENOISE_ATROUS (OIDN / NRD / DLSS-RR are not part of this library)");
+    if (s->denoise_mode == OHB_DENOISE_ATROUS && s->profile != OHB_PROFILE_REALTIME) OHB_FAIL(c, "ohb_set_settings: OHB_DENOISE_ATROUS (SVGF) runs in the realtime profile only");
     c->settings = *s;
     uint32_t spf = s->samples_per_frame; c->settings.samples_per_frame = spf < 1u ? 1u : (spf > 64u ? 64u : spf);   // clampSamplesPerFrame
     return 0;
@@ -488,6 +495,8 @@ static void fillPaths(ohb_ctx* c, PathArrays& P) {
     P.sobolTab = c->sobolTab.as<u4>(); P.queueSorted = c->queueS.as<uint32_t>(); P.sortCount = small + 12;
 }
 int ensurePaths(ohb_ctx* c, uint32_t cap);
+static int ensureSvgf(ohb_ctx* c);
+static void runSvgf(ohb_ctx* c, bool reset);
 
 // One PathTracer::render() of the realtime profile per frame (path_tracer_render.cpp:686-724, :1274-1280):
 // frame index = m_sampleIndex, history count, view-changed flag, prevViewProj = last frame's proj*view, ping-pong flip.
@@ -503,10 +512,21 @@ static int renderRealtime(ohb_ctx* c, const float* view, const float* proj, uint
     for (int k = 0; k < 3; k++) if (c->rtDumpHost[k]) CU(c, c->rtDump[k].reserve(npx * 16));
     SceneDev s; fillScene(c, s);
     uint32_t* small = c->smallCounters.as<uint32_t>();
+    const bool svgf = c->settings.denoise_mode == OHB_DENOISE_ATROUS;
+    if (svgf && ensureSvgf(c)) return 1;
+    float currVP[16];   // proj * view (column-major)
+    for (int col = 0; col < 4; col++) for (int row = 0; row < 4; row++) {
+        float acc = 0.0f; for (int k = 0; k < 4; k++) acc += proj[k * 4 + row] * view[col * 4 + k];
+        currVP[col * 4 + row] = acc;
+    }
     for (uint32_t f = 0; f < nframes; f++) {
         FrameParams fr{}; fillFrameCommon(c, view, proj, fr);
         memcpy(fr.prevViewProj, c->prevViewProj, 64);
-        fr.frameIdx = c->sampleIndex; fr.historyCount = c->historyCount; fr.viewChanged = c->viewChanged ? 1u : 0u; fr.spf = spf;
+        memcpy(fr.currViewProj, currVP, 64);
+        fr.viewRow2[0] = view[2]; fr.viewRow2[1] = view[6]; fr.viewRow2[2] = view[10]; fr.viewRow2[3] = view[14];
+        // denoiseWantsFreshSample (path_tracer_render.cpp:707-712): with the SVGF denoiser the raygen sees historyFrameCount = 0
+        // every frame (a fresh N-spp beauty, no EMA, no ReSTIR reuse); the denoiser owns the temporal accumulation
+        fr.frameIdx = c->sampleIndex; fr.historyCount = svgf ? 0u : c->historyCount; fr.viewChanged = c->viewChanged ? 1u : 0u; fr.spf = spf;
         fr.jitterSobol = sobolQuad(fr.frameIdx);
         PathArrays P{}; fillPaths(c, P);
         P.numPixels = numPixels; P.samplesInBatch = spf; P.firstSampleIndex = fr.frameIdx * spf;
@@ -519,9 +539,11 @@ static int renderRealtime(ohb_ctx* c, const float* view, const float* proj, uint
         im.res0Curr = c->res[cur][0].as<f4>(); im.res1Curr = c->res[cur][1].as<f4>(); im.res2Curr = c->res[cur][2].as<f4>();
         im.radianceDump = c->rtDumpHost[0] ? c->rtDump[0].as<float>() : nullptr; im.giDump = c->rtDumpHost[1] ? c->rtDump[1].as<float>() : nullptr;
         im.counters = c->devCounters.as<unsigned long long>();
+        im.motionAOV = svgf ? c->motionAOV.as<uint32_t>() : nullptr; im.depthAOV = svgf ? c->depthAOV.as<float>() : nullptr;
         launchRealtimeFrame(s, fr, P, im, c->ldr.as<uint32_t>(), c->rtDumpHost[2] ? c->rtDump[2].as<float>() : nullptr, small + 4, c->numSMs, c->stream,
                             &c->launches, c->timingOn ? &c->timing : nullptr);
         c->rtCur = cur;
+        if (svgf) runSvgf(c, c->historyCount == 0u);   // AtrousDenoiser::dispatch on the finished beauty; history resets on the first frame only (path_tracer_render.cpp:756-762)
         // m_prevViewProj = proj * view (column-major)
         for (int col = 0; col < 4; col++) for (int row = 0; row < 4; row++) {
             float acc = 0.0f; for (int k = 0; k < 4; k++) acc += proj[k * 4 + row] * view[col * 4 + k];
@@ -632,6 +654,57 @@ static int traceHook(ohb_ctx* c, const ohb_ray* rays, uint32_t n, ohb_hit* hits,
 int ohb_trace_batch(ohb_ctx* c, const ohb_ray* rays, uint32_t n, ohb_hit* hits) { if (!rays || !hits) return 1; return traceHook(c, rays, n, hits, nullptr); }
 int ohb_occluded_batch(ohb_ctx* c, const ohb_ray* rays, uint32_t n, uint8_t* occ) { if (!rays || !occ) return 1; return traceHook(c, rays, n, nullptr, occ); }
 
+static int ensureSvgf(ohb_ctx* c) {
+    size_t npx = size_t(c->W) * c->H;
+    CU(c, c->motionAOV.reserve(npx * 4)); CU(c, c->depthAOV.reserve(npx * 4));
+    for (int i = 0; i < 2; i++) {
+        CU(c, c->svgfHistColor[i].reserve(npx * 8)); CU(c, c->svgfHistMoments[i].reserve(npx * 8)); CU(c, c->svgfHistGeom[i].reserve(npx * 8));
+        CU(c, c->svgfColor[i].reserve(npx * 8)); CU(c, c->svgfVar[i].reserve(npx * 2));
+    }
+    return 0;
+}
+static void runSvgf(ohb_ctx* c, bool reset) {
+    SvgfBuffers b{};
+    b.beauty = c->ldr.as<uint32_t>(); b.motion = c->motionAOV.as<uint32_t>(); b.depth = c->depthAOV.as<float>(); b.normal = c->normalAOV.as<f4>();
+    for (int i = 0; i < 2; i++) {
+        b.histColor[i] = c->svgfHistColor[i].as<h4>(); b.histMoments[i] = c->svgfHistMoments[i].as<h4>(); b.histGeom[i] = c->svgfHistGeom[i].as<h4>();
+        b.color[i] = c->svgfColor[i].as<h4>(); b.var[i] = c->svgfVar[i].as<uint16_t>();
+    }
+    b.sigmaL = OHB_SVGF_SIGMA_L; b.sigmaNormal = OHB_SVGF_SIGMA_NORMAL; b.sigmaDepth = OHB_SVGF_SIGMA_DEPTH;
+    const int scur = 1 - c->svgfCur;
+    launchSvgf(b, c->W, c->H, scur, reset, c->stream, &c->launches, c->timingOn ? &c->timing : nullptr);
+    c->svgfCur = scur;
+}
+int ohb_svgf_dispatch(ohb_ctx* c, uint8_t* beauty, const float* normal, const float* depth, const uint32_t* motion, int reset) {
+    if (!c) return 1;
+    if (!beauty || !normal || !depth || !motion) OHB_FAIL(c, "ohb_svgf_dispatch: null image");
+    if (c->profile != OHB_PROFILE_REALTIME) OHB_FAIL(c, "ohb_svgf_dispatch: needs a context created with OHB_PROFILE_REALTIME");
+    cudaSetDevice(c->device);
+    if (ensureSvgf(c)) return 1;
+    size_t npx = size_t(c->W) * c->H;
+    CU(c, cudaMemcpyAsync(c->ldr.p, beauty, npx * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->normalAOV.p, normal, npx * 16, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->depthAOV.p, depth, npx * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->motionAOV.p, motion, npx * 4, cudaMemcpyHostToDevice, c->stream));
+    runSvgf(c, reset != 0);
+    CU(c, cudaMemcpyAsync(beauty, c->ldr.p, npx * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaGetLastError());
+    return 0;
+}
+int ohb_read_denoise_state(ohb_ctx* c, uint16_t* color, uint16_t* moments, uint16_t* geom, uint32_t* motion, float* depth) {
+    if (!c) return 1;
+    if (!c->motionAOV.p) OHB_FAIL(c, "ohb_read_denoise_state: no frame has been rendered with OHB_DENOISE_ATROUS");
+    cudaSetDevice(c->device);
+    size_t n = size_t(c->W) * c->H; int k = c->svgfCur;
+    if (color) CU(c, cudaMemcpyAsync(color, c->svgfHistColor[k].p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (moments) CU(c, cudaMemcpyAsync(moments, c->svgfHistMoments[k].p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (geom) CU(c, cudaMemcpyAsync(geom, c->svgfHistGeom[k].p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (motion) CU(c, cudaMemcpyAsync(motion, c->motionAOV.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (depth) CU(c, cudaMemcpyAsync(depth, c->depthAOV.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
 int ohb_set_sample_dump(ohb_ctx* c, float* host, size_t cap) { if (!c) return 1; c->dumpHost = host; c->dumpCapacity = host ? cap : 0; return 0; }
 
 int ohb_get_counters(ohb_ctx* c, ohb_counters* out) {

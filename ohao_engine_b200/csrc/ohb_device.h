@@ -9,7 +9,8 @@
 namespace ohb {
 
 // CUDA-event timing of kernel categories on the launching stream (bench.py roofline line):
-// 0 = closest-hit traversal, 1 = bounce (raygen body), 2 = any-hit traversal, 3 = film, 4 = surface (hit/miss shaders), 5-7 spare.
+// 0 = closest-hit traversal, 1 = bounce (raygen body), 2 = any-hit traversal, 3 = film, 4 = surface (hit/miss shaders),
+// 5 = realtime per-pixel pass, 6 = SVGF denoiser, 7 spare.
 struct TimingHooks {
     struct Span { cudaEvent_t a, b; int cat; };
     std::vector<Span> spans; size_t used = 0; 
@@ -38,6 +39,13 @@ void launchOfflineBatch(const SceneDev& sc, const FrameParams& fr, PathArrays P,
                         uint32_t* work, int numSMs, cudaStream_t st, uint64_t* launches, TimingHooks* th);
 void launchRealtimeFrame(const SceneDev& sc, const FrameParams& fr, PathArrays P, const RTImagesDev& im, uint32_t* ldr, float* denoisedDump,
                          uint32_t* work, int numSMs, cudaStream_t st, uint64_t* launches, TimingHooks* th);
+// images of the SVGF denoiser: persistent ping-ponged history (colour, moments, geometry) + per-frame scratch
+struct SvgfBuffers {
+    uint32_t* beauty; const uint32_t* motion; const float* depth; const f4* normal;
+    h4* histColor[2]; h4* histMoments[2]; h4* histGeom[2]; h4* color[2]; uint16_t* var[2];
+    float sigmaL, sigmaNormal, sigmaDepth;
+};
+void launchSvgf(const SvgfBuffers& b, uint32_t W, uint32_t H, int cur, bool reset, cudaStream_t st, uint64_t* launches, TimingHooks* th);
 void launchResolve(f4* accum, uint32_t* ldr, uint32_t n, int sumMode, cudaStream_t st, uint64_t* launches);
 void launchTraceBatch(const SceneDev& sc, const ohb_ray* rays, uint32_t n, ohb_hit* hits, uint8_t* occ, uint32_t* work, int numSMs, cudaStream_t st, uint64_t* launches);
 

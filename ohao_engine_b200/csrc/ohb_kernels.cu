@@ -505,6 +505,42 @@ void launchRealtimeFrame(const SceneDev& sc, const FrameParams& fr, PathArrays P
     *launches += 2;
 }
 
+// =============================================================================================
+// SVGF denoiser (DenoiseMode::Atrous): AtrousDenoiser::dispatch (atrous_denoise.cpp:392-537).  32x8 pixel blocks:
+// a warp covers one row segment, so the 25 taps of neighbouring lanes share L1 lines.
+// =============================================================================================
+__global__ void __launch_bounds__(256) k_svgf_temporal(SvgfTemporalArgs a) {
+    int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x < a.W && y < a.H) svgfTemporalPixel(a, x, y);
+}
+__global__ void __launch_bounds__(256) k_svgf_atrous(SvgfAtrousArgs a) {
+    int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x < a.W && y < a.H) svgfAtrousPixel(a, x, y);
+}
+void launchSvgf(const SvgfBuffers& b, uint32_t W, uint32_t H, int cur, bool reset, cudaStream_t st, uint64_t* launches, TimingHooks* th) {
+    const int prev = 1 - cur;
+    dim3 grid((W + 31u) / 32u, (H + 7u) / 8u);
+    if (th) th->begin(6, st);
+    SvgfTemporalArgs t{};
+    t.beauty = b.beauty; t.motion = b.motion; t.depth = b.depth; t.normal = b.normal;
+    t.prevColor = b.histColor[prev]; t.prevMoments = b.histMoments[prev]; t.prevGeom = b.histGeom[prev];
+    t.outColor = b.color[0]; t.outMoments = b.histMoments[cur]; t.outVariance = b.var[0]; t.outGeom = b.histGeom[cur];
+    t.W = int(W); t.H = int(H); t.reset = reset ? 1 : 0;
+    k_svgf_temporal<<<grid, 256, 0, st>>>(t);
+    // ping-pong schedule of atrous_denoise.cpp:477-486: iteration 0 writes next frame's colour history
+    h4* A = b.color[0]; h4* B = b.color[1]; h4* HC = b.histColor[cur];
+    h4* inC[OHB_SVGF_ITERATIONS] = {A, HC, B, A, B}; h4* outC[OHB_SVGF_ITERATIONS] = {HC, B, A, B, A};
+    for (int it = 0; it < OHB_SVGF_ITERATIONS; it++) {
+        SvgfAtrousArgs a{};
+        a.inColor = inC[it]; a.outColor16 = outC[it]; a.normal = b.normal; a.depth = b.depth; a.inVar = b.var[it & 1]; a.outVar = b.var[1 - (it & 1)]; a.outLDR = b.beauty;
+        a.W = int(W); a.H = int(H); a.stepSize = 1 << it; a.isFinal = it == OHB_SVGF_ITERATIONS - 1;
+        a.sigmaL = b.sigmaL; a.sigmaNormal = b.sigmaNormal; a.sigmaDepth = b.sigmaDepth;
+        k_svgf_atrous<<<grid, 256, 0, st>>>(a);
+    }
+    if (th) th->end(6, st);
+    *launches += 1 + OHB_SVGF_ITERATIONS;
+}
+
 void launchResolve(f4* accum, uint32_t* ldr, uint32_t n, int sumMode, cudaStream_t st, uint64_t* launches) {
     k_resolve<<<gridFor(n, 256), 256, 0, st>>>(accum, ldr, n, sumMode); (*launches)++;
 }

@@ -15,6 +15,7 @@
 // images, Q2) and the a-trous pass runs after the whole frame has accumulated.  NRD/DLSS AOVs are not produced.
 #pragma once
 #include "ohb_integrator.h"
+#include "ohb_svgf.h"
 
 namespace ohb {
 
@@ -295,6 +296,7 @@ struct RTImagesDev {
     const f4* surfPrev; f4* surfCurr; const f4* shadPrev; f4* shadCurr;
     const f4* res0Prev; const f4* res1Prev; const f4* res2Prev; f4* res0Curr; f4* res1Curr; f4* res2Curr;
     float* radianceDump; float* giDump;     // optional parity dumps (W*H*4 floats)
+    uint32_t* motionAOV; float* depthAOV;   // RG16F motion vectors / R32F linear view Z for the SVGF denoiser (null when it is off)
     unsigned long long* counters;
 };
 OHB_HD bool prevPixelOf(const FrameParams& fr, f3 p, int& qx, int& qy) {
@@ -443,6 +445,7 @@ OHB_HD void pixelRT(const SceneDev& sc, const FrameParams& fr, const PathArrays&
         radiance += giDiffuse;
     }
     if (im.giDump) { float* o = im.giDump + pi * 4u; o[0] = giDiffuse.x; o[1] = giDiffuse.y; o[2] = giDiffuse.z; o[3] = 1.0f; }
+    if (im.motionAOV) svgfGuides(fr.currViewProj, fr.prevViewProj, fr.viewRow2, fr.W, fr.H, fr.frameIdx, hit, firstHitPos, im.motionAOV[pi], im.depthAOV[pi]);
     im.surfCurr[pi] = hit ? mk4(firstHitPos, firstHitDist) : mk4(0.0f, 0.0f, 0.0f, -1.0f);
     im.shadCurr[pi] = hit ? mk4(firstHitNormal, firstHitRoughness) : mk4(0.0f, 0.0f, 1.0f, -1.0f);
 

@@ -534,6 +534,7 @@ static void tonemapStore(V3 acc, uint8_t* px) {   // pt_raygen_offline.rgen:1339
 }
 
 #include "oracle_realtime.inl"
+#include "oracle_svgf.inl"
 
 }  // namespace orc
 
@@ -809,6 +810,32 @@ int orc_render_realtime(void* h, orc_rt_args* a) {
     a->counters.samples = total.samples; a->counters.closest_rays = total.closest; a->counters.shadow_rays = total.shadow; a->counters.closest_hits = total.hits;
     return 0;
 }
+
+// Guide AOVs of the SVGF denoiser from this frame's surface-history plane (firstHitPos, firstHitDist).
+// currViewProj = inverse(invProj) * inverse(invView) and viewMat = inverse(invView), as the shader derives them.
+void orc_svgf_guides(const float* surf, uint32_t W, uint32_t H, const float* view16, const float* proj16, const float* prevViewProj16, uint32_t frameIdx,
+                     uint32_t* motion, float* depth) {
+    M4 invView = inverse(toM4(view16)), invProj = inverse(toM4(proj16));
+    M4 viewMat = inverse(invView), currViewProj = mulm(inverse(invProj), viewMat), prevVP = toM4(prevViewProj16);
+    for (uint32_t y = 0; y < H; y++) for (uint32_t x = 0; x < W; x++) {
+        size_t pi = size_t(y) * W + x;
+        svgfGuidesPixel(currViewProj, prevVP, viewMat, W, H, frameIdx, V4{surf[pi * 4], surf[pi * 4 + 1], surf[pi * 4 + 2], surf[pi * 4 + 3]}, motion[pi], depth[pi]);
+    }
+}
+struct orc_svgf_args {
+    int32_t width, height, reset, nthreads;
+    float sigma_l, sigma_normal, sigma_depth, _pad;
+    uint8_t* beauty; const uint32_t* motion; const float* depth; const float* normal;
+    const uint16_t* prev_color; const uint16_t* prev_moments; const uint16_t* prev_geom;
+    uint16_t* cur_color; uint16_t* cur_moments; uint16_t* cur_geom;
+};
+int orc_svgf_dispatch(orc_svgf_args* a) {
+    SvgfImages im{a->width, a->height, a->beauty, a->motion, a->depth, a->normal, a->prev_color, a->prev_moments, a->prev_geom, a->cur_color, a->cur_moments, a->cur_geom};
+    svgfDispatch(im, a->reset, a->sigma_l, a->sigma_normal, a->sigma_depth, a->nthreads);
+    return 0;
+}
+uint16_t orc_f2h(float f) { return halfBits(f); }
+float orc_h2f(uint16_t h) { return halfToFloat(h); }
 
 void orc_tonemap(const float* accum, uint32_t npix, uint8_t* ldr) {
     for (uint32_t i = 0; i < npix; i++) tonemapStore(V3{accum[4 * i], accum[4 * i + 1], accum[4 * i + 2]}, ldr + 4 * size_t(i));

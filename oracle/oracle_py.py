@@ -17,7 +17,7 @@ _LIB = None
 class Settings(C.Structure):   # ohb_settings (include/ohao_b200.h)
     _fields_ = [("profile", C.c_uint32), ("max_bounces", C.c_uint32), ("flags", C.c_uint32), ("firefly_clamp_lum", C.c_float),
                 ("sampler_type", C.c_uint32), ("anisotropy_strength", C.c_float), ("anisotropy_rotation", C.c_float),
-                ("subsurface_strength", C.c_float), ("samples_per_frame", C.c_uint32), ("_pad", C.c_uint32 * 3)]
+                ("subsurface_strength", C.c_float), ("samples_per_frame", C.c_uint32), ("denoise_mode", C.c_uint32), ("_pad", C.c_uint32 * 2)]
 
 
 class Counters(C.Structure):   # ohb_counters
@@ -59,10 +59,59 @@ class RTArgs(C.Structure):
                 ("nthreads", C.c_int32), ("counters", Counters)]
 
 
+class SvgfArgs(C.Structure):   # orc_svgf_args (oracle.cpp) == emul_svgf_args (tests/emul/emul.cpp)
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("reset", C.c_int32), ("nthreads", C.c_int32),
+                ("sigma_l", C.c_float), ("sigma_normal", C.c_float), ("sigma_depth", C.c_float), ("_pad", C.c_float),
+                ("beauty", C.c_void_p), ("motion", C.c_void_p), ("depth", C.c_void_p), ("normal", C.c_void_p),
+                ("prev_color", C.c_void_p), ("prev_moments", C.c_void_p), ("prev_geom", C.c_void_p),
+                ("cur_color", C.c_void_p), ("cur_moments", C.c_void_p), ("cur_geom", C.c_void_p)]
+
+
+SVGF_SIGMAS = (0.4, 0.30, 2.0)   # kSigmaL, kSigmaNormal, kSigmaDepth (atrous_denoise.cpp:38-40)
+
+
+class SvgfState:
+    """Host mirror of AtrousDenoiser's persistent history (atrous_denoise.cpp:79-121): colour, moments, geometry as raw
+    fp16 bits, ping-ponged; `cur` = the set written by the last dispatch."""
+
+    def __init__(self, width, height):
+        self.W, self.H = width, height
+        z = lambda: np.zeros((height, width, 4), np.uint16)
+        self.color = [z(), z()]; self.moments = [z(), z()]; self.geom = [z(), z()]; self.cur = 0
+
+
+def _svgf_dispatch(fn, st: SvgfState, beauty, motion, depth, normal, reset, sigmas=SVGF_SIGMAS, nthreads=None):
+    """Runs one AtrousDenoiser::dispatch through `fn` (the oracle's or the emulator's entry point); returns the denoised RGBA8."""
+    out = np.ascontiguousarray(beauty, np.uint8).copy()
+    motion = np.ascontiguousarray(motion, np.uint32); depth = np.ascontiguousarray(depth, np.float32); normal = np.ascontiguousarray(normal, np.float32)
+    a = SvgfArgs(); a.width, a.height, a.reset, a.nthreads = st.W, st.H, int(bool(reset)), nthreads or (os.cpu_count() or 1)
+    a.sigma_l, a.sigma_normal, a.sigma_depth = sigmas
+    p, c = st.cur, 1 - st.cur
+    a.beauty, a.motion, a.depth, a.normal = _p(out), _p(motion), _p(depth), _p(normal)
+    a.prev_color, a.prev_moments, a.prev_geom = _p(st.color[p]), _p(st.moments[p]), _p(st.geom[p])
+    a.cur_color, a.cur_moments, a.cur_geom = _p(st.color[c]), _p(st.moments[c]), _p(st.geom[c])
+    fn(C.byref(a))
+    st.cur = c
+    return out
+
+
+def svgf_dispatch(st: SvgfState, beauty, motion, depth, normal, reset, sigmas=SVGF_SIGMAS, nthreads=None):
+    return _svgf_dispatch(lib().orc_svgf_dispatch, st, beauty, motion, depth, normal, reset, sigmas, nthreads)
+
+
+def svgf_guides(surf, view, proj, prev_view_proj, frame_index):
+    """(motion RG16F bits packed x | y << 16, linear view Z) of a frame from its surface-history plane."""
+    surf = np.ascontiguousarray(surf, np.float32); H, W = surf.shape[:2]
+    motion = np.zeros((H, W), np.uint32); depth = np.zeros((H, W), np.float32)
+    v = (C.c_float * 16)(*[float(x) for x in view]); pr = (C.c_float * 16)(*[float(x) for x in proj]); pv = (C.c_float * 16)(*[float(x) for x in prev_view_proj])
+    lib().orc_svgf_guides(_p(surf), W, H, v, pr, pv, int(frame_index), _p(motion), _p(depth))
+    return motion, depth
+
+
 def build(force: bool = False) -> str:
     """Compile oracle/liboracle.so (and oracle/_ref when /root/reference exists)."""
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h", ".inc"))]
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h", ".inc", ".inl"))]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     if os.path.isdir("/root/reference/ohao"):
@@ -79,6 +128,10 @@ def lib() -> C.CDLL:
         _LIB.orc_scene_destroy.argtypes = [C.c_void_p]
         _LIB.orc_render_offline.argtypes = [C.c_void_p, C.POINTER(RenderArgs)]
         _LIB.orc_render_realtime.argtypes = [C.c_void_p, C.POINTER(RTArgs)]
+        _LIB.orc_svgf_dispatch.argtypes = [C.POINTER(SvgfArgs)]
+        _LIB.orc_svgf_guides.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_uint32, C.c_void_p, C.c_void_p]
+        _LIB.orc_f2h.restype = C.c_uint16; _LIB.orc_f2h.argtypes = [C.c_float]
+        _LIB.orc_h2f.restype = C.c_float; _LIB.orc_h2f.argtypes = [C.c_uint16]
         _LIB.orc_sampler_1d.restype = C.c_float
         _LIB.orc_sampler_1d.argtypes = [C.c_uint32] * 5
         _LIB.orc_sobol_raw.restype = C.c_float
@@ -198,11 +251,12 @@ class OracleScene:
         return dict(accum=accum, ldr=ldr, albedo=alb, normal=nrm, samples=sd,
                     counters=dict(samples=c.samples, closest_rays=c.closest_rays, shadow_rays=c.shadow_rays, closest_hits=c.closest_hits))
 
-    def render_realtime(self, st: "RealtimeState", view, proj, settings=None, view_changed=False, nthreads=None, dumps=False):
-        """One realtime frame; flips the ping-pong buffers of `st` and advances its counters like PathTracer::render."""
+    def render_realtime(self, st: "RealtimeState", view, proj, settings=None, view_changed=False, nthreads=None, dumps=False, fresh=False):
+        """One realtime frame; flips the ping-pong buffers of `st` and advances its counters like PathTracer::render.
+        fresh = denoiseWantsFreshSample (path_tracer_render.cpp:707-712): the raygen sees historyFrameCount = 0."""
         a = RTArgs()
         a.view[:] = [float(x) for x in view]; a.proj[:] = [float(x) for x in proj]; a.prev_view_proj[:] = [float(x) for x in st.prev_view_proj]
-        a.width, a.height, a.frame_index, a.history_count, a.view_changed = st.W, st.H, st.frame_index, st.history, int(view_changed)
+        a.width, a.height, a.frame_index, a.history_count, a.view_changed = st.W, st.H, st.frame_index, (0 if fresh else st.history), int(view_changed)
         a.settings = settings or realtime_settings()
         p, c = st.cur, 1 - st.cur
         a.accum_prev, a.accum_curr = _p(st.accum[p]), _p(st.accum[c]); a.surf_prev, a.surf_curr = _p(st.surf[p]), _p(st.surf[c])

@@ -158,6 +158,45 @@ void* emul_scene_create(const emul_scene_desc* d) {
 void emul_scene_destroy(void* h) { delete (EmulScene*)h; }
 void emul_accel_stats(void* h, uint32_t* numNodes, float* sah) { EmulScene* s = (EmulScene*)h; *numNodes = s->numNodes; *sah = s->sah; }
 uint32_t emul_accel_levels(void* h) { return ((EmulScene*)h)->levels; }
+// ---- SVGF denoiser (ohb_svgf.h) driven like launchSvgf (ohb_kernels.cu) ---------------------------------------
+struct emul_svgf_args {
+    int32_t width, height, reset, nthreads;
+    float sigma_l, sigma_normal, sigma_depth, _pad;
+    uint32_t* beauty; const uint32_t* motion; const float* depth; const f4* normal;
+    const h4* prev_color; const h4* prev_moments; const h4* prev_geom;
+    h4* cur_color; h4* cur_moments; h4* cur_geom;
+};
+int emul_svgf_dispatch(emul_svgf_args* a) {
+    const int W = a->width, H = a->height; const size_t n = size_t(W) * H;
+    std::vector<h4> colorA(n), colorB(n); std::vector<uint16_t> varA(n), varB(n);
+    SvgfTemporalArgs t{};
+    t.beauty = a->beauty; t.motion = a->motion; t.depth = a->depth; t.normal = a->normal;
+    t.prevColor = a->prev_color; t.prevMoments = a->prev_moments; t.prevGeom = a->prev_geom;
+    t.outColor = colorA.data(); t.outMoments = a->cur_moments; t.outVariance = varA.data(); t.outGeom = a->cur_geom;
+    t.W = W; t.H = H; t.reset = a->reset;
+    for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) svgfTemporalPixel(t, x, y);
+    h4* A = colorA.data(); h4* B = colorB.data(); h4* HC = a->cur_color;
+    h4* inC[OHB_SVGF_ITERATIONS] = {A, HC, B, A, B}; h4* outC[OHB_SVGF_ITERATIONS] = {HC, B, A, B, A};
+    uint16_t* var[2] = {varA.data(), varB.data()};
+    for (int it = 0; it < OHB_SVGF_ITERATIONS; it++) {
+        SvgfAtrousArgs k{};
+        k.inColor = inC[it]; k.outColor16 = outC[it]; k.normal = a->normal; k.depth = a->depth; k.inVar = var[it & 1]; k.outVar = var[1 - (it & 1)]; k.outLDR = a->beauty;
+        k.W = W; k.H = H; k.stepSize = 1 << it; k.isFinal = it == OHB_SVGF_ITERATIONS - 1; k.sigmaL = a->sigma_l; k.sigmaNormal = a->sigma_normal; k.sigmaDepth = a->sigma_depth;
+        for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) svgfAtrousPixel(k, x, y);
+    }
+    return 0;
+}
+// guide AOVs as k_rt_pixel writes them: proj * view of this frame, row 2 of view
+void emul_svgf_guides(const float* surf, uint32_t W, uint32_t H, const float* view, const float* proj, const float* prevViewProj, uint32_t frameIdx, uint32_t* motion, float* depth) {
+    float currVP[16], row2[4] = {view[2], view[6], view[10], view[14]};
+    for (int col = 0; col < 4; col++) for (int row = 0; row < 4; row++) { float acc = 0.0f; for (int k = 0; k < 4; k++) acc += proj[k * 4 + row] * view[col * 4 + k]; currVP[col * 4 + row] = acc; }
+    for (size_t pi = 0; pi < size_t(W) * H; pi++) {
+        bool hit = surf[pi * 4 + 3] > 0.0f;
+        svgfGuides(currVP, prevViewProj, row2, W, H, frameIdx, hit, hit ? mk3(surf[pi * 4], surf[pi * 4 + 1], surf[pi * 4 + 2]) : mk3(0.0f), motion[pi], depth[pi]);
+    }
+}
+uint16_t emul_f2h(float f) { return f2h(f); }
+float emul_h2f(uint16_t h) { return h2f(h); }
 void emul_trav_stats(unsigned long long* nodes, unsigned long long* tris, int reset) { *nodes = g_statNodes; *tris = g_statTris; if (reset) { g_statNodes = 0; g_statTris = 0; } }
 void emul_set_warp_noise(unsigned on) { g_emulWarpNoise = on; g_emulWarpState = 12345u; }
 

@@ -43,6 +43,10 @@ def lib():
         _LIB.emul_accel_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
         _LIB.emul_accel_levels.argtypes = [C.c_void_p]; _LIB.emul_accel_levels.restype = C.c_uint32
         _LIB.emul_set_warp_noise.argtypes = [C.c_uint]
+        _LIB.emul_svgf_dispatch.argtypes = [C.POINTER(O.SvgfArgs)]
+        _LIB.emul_svgf_guides.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_uint32, C.c_void_p, C.c_void_p]
+        _LIB.emul_f2h.restype = C.c_uint16; _LIB.emul_f2h.argtypes = [C.c_float]
+        _LIB.emul_h2f.restype = C.c_float; _LIB.emul_h2f.argtypes = [C.c_uint16]
         _LIB.emul_trav_stats.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.c_int]
     return _LIB
 
@@ -90,11 +94,11 @@ class EmulScene:
         u = np.ascontiguousarray(u12, np.float32); n = len(u); dp = np.zeros((n, 4), np.float32); pd = np.zeros(n, np.float32)
         lib().emul_env_sample_batch(self.h, _p(u), n, _p(dp), _p(pd)); return dp, pd
 
-    def render_realtime(self, st, view, proj, settings=None, view_changed=False, dumps=False):
+    def render_realtime(self, st, view, proj, settings=None, view_changed=False, dumps=False, fresh=False):
         """Same contract as OracleScene.render_realtime (st = oracle_py.RealtimeState)."""
         a = RTArgs()
         a.view[:] = [float(x) for x in view]; a.proj[:] = [float(x) for x in proj]; a.prev_view_proj[:] = [float(x) for x in st.prev_view_proj]
-        a.width, a.height, a.frame_index, a.history_count, a.view_changed = st.W, st.H, st.frame_index, st.history, int(view_changed)
+        a.width, a.height, a.frame_index, a.history_count, a.view_changed = st.W, st.H, st.frame_index, (0 if fresh else st.history), int(view_changed)
         a.settings = settings or O.realtime_settings()
         p, c = st.cur, 1 - st.cur
         a.accum_prev, a.accum_curr = _p(st.accum[p]), _p(st.accum[c]); a.surf_prev, a.surf_curr = _p(st.surf[p]), _p(st.surf[c])
@@ -127,6 +131,19 @@ class EmulScene:
         c = a.counters
         return dict(accum=accum, ldr=ldr, albedo=alb, normal=nrm, samples=sd,
                     counters=dict(samples=c[0], closest_rays=c[1], shadow_rays=c[2], closest_hits=c[3]))
+
+
+def svgf_dispatch(st, beauty, motion, depth, normal, reset, sigmas=O.SVGF_SIGMAS):
+    """One AtrousDenoiser::dispatch through the host build of ohb_svgf.h (st = oracle_py.SvgfState)."""
+    return O._svgf_dispatch(lib().emul_svgf_dispatch, st, beauty, motion, depth, normal, reset, sigmas, 1)
+
+
+def svgf_guides(surf, view, proj, prev_view_proj, frame_index):
+    surf = np.ascontiguousarray(surf, np.float32); H, W = surf.shape[:2]
+    motion = np.zeros((H, W), np.uint32); depth = np.zeros((H, W), np.float32)
+    v = (C.c_float * 16)(*[float(x) for x in view]); pr = (C.c_float * 16)(*[float(x) for x in proj]); pv = (C.c_float * 16)(*[float(x) for x in prev_view_proj])
+    lib().emul_svgf_guides(_p(surf), W, H, v, pr, pv, int(frame_index), _p(motion), _p(depth))
+    return motion, depth
 
 
 def set_warp_noise(on: bool):
