@@ -184,7 +184,13 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner to fd 1 while the communicator is created; keep stdout to the one JSON line
+        sys.stdout.flush(); saved = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+        finally:
+            os.dup2(saved, 1); os.close(saved)
 
     from ohao_engine_b200 import binding as B
     ps, cam, desc = make_workload(args.workload)

@@ -53,7 +53,7 @@ int main(int argc, char** argv) {
     auto& camera = renderer.getCamera();
     camera.setPosition({0.0f, 0.0f, 13.0f}); camera.setFov(38.0f); camera.setRotation(0.0f, -90.0f);
     renderer.setRenderMode(realtime ? RenderMode::RTRealtime : RenderMode::RTOffline);
-    renderer.setDenoiseMode(realtime ? DenoiseMode::Atrous : DenoiseMode::None);
+    renderer.setDenoiseMode(denoiseFlag(argc, argv, realtime ? DenoiseMode::Atrous : DenoiseMode::None));   // Atrous = the SVGF denoiser (realtime profile)
     renderer.setRenderSeed(uint32_t(flagValue(argc, argv, "seed", 0)));
     if (!renderer.updateSceneBuffers()) { std::cerr << "FATAL: scene upload failed\n"; return 1; }
 

@@ -228,10 +228,13 @@ inline PackedScene packScene(Scene& scene, bool haveEnv, float envIntensity) {
 // ---- settings ------------------------------------------------------------------------------------------------------
 enum class RTRenderProfile { Offline = 0, Realtime = 1 };
 enum class RenderMode { RTOffline, RTRealtime };
-enum class DenoiseMode { None, OIDN, Atrous };      // only None / the realtime in-shader a-trous exist on this path (OIDN is a §8f "next" row)
+// denoise/denoise_types.hpp:13-19, same values.  Built on this path: None and Atrous (the SVGF denoiser, realtime profile);
+// OIDN / NRD / DLSS-RR are third-party libraries (OIDN is the open §8f "next" row) and are refused by ohb_set_settings.
+enum class DenoiseMode : uint32_t { None = 0, OIDN = 1, NRD = 3, Atrous = 4, DLSSRR = 5 };
 struct RTRenderSettings {                            // rt_settings.hpp:17-35
     RTRenderProfile profile = RTRenderProfile::Offline; uint32_t maxBounces = 4; bool enableAuxiliaryAOVs = true, enableInternalDenoise = false, enableFireflyClamp = false;
     float fireflyClampLuminance = 0.0f, anisotropyStrength = 0.0f, anisotropyRotation = 0.0f, subsurfaceStrength = 0.0f; uint32_t samplesPerFrame = 1;
+    DenoiseMode denoiseMode = DenoiseMode::None;
 };
 inline constexpr RTRenderSettings kOfflineRTSettings{RTRenderProfile::Offline, 4, true, false, false, 0.0f, 0, 0, 0, 1};
 inline constexpr RTRenderSettings kRealtimeRTSettings{RTRenderProfile::Realtime, 2, true, true, true, 10.0f, 0, 0, 0, 1};
@@ -241,6 +244,7 @@ inline ohb_settings toOhb(const RTRenderSettings& s) {
     o.firefly_clamp_lum = s.fireflyClampLuminance; o.sampler_type = OHB_SAMPLER_SOBOL;     // both profiles run Sobol (Q3)
     o.anisotropy_strength = s.anisotropyStrength; o.anisotropy_rotation = s.anisotropyRotation; o.subsurface_strength = s.subsurfaceStrength;
     o.samples_per_frame = std::min(std::max(s.samplesPerFrame, 1u), 64u);                 // clampSamplesPerFrame
+    o.denoise_mode = uint32_t(s.denoiseMode);
     return o;
 }
 
@@ -293,7 +297,7 @@ public:
     [[nodiscard]] bool initialize() { return true; }                       // the CUDA context is created lazily by ensureRTRenderer, like the reference
     void setScene(Scene* s) { m_scene = s; m_sceneDirty = true; }
     void setRenderMode(RenderMode m) { if (m != m_mode) { m_mode = m; m_rt.reset(); m_sceneDirty = true; } }
-    void setDenoiseMode(DenoiseMode d) { m_denoise = d; }
+    void setDenoiseMode(DenoiseMode d) { m_denoise = d; m_settingsDirty = true; }
     DenoiseMode getDenoiseMode() const { return m_denoise; }
     void setEnvironmentMap(std::vector<float> rgba32f, uint32_t w, uint32_t h) { m_env = std::move(rgba32f); m_envW = w; m_envH = h; m_sceneDirty = true; }
     void setEnvIntensityScale(float s) { m_envIntensity = s; m_lightsDirty = true; }
@@ -324,7 +328,13 @@ public:
     void render(uint32_t nsamples = 1) {
         if (m_sceneDirty && !updateSceneBuffers()) return;
         if (m_lightsDirty && !updateRTLightParams()) return;
-        if (m_settingsDirty) { RTRenderSettings s = m_rt->getDefaultSettings(); s.samplesPerFrame = m_spf; if (m_denoise == DenoiseMode::None) s.enableInternalDenoise = false; m_rt->setRenderSettings(s); m_settingsDirty = false; }
+        if (m_settingsDirty) {
+            RTRenderSettings s = m_rt->getDefaultSettings(); s.samplesPerFrame = m_spf;
+            if (m_denoise == DenoiseMode::None) s.enableInternalDenoise = false;
+            // applyRTRenderSettings (renderer.cpp:482-493): the Atrous override is injected into the tracer's settings (realtime profile only here)
+            if (m_denoise == DenoiseMode::Atrous && m_mode == RenderMode::RTRealtime) s.denoiseMode = DenoiseMode::Atrous;
+            m_rt->setRenderSettings(s); m_settingsDirty = false;
+        }
         m_rt->render(m_camera.getViewMatrix(), m_camera.getProjection(m_w, m_h), nsamples);
     }
     std::span<const uint8_t> getPixelSpan() {                                // RGBA8, top row first; valid immediately (no 3-frame ring lag)
@@ -397,6 +407,23 @@ inline std::string flagString(int argc, char** argv, const char* name, const cha
         std::string a = argv[i];
         if (a == key && i + 1 < argc) return argv[i + 1];
         if (a.rfind(key + "=", 0) == 0) return a.substr(key.size() + 1);
+    }
+    return def;
+}
+// --denoise=<mode> of the reference examples (parseDenoiseMode, denoise/denoise_types.cpp): none | atrous (alias svgf);
+// oidn / nrd / dlssrr parse but are refused by the library (ohb_set_settings) when the renderer applies them.
+inline DenoiseMode denoiseFlag(int argc, char** argv, DenoiseMode def) {
+    const std::string key = "--denoise=";
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        if (a.rfind(key, 0) != 0) continue;
+        std::string v = a.substr(key.size());
+        if (v == "none") return DenoiseMode::None;
+        if (v == "atrous" || v == "svgf") return DenoiseMode::Atrous;
+        if (v == "oidn") return DenoiseMode::OIDN;
+        if (v == "nrd") return DenoiseMode::NRD;
+        if (v == "dlssrr") return DenoiseMode::DLSSRR;
+        std::cerr << "unknown --denoise mode '" << v << "', using the default\n";
     }
     return def;
 }

@@ -58,7 +58,7 @@ int main(int argc, char** argv) {
     }
     renderer.setScene(scene.get());
     renderer.setRenderMode(realtime ? RenderMode::RTRealtime : RenderMode::RTOffline);
-    renderer.setDenoiseMode(realtime ? DenoiseMode::Atrous : DenoiseMode::None);
+    renderer.setDenoiseMode(denoiseFlag(argc, argv, realtime ? DenoiseMode::Atrous : DenoiseMode::None));   // Atrous = the SVGF denoiser (realtime profile)
     if (!renderer.updateSceneBuffers()) { std::cerr << "FATAL: scene upload failed\n"; return 1; }
     const float orbitRadius = mode == "env" ? 8.0f : (mode == "mirror" ? 4.5f : 4.2f), orbitHeight = mode == "env" ? 1.0f : -3.5f;
     const bool write = !hasFlag(argc, argv, "no-write");
