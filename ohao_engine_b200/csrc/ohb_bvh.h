@@ -340,6 +340,15 @@ OHB_HD void emitWideNode(const BuildArrays& b, const WideItem& it, WideItem* out
         int c = child[best];
         fetch(best, b.left[c]); fetch(nc, b.right[c]); nc++;
     }
+    // Free slots left and only leaf-sized subtrees: split the multi-triangle leaves too (largest area x count first).
+    // The slab test of a visit costs the same for 8 slots as for 4, so every extra box is free culling of triangle tests.
+    while (nc < 8) {
+        int best = -1; float bestA = -1.0f;
+        for (int k = 0; k < nc; k++) if (cnt[k] >= 2u && cnt[k] <= OHB_MAX_LEAF) { float a = boxArea(lo[k], hi[k]) * float(cnt[k]); if (a > bestA) { bestA = a; best = k; } }
+        if (best < 0) break;
+        int c = child[best];
+        fetch(best, b.left[c]); fetch(nc, b.right[c]); nc++;
+    }
     // node box = union of the padded child boxes
     f3 nlo = mk3(3.0e38f), nhi = mk3(-3.0e38f);
     float leafArea = 0.0f;

@@ -266,7 +266,7 @@ static TraceKnobs traceKnobs() {
     static const TraceKnobs k = []() {
         auto geti = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
         TraceKnobs r; r.minActive = geti("OHB_TRACE_MIN_ACTIVE", 20); r.postponeDen = geti("OHB_POSTPONE_DEN", OHB_POSTPONE_DEN_DEFAULT);
-        if (r.postponeDen < 2) r.postponeDen = 2;      // 0 or 1 would postpone every triangle forever
+        if (r.postponeDen == 1) r.postponeDen = 2;      // 1 would postpone every triangle forever; 0 = never postpone
         return r;
     }();
     return k;

@@ -227,7 +227,7 @@ OHB_HD uint32_t intersectWideNode(const Trav& t, const u4* np, float thi, uint32
 
 // Runs until the query is finished (returns true) or fewer than `minActive` lanes of the warp are still
 // traversing (returns false; call again later).  ANY = TerminateOnFirstHit.  Lanes postpone their remaining leaf
-// triangles when fewer than 1/postponeDen of the lanes that entered the triangle loop are still in it (>= 2).
+// triangles when fewer than 1/postponeDen of the lanes that entered the triangle loop are still in it (>= 2; 0 = never).
 // (A variant that parked triangle groups and tested them in warp-voted steps to raise the SIMT efficiency of the
 // triangle test was measured 17 % SLOWER on both workloads, profiles/r1e_sweep.txt: a closest hit that is found
 // late stops culling the nodes behind it.  Triangles are therefore tested right after the node visit.)
@@ -250,9 +250,9 @@ OHB_HD bool travRun(Trav& t, TravStackEntry* stack, const SceneDev& s, int minAc
             t.Gt = t.G; t.G.x = 0u; t.G.y = 0u;            // a postponed triangle group came off the stack
         }
         // leaf triangles; when most lanes of the warp have none left, the rest postpone theirs (Ylitie et al. §4.3)
-        const int entered = OHB_WARP_ACTIVE();
+        const int entered = postponeDen ? OHB_WARP_ACTIVE() : 0;
         while (t.Gt.y) {
-            if (OHB_WARP_ACTIVE() * postponeDen < entered && t.sp < OHB_POSTPONE_SLOTS) { stack[t.sp++] = t.Gt; t.Gt.y = 0u; break; }
+            if (postponeDen && OHB_WARP_ACTIVE() * postponeDen < entered && t.sp < OHB_POSTPONE_SLOTS) { stack[t.sp++] = t.Gt; t.Gt.y = 0u; break; }
             const uint32_t k = bfind32(t.Gt.y);
             t.Gt.y &= ~(1u << k);
             const f4* tp = s.tris + size_t(t.Gt.x + k) * 3u;
