@@ -299,6 +299,10 @@ def main():
                  "rt_pixel": (W * H * args.steps, 352 * spp + 416),     # per pixel: N finished path records + 10 history planes in / 6 out
                  "svgf": (W * H * args.steps, 278)}                      # per pixel: temporal pass 78 B + 5 a-trous iterations x 40 B
         kern = {}
+        fused = tim.get("surface", {}).get("launches", 1) == 0 and not realtime
+        if fused:
+            # k_shade (surface + bounce fused, payload in registers): 248 + 304 - 2 x 64 B of payload traffic; reported as "shade"
+            units["shade"] = (cnt["closest_rays"], 424); tim["shade"] = tim.pop("bounce")
         for k, x in tim.items():
             if x["launches"] == 0: continue
             nunits, bpu = units[k]

@@ -385,22 +385,29 @@ OHB_HD void raygenPath(const FrameParams& fr, const PathArrays& P, uint32_t p) {
     P.rad[p] = mk4(0, 0, 0, 0);
 }
 
-// k_surface: the closest-hit / miss shader of path p's last query -> payload record.
-// Returns true for a hit (the caller sorts hits to the front of queueSorted, misses to the back).
-OHB_HD bool surfacePath(const SceneDev& sc, const FrameParams& fr, const PathArrays& P, uint32_t p) {
+// The closest-hit / miss shader of path p's last query -> the four payload quads.  Returns true for a hit.
+OHB_HD bool surfaceShade(const SceneDev& sc, const FrameParams& fr, const PathArrays& P, uint32_t p, f4& q0, f4& q1, f4& q2, f4& q3) {
     f3 o = xyz(P.rayO[p]), d = xyz(P.rayD[p]);
     ohb_hit h = P.hit[p];
     Payload pl;
     if (h.prim == OHB_MISS) {
         missShader(sc, fr, d, pl);
-        P.pay0[p] = mk4(pl.color, -1.0f); P.pay1[p] = mk4(pl.envPdf, 0.0f, 0.0f, 0.0f);
+        q0 = mk4(pl.color, -1.0f); q1 = mk4(pl.envPdf, 0.0f, 0.0f, 0.0f); q2 = q3 = mk4(0.0f, 0.0f, 0.0f, 0.0f);
         return false;
-    } else {
-        closestHitShader(sc, o, d, h, pl);
-        P.pay0[p] = mk4(pl.hitPos, pl.hitDist); P.pay1[p] = mk4(pl.hitNormal, pl.attenuation.x);
-        P.pay2[p] = mk4(pl.hitAlbedo, pl.attenuation.y); P.pay3[p] = mk4(pl.color, pl.attenuation.z);
-        return true;
     }
+    closestHitShader(sc, o, d, h, pl);
+    q0 = mk4(pl.hitPos, pl.hitDist); q1 = mk4(pl.hitNormal, pl.attenuation.x);
+    q2 = mk4(pl.hitAlbedo, pl.attenuation.y); q3 = mk4(pl.color, pl.attenuation.z);
+    return true;
+}
+// k_surface: payload record of path p to memory.
+// Returns true for a hit (the caller sorts hits to the front of queueSorted, misses to the back).
+OHB_HD bool surfacePath(const SceneDev& sc, const FrameParams& fr, const PathArrays& P, uint32_t p) {
+    f4 q0, q1, q2, q3;
+    const bool hit = surfaceShade(sc, fr, P, p, q0, q1, q2, q3);
+    P.pay0[p] = q0; P.pay1[p] = q1;
+    if (hit) { P.pay2[p] = q2; P.pay3[p] = q3; }
+    return hit;
 }
 
 // reflect + roughness jitter + below-horizon re-sample: :573-592 (B set-up) == :843-862 == :1151-1170
@@ -414,18 +421,17 @@ OHB_HD f3 sampleSpecDir(ShadeCtx& cx, f3 d, f3 N, float rough) {
     return refl;
 }
 
-// k_bounce: the raygen's per-bounce body for the path of queue entry e, after k_surface.
+// The raygen's per-bounce body for the path of queue entry e, given the payload (q0..q3) of its last query.
 // Returns the path's next queue entry, or OHB_Q_NONE if it traces no further closest-hit ray.
-OHB_HD uint32_t bouncePath(const SceneDev& sc, const FrameParams& fr, const PathArrays& P, uint32_t e) {
+OHB_HD uint32_t bounceBody(const SceneDev& sc, const FrameParams& fr, const PathArrays& P, uint32_t e, f4 q0, f4 q1, f4 q2, f4 q3) {
     const uint32_t p = OHB_Q_PATH(e);
     const bool isMiss = (e & OHB_Q_MISS) != 0u, primary = (e & OHB_Q_PRIMARY) != 0u;
     // every load of the path record is issued here, before the first use
     const u4 m = P.meta[p];
-    const f4 rad4 = P.rad[p], q0 = P.pay0[p], q1 = P.pay1[p], d4 = P.rayD[p];
+    const f4 rad4 = P.rad[p], d4 = P.rayD[p];
     const f4 zero4 = mk4(0.0f, 0.0f, 0.0f, 0.0f);
     const f4 pa4 = (e & OHB_Q_PEND_A) ? P.pendA[p] : zero4, pb4 = (e & OHB_Q_PEND_B) ? P.pendB[p] : zero4;
     const f4 t4 = primary ? mk4(1.0f, 1.0f, 1.0f, 0.0f) : P.thr[p];
-    const f4 q2 = isMiss ? zero4 : P.pay2[p], q3 = isMiss ? zero4 : P.pay3[p];
     ShadeCtx cx(sc, fr, P);
     cx.path = p; cx.state = m.w;
     uint32_t px = m.x & 0xFFFFu, py = m.x >> 16;
@@ -547,10 +553,20 @@ OHB_HD uint32_t bouncePath(const SceneDev& sc, const FrameParams& fr, const Path
     P.rayO[p] = mk4(nextO, 0.0f); P.rayD[p] = mk4(nextD, 0.0f);
     return p | ((keep & OHB_ST_PEND_A) ? OHB_Q_PEND_A : 0u) | ((keep & OHB_ST_PEND_B) ? OHB_Q_PEND_B : 0u);
 }
-// Both shading stages back to back (host emulator / single-kernel fallback for tests).
+// k_bounce: per-bounce body after k_surface, payload read back from memory.
+OHB_HD uint32_t bouncePath(const SceneDev& sc, const FrameParams& fr, const PathArrays& P, uint32_t e) {
+    const uint32_t p = OHB_Q_PATH(e);
+    const f4 zero4 = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+    const bool isMiss = (e & OHB_Q_MISS) != 0u;
+    const f4 q0 = P.pay0[p], q1 = P.pay1[p], q2 = isMiss ? zero4 : P.pay2[p], q3 = isMiss ? zero4 : P.pay3[p];
+    return bounceBody(sc, fr, P, e, q0, q1, q2, q3);
+}
+// k_shade: both shading stages in one kernel, the payload stays in registers (no 64-B payload round trip through HBM,
+// no second queue); warps mix hits and misses.
 OHB_HD uint32_t shadePath(const SceneDev& sc, const FrameParams& fr, const PathArrays& P, uint32_t e) {
-    const bool hit = surfacePath(sc, fr, P, OHB_Q_PATH(e));
-    return bouncePath(sc, fr, P, hit ? e : (e | OHB_Q_MISS));
+    f4 q0, q1, q2, q3;
+    const bool hit = surfaceShade(sc, fr, P, OHB_Q_PATH(e), q0, q1, q2, q3);
+    return bounceBody(sc, fr, P, hit ? e : (e | OHB_Q_MISS), q0, q1, q2, q3);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -381,6 +381,20 @@ __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_bounce(SceneDev sc, Fra
         if (e != OHB_Q_NONE) { uint32_t q = alloc_slot(P.countOut); P.queueOut[q] = e; }
     }
 }
+// Fused shading (k_surface + k_bounce in one pass over queueIn, payload in registers: shadePath).  It moves 30 % fewer
+// bytes per path, but it is 5 800 SASS instructions of straight-line code and the shading kernels are instruction-FETCH
+// limited as soon as warps diverge over much of it (ncu stall_no_instruction 11-20 cycles per issue on the textured,
+// env-lit helmet scene, 3-6 on Cornell: profiles/r1q_ncu_shade_*.txt).  Measured (profiles/r1p_sweep.txt): Cornell
+// +56 %, synthetic 2 M +0 %, helmet -24 %.  launchOfflineBatch therefore uses it only when the scene executes neither
+// the texture code nor the env-map code (no env map bound, 1x1 texture layers); OHB_FUSED_SHADE=0/1 forces a choice.
+template <int MINB>
+__global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(SceneDev sc, FrameParams fr, PathArrays P) {
+    const uint32_t n = *P.countIn;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t e = shadePath(sc, fr, P, P.queueIn[i]);
+        if (e != OHB_Q_NONE) { uint32_t q = alloc_slot(P.countOut); P.queueOut[q] = e; }
+    }
+}
 // Between iterations: account the rays just traced, clear the queues that are about to be refilled.
 __global__ void k_advance(PathArrays P, uint32_t* work, int afterRaygen) {
     if (blockIdx.x || threadIdx.x) return;
@@ -419,18 +433,26 @@ void launchOfflineBatch(const SceneDev& sc, const FrameParams& fr, PathArrays P,
     unsigned shadeGrid = unsigned(numSMs) * 8u;
     uint32_t iters = 1u + 2u * fr.maxBounces;
     static const int bounceOcc = []() { const char* e = getenv("OHB_BOUNCE_OCC"); return e ? atoi(e) : 8; }();
+    static const int fusedKnob = []() { const char* e = getenv("OHB_FUSED_SHADE"); return e ? atoi(e) : -1; }();   // -1 = by scene, see k_shade
+    const bool fusedShade = fusedKnob >= 0 ? fusedKnob != 0 : (sc.env == nullptr && sc.texW <= 1u && sc.texH <= 1u);
     for (uint32_t it = 0; it < iters; it++) {
         if (th) th->begin(0, st);
         launchTraceClosest(traceGrid, sc, P, work, st);
         if (th) th->end(0, st);
-        if (th) th->begin(4, st);
-        k_surface<<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P);
-        if (th) th->end(4, st);
-        if (th) th->begin(1, st);
-        if (bounceOcc >= 8)      k_bounce<8><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P);
-        else if (bounceOcc >= 6) k_bounce<6><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P);
-        else                     k_bounce<1><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P);
-        if (th) th->end(1, st);
+        if (fusedShade) {
+            if (th) th->begin(1, st);
+            if (bounceOcc >= 8) k_shade<8><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P); else k_shade<6><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P);
+            if (th) th->end(1, st);
+        } else {
+            if (th) th->begin(4, st);
+            k_surface<<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P);
+            if (th) th->end(4, st);
+            if (th) th->begin(1, st);
+            if (bounceOcc >= 8)      k_bounce<8><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P);
+            else if (bounceOcc >= 6) k_bounce<6><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P);
+            else                     k_bounce<1><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P);
+            if (th) th->end(1, st);
+        }
         if (th) th->begin(2, st);
         launchTraceShadow(traceGrid, sc, P, work + 1, st);
         if (th) th->end(2, st);
