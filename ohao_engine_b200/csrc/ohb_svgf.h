@@ -152,7 +152,9 @@ OHB_HD void svgfAtrousPixel(const SvgfAtrousArgs& a, int px, int py) {
     }
     float centerVar = gW > 0.0f ? gVar / gW : h2f(a.inVar[pi]);
     float sqrtVar = sqrtf(fmaxf(centerVar, 1e-8f));
-    const float denL = sqrtVar * a.sigmaL + 1e-6f, denN = a.sigmaNormal * a.sigmaNormal + 1e-4f, denD = a.sigmaDepth * a.sigmaDepth + 1e-4f;
+    // the three edge-stop denominators are loop invariants: one reciprocal each instead of 75 IEEE divisions per pixel
+    // (x * (1/d) vs x / d differ in the last ulp of the exponent argument, the same class as expf vs libm exp)
+    const float invL = -1.0f / (sqrtVar * a.sigmaL + 1e-6f), invN = -1.0f / (a.sigmaNormal * a.sigmaNormal + 1e-4f), invD = -1.0f / (a.sigmaDepth * a.sigmaDepth + 1e-4f);
     f3 sum = mk3(0.0f); float weightSum = 0.0f, varSum = 0.0f;
     for (int dy = -2; dy <= 2; dy++) for (int dx = -2; dx <= 2; dx++) {
         int x = clampi(px + dx * a.stepSize, 0, a.W - 1), y = clampi(py + dy * a.stepSize, 0, a.H - 1);
@@ -161,9 +163,9 @@ OHB_HD void svgfAtrousPixel(const SvgfAtrousArgs& a, int px, int py) {
         f3 sN = xyz(a.normal[qi]) * 2.0f - mk3(1.0f);
         float sD = a.depth[qi], sVar = h2f(a.inVar[qi]);
         float w = kern[dx + 2] * kern[dy + 2];
-        w *= expf(-fabsf(cL - svgfLuma(sColor)) / denL);
-        w *= expf(-fmaxf(1.0f - dot(cN, sN), 0.0f) / denN);
-        w *= expf(-fabsf(cD - sD) / denD);
+        w *= expf(fabsf(cL - svgfLuma(sColor)) * invL);
+        w *= expf(fmaxf(1.0f - dot(cN, sN), 0.0f) * invN);
+        w *= expf(fabsf(cD - sD) * invD);
         sum += sColor * w; weightSum += w; varSum += w * w * sVar;
     }
     f3 outC = weightSum > 1e-6f ? mk3(sum.x / weightSum, sum.y / weightSum, sum.z / weightSum) : cColor;
