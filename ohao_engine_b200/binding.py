@@ -97,7 +97,7 @@ def load_library() -> C.CDLL:
     """Load libohao_b200.so and bind every ABI symbol.  Raises if the library is missing."""
     global _LIB
     if _LIB is None:
-        path = _build.LIB_PATH
+        path = os.environ.get("OHAO_B200_LIB") or _build.LIB_PATH      # override: A/B runs of two builds of the same ABI
         if not os.path.exists(path):
             raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(the CUDA extension is mandatory, there is no CPU fallback)")

@@ -41,7 +41,15 @@ OHB_HD f3 operator-(f3 a) { return mk3(-a.x, -a.y, -a.z); }
 OHB_HD f3 operator*(f3 a, f3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
 OHB_HD f3 operator*(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
 OHB_HD f3 operator*(float s, f3 a) { return mk3(a.x * s, a.y * s, a.z * s); }
-OHB_HD f3 operator/(f3 a, float s) { float r = 1.0f / s; return mk3(a.x * r, a.y * r, a.z * r); }   // one IEEE reciprocal (<= 1.5 ulp vs 3 divides)
+// vec3 / float with one reciprocal.  Device: MUFU.RCP (1 ulp) instead of the 16-instruction IEEE sequence (code size, see normalize).
+OHB_HD f3 operator/(f3 a, float s) {
+#if defined(__CUDA_ARCH__)
+    float r = __fdividef(1.0f, s);
+#else
+    float r = 1.0f / s;
+#endif
+    return mk3(a.x * r, a.y * r, a.z * r);
+}
 OHB_HD f3 operator/(f3 a, f3 b) { return mk3(a.x / b.x, a.y / b.y, a.z / b.z); }
 OHB_HD f3& operator+=(f3& a, f3 b) { a = a + b; return a; }
 OHB_HD f3& operator*=(f3& a, f3 b) { a = a * b; return a; }
@@ -50,7 +58,16 @@ OHB_HD f3& operator/=(f3& a, float s) { a = a / s; return a; }
 OHB_HD float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 OHB_HD f3 cross(f3 a, f3 b) { return mk3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
 OHB_HD float length(f3 a) { return sqrtf(dot(a, a)); }
-OHB_HD f3 normalize(f3 a) { return a * (1.0f / sqrtf(dot(a, a))); }
+// GLSL normalize().  Device: one MUFU.RSQ (<= 2 ulp) like the inversesqrt a GPU driver emits for the shader; the
+// IEEE sqrt + IEEE reciprocal it replaces was 16 instructions at each of ~25 call sites, 9 % of k_bounce's code, and
+// the shading kernels are instruction-fetch bound (their bodies are 2-3x the 32 KB L1.5 instruction cache).
+OHB_HD f3 normalize(f3 a) {
+#if OHB_DEVICE_CODE
+    return a * rsqrtf(dot(a, a));
+#else
+    return a * (1.0f / sqrtf(dot(a, a)));
+#endif
+}
 OHB_HD f3 vabs(f3 a) { return mk3(fabsf(a.x), fabsf(a.y), fabsf(a.z)); }
 OHB_HD f3 vmin(f3 a, f3 b) { return mk3(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)); }
 OHB_HD f3 vmax(f3 a, f3 b) { return mk3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }

@@ -59,14 +59,17 @@ struct PathArrays {
 
 struct Payload { f3 color, attenuation, hitPos, hitNormal, hitAlbedo; float hitDist, envPdf; };
 
-// pt_miss.rmiss:52-82
-OHB_HD f3 envRadiance(const SceneDev& sc, f3 dir) {   // dir normalised; dirToEquirect + bilinear fetch x envIntensity
-    float phi = ohb_atan2(dir.z, dir.x);
-    float theta = asinf(clampf(dir.y, -1.0f, 1.0f));
+// pt_miss.rmiss:52-82: dirToEquirect + bilinear fetch x envIntensity (dir normalised).  One shared copy: the miss shader
+// and env NEE both call it (two inlined copies in the fused k_shade).
+OHB_SHARED_FN f4 envRadianceShared(const f4* env, uint32_t envW, uint32_t envH, float envIntensity, float dx, float dy, float dz) {
+    float phi = ohb_atan2(dz, dx);
+    float theta = asinf(clampf(dy, -1.0f, 1.0f));
     f2 uv; uv.x = phi / 6.2831853f + 0.5f; uv.y = theta / 3.1415926f + 0.5f;
-    float envS = (sc.envIntensity > 0.0f) ? sc.envIntensity : 1.0f;
-    return xyz(sampleEnvTexture(sc, uv)) * envS;
+    float envS = (envIntensity > 0.0f) ? envIntensity : 1.0f;
+    f3 c = xyz(sampleEnvTexel4(env, int(envW), int(envH), uv)) * envS;
+    return mk4(c, 0.0f);
 }
+OHB_HD f3 envRadiance(const SceneDev& sc, f3 dir) { return xyz(envRadianceShared(sc.env, sc.envW, sc.envH, sc.envIntensity, dir.x, dir.y, dir.z)); }
 OHB_HD void missShader(const SceneDev& sc, const FrameParams& fr, f3 rayDir, Payload& p) {
     p.hitDist = -1.0f;
     bool haveEnv = sc.envMapTexIdx != 0xFFFFFFFFu && sc.env != nullptr;
@@ -163,12 +166,8 @@ static __device__ __host__ __noinline__ f3 cosineHemisphereShared(f3 N, f2 u) { 
 static inline f3 cosineHemisphereShared(f3 N, f2 u) { return cosineHemisphere(N, u); }
 #endif
 OHB_HD float misBalance(float a, float b) { return a / fmaxf(a + b, 1e-6f); }   // mis.glsl:7-9
-OHB_HD float ggxD_anisoOrIso(f3 N, f3 H, float NdotH, float roughness, float anisotropy, float rotation) {   // ggx_aniso.glsl:24-58
-    if (anisotropy < 0.001f) {
-        float a = roughness * roughness, a2 = a * a;
-        float denom = NdotH * NdotH * (a2 - 1.0f) + 1.0f;
-        return a2 / (3.14159265f * denom * denom + 0.0001f);
-    }
+// anisotropic branch of ggxD_anisoOrIso: one shared, cold copy (anisotropy is 0 unless RTRenderSettings sets it)
+OHB_SHARED_FN float ggxD_aniso(f3 N, f3 H, float NdotH, float roughness, float anisotropy, float rotation) {
     f3 up = mk3(0, 1, 0);
     f3 ref = fabsf(dot(up, N)) > 0.97f ? mk3(1, 0, 0) : up;
     f3 T = normalize(ref - N * dot(ref, N));
@@ -181,6 +180,14 @@ OHB_HD float ggxD_anisoOrIso(f3 N, f3 H, float NdotH, float roughness, float ani
     float TdotH = dot(Tr, H), BdotH = dot(Br, H);
     float dd = (TdotH * TdotH / rT) + (BdotH * BdotH / rB) + NdotH * NdotH;
     return 1.0f / (3.14159265f * rT * rB * dd * dd + 0.0001f);
+}
+OHB_HD float ggxD_anisoOrIso(f3 N, f3 H, float NdotH, float roughness, float anisotropy, float rotation) {   // ggx_aniso.glsl:24-58
+    if (anisotropy < 0.001f) {
+        float a = roughness * roughness, a2 = a * a;
+        float denom = NdotH * NdotH * (a2 - 1.0f) + 1.0f;
+        return a2 / (3.14159265f * denom * denom + 0.0001f);
+    }
+    return ggxD_aniso(N, H, NdotH, roughness, anisotropy, rotation);
 }
 OHB_HD f3 schlick(f3 F0, float c) { return F0 + (mk3(1.0f) - F0) * pow5(1.0f - c); }   // pow(x, 5.0) as 3 multiplies (<= 2 ulp)
 OHB_HD float specProbOf(f3 rayDir, f3 N, f3 F0, float rough, float metal) {

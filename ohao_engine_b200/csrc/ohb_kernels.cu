@@ -382,11 +382,13 @@ __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_bounce(SceneDev sc, Fra
     }
 }
 // Fused shading (k_surface + k_bounce in one pass over queueIn, payload in registers: shadePath).  It moves 30 % fewer
-// bytes per path, but it is 5 800 SASS instructions of straight-line code and the shading kernels are instruction-FETCH
-// limited as soon as warps diverge over much of it (ncu stall_no_instruction 11-20 cycles per issue on the textured,
-// env-lit helmet scene, 3-6 on Cornell: profiles/r1q_ncu_shade_*.txt).  Measured (profiles/r1p_sweep.txt): Cornell
-// +56 %, synthetic 2 M +0 %, helmet -24 %.  launchOfflineBatch therefore uses it only when the scene executes neither
-// the texture code nor the env-map code (no env map bound, 1x1 texture layers); OHB_FUSED_SHADE=0/1 forces a choice.
+// bytes per path, but the shading kernels are instruction-FETCH limited: their straight-line bodies are 2-3x the 32 KB
+// L1.5 instruction cache, and as soon as warps diverge over much of the code the schedulers starve (ncu
+// stall_no_instruction 11-20 cycles per issue for the first version on the textured helmet scene, 3-6 on Cornell:
+// profiles/r1q_ncu_shade_*.txt).  Measured after the code-size work (shared sampler / texture / anisotropy helpers,
+// MUFU reciprocals; k_shade 5 800 -> 4 400 SASS instructions; profiles/r1u_sweep.txt, r1v_sweep.txt): Cornell +69 %,
+// synthetic 2 M +7 %, textured helmet -9 %.  launchOfflineBatch therefore fuses when the scene's closest-hit shader runs
+// no texture code (1x1 layers); OHB_FUSED_SHADE=0/1 forces a choice.
 template <int MINB>
 __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(SceneDev sc, FrameParams fr, PathArrays P) {
     const uint32_t n = *P.countIn;
@@ -434,7 +436,7 @@ void launchOfflineBatch(const SceneDev& sc, const FrameParams& fr, PathArrays P,
     uint32_t iters = 1u + 2u * fr.maxBounces;
     static const int bounceOcc = []() { const char* e = getenv("OHB_BOUNCE_OCC"); return e ? atoi(e) : 8; }();
     static const int fusedKnob = []() { const char* e = getenv("OHB_FUSED_SHADE"); return e ? atoi(e) : -1; }();   // -1 = by scene, see k_shade
-    const bool fusedShade = fusedKnob >= 0 ? fusedKnob != 0 : (sc.env == nullptr && sc.texW <= 1u && sc.texH <= 1u);
+    const bool fusedShade = fusedKnob >= 0 ? fusedKnob != 0 : (sc.texW <= 1u && sc.texH <= 1u);
     for (uint32_t it = 0; it < iters; it++) {
         if (th) th->begin(0, st);
         launchTraceClosest(traceGrid, sc, P, work, st);
