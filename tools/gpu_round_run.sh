@@ -16,10 +16,10 @@ timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_be
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/${TAG}_launches_helmet.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/${TAG}_ncu_b.log 2>&1
 for WL in helmet synthetic2m; do
   REP=/tmp/${TAG}_full_$WL
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'^k_(trace|surface|bounce|film)' --launch-skip 0 -c 36 -o $REP python bench.py --workload $WL --steps 1 --warmup 3 --spp-step 4 --no-cpu-baseline > $O/${TAG}_ncu_full_$WL.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'^k_(trace|surface|bounce|shade|film)' --launch-skip 0 -c 36 -o $REP python bench.py --workload $WL --steps 1 --warmup 3 --spp-step 4 --no-cpu-baseline > $O/${TAG}_ncu_full_$WL.log 2>&1
   python tools/ncu_summary.py $REP.ncu-rep > $O/${TAG}_ncu_full_$WL.txt 2>&1
   OHB_TRAFFIC_JSON=$O/${TAG}_traffic.json python tools/ncu_traffic.py $REP.ncu-rep $WL/offline $O/${TAG}_ncu_full_$WL.log > /dev/null 2>&1
-  for K in k_trace_closest k_trace_shadow k_bounce k_surface; do
+  for K in k_trace_closest k_trace_shadow k_bounce k_surface k_shade; do
     python tools/ncu_lines.py $REP.ncu-rep "regex:^$K" 2 30 > $O/${TAG}_${WL}_${K}_lines.txt 2>&1
   done
 done
