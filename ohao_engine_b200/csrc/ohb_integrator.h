@@ -5,10 +5,11 @@
 // a state machine: every wavefront iteration traces ONE closest-hit ray per live path
 // (k_trace_closest), shades it (shadePath below: closest-hit/miss shader + the raygen's per-bounce
 // body), emits at most two visibility rays whose contributions are parked in `pend` until the
-// any-hit kernel has answered, and writes the next ray.  Shading itself is two kernels per iteration:
-// k_surface (= the closest-hit / miss SHADERS: geometry + texture gathers -> 64-B payload record) and
-// k_bounce (= the raygen's per-bounce body: NEE, MIS, lobe sampling, state machine), so each stays small
-// enough for the instruction cache and its warps diverge two ways at most (hit / miss).  Stage B (specular chain) and Stage C
+// any-hit kernel has answered, and writes the next ray.  Shading is ONE kernel per iteration (k_shade): the
+// closest-hit / miss SHADERS (geometry + texture gathers -> payload) and the raygen's per-bounce body (NEE, MIS, lobe
+// sampling, state machine) back to back with the 64-B payload in registers, over a queue that k_sort_hits has split into
+// hit-only and miss-only warps.  (The realtime profile keeps k_surface + k_bounce_rt with the payload in memory.)
+// Stage B (specular chain) and Stage C
 // (diffuse chain) of one sample run back-to-back on the same path slot because the Sobol dimension
 // counter is shared: C's first dimension depends on how many B consumed.  Contributions are added
 // in exactly the reference's order, so a sample's radiance differs from the megakernel only by
@@ -48,6 +49,7 @@ struct PathArrays {
     f4* shO; f4* shD;              // visibility-ray queue: (origin, tmax) (dir, bits(path << 1 | slot))
     uint32_t* shCount;
     uint32_t* queueIn; uint32_t* queueOut; uint32_t* countIn; uint32_t* countOut;
+    uint8_t* hitFlag;              // per slot of queueIn: 1 = the closest-hit query hit (k_trace_closest -> k_sort_hits of the fused shading path)
     uint32_t* queueSorted; uint32_t* sortCount;   // k_surface re-emits queueIn two-ended: hits from the front, misses from the back; sortCount[0..1]
     unsigned long long* counters;  // [0] samples [1] closest rays [2] shadow rays [3] closest hits
     f4* albedoAOV; f4* normalAOV;  // W*H images (first hit of the last sample rendered)
@@ -560,16 +562,7 @@ OHB_HD uint32_t bounceBody(const SceneDev& sc, const FrameParams& fr, const Path
     P.rayO[p] = mk4(nextO, 0.0f); P.rayD[p] = mk4(nextD, 0.0f);
     return p | ((keep & OHB_ST_PEND_A) ? OHB_Q_PEND_A : 0u) | ((keep & OHB_ST_PEND_B) ? OHB_Q_PEND_B : 0u);
 }
-// k_bounce: per-bounce body after k_surface, payload read back from memory.
-OHB_HD uint32_t bouncePath(const SceneDev& sc, const FrameParams& fr, const PathArrays& P, uint32_t e) {
-    const uint32_t p = OHB_Q_PATH(e);
-    const f4 zero4 = mk4(0.0f, 0.0f, 0.0f, 0.0f);
-    const bool isMiss = (e & OHB_Q_MISS) != 0u;
-    const f4 q0 = P.pay0[p], q1 = P.pay1[p], q2 = isMiss ? zero4 : P.pay2[p], q3 = isMiss ? zero4 : P.pay3[p];
-    return bounceBody(sc, fr, P, e, q0, q1, q2, q3);
-}
-// k_shade: both shading stages in one kernel, the payload stays in registers (no 64-B payload round trip through HBM,
-// no second queue); warps mix hits and misses.
+// k_shade: both shading stages in one kernel, the payload stays in registers (no 64-B payload round trip through HBM).
 OHB_HD uint32_t shadePath(const SceneDev& sc, const FrameParams& fr, const PathArrays& P, uint32_t e) {
     f4 q0, q1, q2, q3;
     const bool hit = surfaceShade(sc, fr, P, OHB_Q_PATH(e), q0, q1, q2, q3);

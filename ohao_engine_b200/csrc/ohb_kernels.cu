@@ -308,6 +308,7 @@ struct PathClosestIO {
         uint32_t p = OHB_Q_PATH(P.queueIn[i]);
         bool hit = t.best.prim != OHB_MISS;
         reinterpret_cast<float4*>(P.hit)[p] = make_float4(hit ? t.best.t : -1.0f, t.best.u, t.best.v, __uint_as_float(t.best.prim));
+        P.hitFlag[i] = hit ? 1u : 0u;
         hits += hit;
     }
 };
@@ -356,45 +357,99 @@ static void launchTraceShadow(unsigned smGrid8, const SceneDev& sc, const PathAr
 #undef OHB_LAUNCH_TS
 }
 #define SHADE_THREADS 128
+// ---- queue emission, STABLE AT TILE GRANULARITY ------------------------------------------------------------------
+// A CTA walks a contiguous tile of QTILE queue entries (QTILE_ROUNDS rounds of SHADE_THREADS), stages what it emits in
+// shared memory in queue order and claims its output range with ONE atomic per tile.  With per-warp atomics every pass
+// cuts the queue into 32-entry chunks that land in arrival order; a few iterations later the 32 paths a warp reads come
+// from many places, the 16-B path-record accesses stop sharing sectors and the shading kernels — which live on that
+// locality — slow down.  Measured (profiles/r1z_sweep.txt): helmet 1034 -> 1258, Cornell 674 -> 894, 2 M 215 -> 230
+// Msamples/s against the same kernels with warp-granular emission.
+#define QTILE_ROUNDS 8
+#define QTILE (SHADE_THREADS * QTILE_ROUNDS)
+struct TileEmit {
+    uint32_t* sOut; uint32_t* sW; uint32_t* sBase; uint32_t kept;
+    __device__ __forceinline__ void begin() { kept = 0u; }
+    // every thread of the CTA calls this once per round (keep = this thread emits e)
+    __device__ __forceinline__ void round(bool keep, uint32_t e) {
+        const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0u) sW[warp] = uint32_t(__popc(m));
+        __syncthreads();
+        uint32_t off = kept, tot = 0u;
+#pragma unroll
+        for (uint32_t w = 0; w < SHADE_THREADS / 32; w++) { if (w < warp) off += sW[w]; tot += sW[w]; }
+        if (keep) sOut[off + uint32_t(__popc(m & ((1u << lane) - 1u)))] = e;
+        kept += tot;
+        __syncthreads();
+    }
+    // forward = true: queue[base + j]; false: queue[last - (base + j)] (the back-to-front half of a two-ended queue)
+    __device__ __forceinline__ void flush(uint32_t* counter, uint32_t* queue, bool forward, uint32_t last) {
+        if (threadIdx.x == 0u) *sBase = kept ? atomicAdd(counter, kept) : 0u;
+        __syncthreads();
+        const uint32_t base = *sBase;
+        for (uint32_t j = threadIdx.x; j < kept; j += SHADE_THREADS) queue[forward ? base + j : last - (base + j)] = sOut[j];
+        __syncthreads();
+    }
+};
+#define OHB_TILE_EMIT(name) __shared__ uint32_t name##_out[QTILE], name##_w[SHADE_THREADS / 32], name##_base; TileEmit name{name##_out, name##_w, &name##_base, 0u}
+
+template <bool RT>
 __global__ void __launch_bounds__(SHADE_THREADS) k_raygen(FrameParams fr, PathArrays P, uint32_t total) {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= total) return;
-    raygenPath(fr, P, p);
-    if (OHB_ST_STAGE(P.meta[p].w) != ST_DONE) { uint32_t q = alloc_slot(P.countIn); P.queueIn[q] = p | OHB_Q_PRIMARY; }
+    OHB_TILE_EMIT(q);
+    const uint32_t tile = blockIdx.x * QTILE;
+    q.begin();
+    for (int r = 0; r < QTILE_ROUNDS; r++) {
+        const uint32_t p = tile + uint32_t(r) * SHADE_THREADS + threadIdx.x;
+        bool keep = false;
+        if (p < total) { if (RT) raygenPathRT(fr, P, p); else raygenPath(fr, P, p); keep = OHB_ST_STAGE(P.meta[p].w) != ST_DONE; }
+        q.round(keep, RT ? p : (p | OHB_Q_PRIMARY));
+    }
+    q.flush(P.countIn, P.queueIn, true, 0u);
 }
+// hits to the front of queueSorted, misses (flagged) to the back, in queue order: the shading kernels then run hit-only
+// and miss-only warps (35 % of the helmet scene's bounce rays miss).  It reads k_trace_closest's per-slot hit flags;
+// emitting from the trace kernel's own store would scatter the path indices (rays finish in arbitrary order, r1i).
+__global__ void __launch_bounds__(SHADE_THREADS) k_sort_hits(PathArrays P) {
+    OHB_TILE_EMIT(qh); OHB_TILE_EMIT(qm);
+    const uint32_t n = *P.countIn;
+    for (uint32_t tile = blockIdx.x * QTILE; tile < n; tile += gridDim.x * QTILE) {
+        qh.begin(); qm.begin();
+        for (int r = 0; r < QTILE_ROUNDS; r++) {
+            const uint32_t i = tile + uint32_t(r) * SHADE_THREADS + threadIdx.x;
+            const bool valid = i < n;
+            const uint32_t e = valid ? P.queueIn[i] : 0u;
+            const bool hit = valid && P.hitFlag[i] != 0u;
+            qh.round(hit, e); qm.round(valid && !hit, e | OHB_Q_MISS);
+        }
+        qh.flush(P.sortCount, P.queueSorted, true, 0u); qm.flush(P.sortCount + 1, P.queueSorted, false, n - 1u);
+    }
+}
+// k_surface: closest-hit / miss shaders of the sorted queue -> payload records (realtime profile; the offline profile fuses it into k_shade)
 __global__ void __launch_bounds__(SHADE_THREADS) k_surface(SceneDev sc, FrameParams fr, PathArrays P) {
     const uint32_t n = *P.countIn;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint32_t e = P.queueIn[i];
-        // two-ended re-emit: k_bounce then runs hit-only and miss-only warps (35 % of bounce rays miss on the helmet scene).
-        // It has to happen HERE, in queue order: emitting from k_trace_closest's store (rays finish in arbitrary order)
-        // scatters the path indices and made k_surface + k_bounce 60 % slower (sector-inefficient path records, r1i).
-        if (surfacePath(sc, fr, P, OHB_Q_PATH(e))) P.queueSorted[alloc_slot(P.sortCount)] = e;
-        else                                       P.queueSorted[n - 1u - alloc_slot(P.sortCount + 1)] = e | OHB_Q_MISS;
-    }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        surfacePath(sc, fr, P, OHB_Q_PATH(P.queueSorted[i]));
 }
-template <int MINB>
-__global__ void __launch_bounds__(SHADE_THREADS, MINB) k_bounce(SceneDev sc, FrameParams fr, PathArrays P) {
-    const uint32_t n = *P.countIn;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint32_t e = bouncePath(sc, fr, P, P.queueSorted[i]);
-        if (e != OHB_Q_NONE) { uint32_t q = alloc_slot(P.countOut); P.queueOut[q] = e; }
-    }
-}
-// Fused shading (k_surface + k_bounce in one pass over queueIn, payload in registers: shadePath).  It moves 30 % fewer
-// bytes per path, but the shading kernels are instruction-FETCH limited: their straight-line bodies are 2-3x the 32 KB
-// L1.5 instruction cache, and as soon as warps diverge over much of the code the schedulers starve (ncu
-// stall_no_instruction 11-20 cycles per issue for the first version on the textured helmet scene, 3-6 on Cornell:
-// profiles/r1q_ncu_shade_*.txt).  Measured after the code-size work (shared sampler / texture / anisotropy helpers,
-// MUFU reciprocals; k_shade 5 800 -> 4 400 SASS instructions; profiles/r1u_sweep.txt, r1v_sweep.txt): Cornell +69 %,
-// synthetic 2 M +7 %, textured helmet -9 %.  launchOfflineBatch therefore fuses when the scene's closest-hit shader runs
-// no texture code (1x1 layers); OHB_FUSED_SHADE=0/1 forces a choice.
+// k_shade: closest-hit / miss shaders + the raygen's per-bounce body in one kernel, the payload stays in registers
+// (shadePath): 376 B of DRAM traffic per path on the 2 M scene against 831 B for a k_surface + k_bounce pair
+// (profiles/r1x_ncu_full_synthetic2m_kshade.txt).  The shading kernels are instruction-FETCH limited — straight-line
+// bodies of 2-3x the 32 KB L1.5 instruction cache, ncu stall_no_instruction 4-6 of 8 warps per scheduler — so the
+// fused kernel only pays off with the code-size work (shared sampler / texture / env-lookup / anisotropy copies, MUFU
+// reciprocals: 5 800 -> 3 900 SASS instructions) and with hit-only / miss-only warps (k_sort_hits): profiles/r1p, r1u,
+// r1v, r1z sweeps record each step.
 template <int MINB>
 __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(SceneDev sc, FrameParams fr, PathArrays P) {
+    OHB_TILE_EMIT(q);
     const uint32_t n = *P.countIn;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint32_t e = shadePath(sc, fr, P, P.queueIn[i]);
-        if (e != OHB_Q_NONE) { uint32_t q = alloc_slot(P.countOut); P.queueOut[q] = e; }
+    for (uint32_t tile = blockIdx.x * QTILE; tile < n; tile += gridDim.x * QTILE) {
+        q.begin();
+        for (int r = 0; r < QTILE_ROUNDS; r++) {
+            const uint32_t i = tile + uint32_t(r) * SHADE_THREADS + threadIdx.x;
+            uint32_t e = OHB_Q_NONE;
+            if (i < n) e = shadePath(sc, fr, P, P.queueSorted[i]);
+            q.round(e != OHB_Q_NONE, e);
+        }
+        q.flush(P.countOut, P.queueOut, true, 0u);
     }
 }
 // Between iterations: account the rays just traced, clear the queues that are about to be refilled.
@@ -428,33 +483,21 @@ void launchOfflineBatch(const SceneDev& sc, const FrameParams& fr, PathArrays P,
     uint32_t total = P.numPixels * P.samplesInBatch;
     k_zero_u32<<<1, 32, 0, st>>>(P.countIn, 1); k_zero_u32<<<1, 32, 0, st>>>(P.countOut, 1);
     k_sobol_tab<<<gridFor(P.samplesInBatch, 64), 64, 0, st>>>(const_cast<u4*>(P.sobolTab), P.firstSampleIndex, P.samplesInBatch); (*launches)++;
-    k_raygen<<<gridFor(total, SHADE_THREADS), SHADE_THREADS, 0, st>>>(fr, P, total);
+    k_raygen<false><<<gridFor(total, QTILE), SHADE_THREADS, 0, st>>>(fr, P, total);
     k_advance<<<1, 32, 0, st>>>(P, work, 1);
     *launches += 4;
     unsigned traceGrid = unsigned(numSMs) * 8u;
     unsigned shadeGrid = unsigned(numSMs) * 8u;
     uint32_t iters = 1u + 2u * fr.maxBounces;
     static const int bounceOcc = []() { const char* e = getenv("OHB_BOUNCE_OCC"); return e ? atoi(e) : 8; }();
-    static const int fusedKnob = []() { const char* e = getenv("OHB_FUSED_SHADE"); return e ? atoi(e) : -1; }();   // -1 = by scene, see k_shade
-    const bool fusedShade = fusedKnob >= 0 ? fusedKnob != 0 : (sc.texW <= 1u && sc.texH <= 1u);
     for (uint32_t it = 0; it < iters; it++) {
         if (th) th->begin(0, st);
         launchTraceClosest(traceGrid, sc, P, work, st);
         if (th) th->end(0, st);
-        if (fusedShade) {
-            if (th) th->begin(1, st);
-            if (bounceOcc >= 8) k_shade<8><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P); else k_shade<6><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P);
-            if (th) th->end(1, st);
-        } else {
-            if (th) th->begin(4, st);
-            k_surface<<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P);
-            if (th) th->end(4, st);
-            if (th) th->begin(1, st);
-            if (bounceOcc >= 8)      k_bounce<8><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P);
-            else if (bounceOcc >= 6) k_bounce<6><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P);
-            else                     k_bounce<1><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P);
-            if (th) th->end(1, st);
-        }
+        if (th) th->begin(1, st);
+        k_sort_hits<<<shadeGrid, SHADE_THREADS, 0, st>>>(P);
+        if (bounceOcc >= 8) k_shade<8><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P); else k_shade<6><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P);
+        if (th) th->end(1, st);
         if (th) th->begin(2, st);
         launchTraceShadow(traceGrid, sc, P, work + 1, st);
         if (th) th->end(2, st);
@@ -471,17 +514,18 @@ void launchOfflineBatch(const SceneDev& sc, const FrameParams& fr, PathArrays P,
 // =============================================================================================
 // Realtime profile: one frame = N-spp wavefront + per-pixel ReSTIR GI / EMA + a-trous (ohb_realtime.h)
 // =============================================================================================
-__global__ void __launch_bounds__(SHADE_THREADS) k_raygen_rt(FrameParams fr, PathArrays P, uint32_t total) {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= total) return;
-    raygenPathRT(fr, P, p);
-    if (OHB_ST_STAGE(P.meta[p].w) != ST_DONE) { uint32_t q = alloc_slot(P.countIn); P.queueIn[q] = p; }
-}
 __global__ void __launch_bounds__(SHADE_THREADS, 8) k_bounce_rt(SceneDev sc, FrameParams fr, PathArrays P) {
+    OHB_TILE_EMIT(q);
     const uint32_t n = *P.countIn;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint32_t p = OHB_Q_PATH(P.queueSorted[i]);
-        if (bouncePathRT(sc, fr, P, p)) { uint32_t q = alloc_slot(P.countOut); P.queueOut[q] = p; }
+    for (uint32_t tile = blockIdx.x * QTILE; tile < n; tile += gridDim.x * QTILE) {
+        q.begin();
+        for (int r = 0; r < QTILE_ROUNDS; r++) {
+            const uint32_t i = tile + uint32_t(r) * SHADE_THREADS + threadIdx.x;
+            uint32_t p = 0u; bool keep = false;
+            if (i < n) { p = OHB_Q_PATH(P.queueSorted[i]); keep = bouncePathRT(sc, fr, P, p); }
+            q.round(keep, p);
+        }
+        q.flush(P.countOut, P.queueOut, true, 0u);
     }
 }
 __global__ void __launch_bounds__(128) k_rt_pixel(SceneDev sc, FrameParams fr, PathArrays P, RTImagesDev im) {
@@ -497,7 +541,7 @@ void launchRealtimeFrame(const SceneDev& sc, const FrameParams& fr, PathArrays P
     uint32_t total = P.numPixels * P.samplesInBatch;
     k_zero_u32<<<1, 32, 0, st>>>(P.countIn, 1); k_zero_u32<<<1, 32, 0, st>>>(P.countOut, 1);
     k_sobol_tab<<<gridFor(P.samplesInBatch, 64), 64, 0, st>>>(const_cast<u4*>(P.sobolTab), P.firstSampleIndex, P.samplesInBatch);
-    k_raygen_rt<<<gridFor(total, SHADE_THREADS), SHADE_THREADS, 0, st>>>(fr, P, total);
+    k_raygen<true><<<gridFor(total, QTILE), SHADE_THREADS, 0, st>>>(fr, P, total);
     k_advance<<<1, 32, 0, st>>>(P, work, 1);
     *launches += 5;
     unsigned grid = unsigned(numSMs) * 8u;
@@ -507,6 +551,7 @@ void launchRealtimeFrame(const SceneDev& sc, const FrameParams& fr, PathArrays P
         launchTraceClosest(grid, sc, P, work, st);
         if (th) th->end(0, st);
         if (th) th->begin(4, st);
+        k_sort_hits<<<grid, SHADE_THREADS, 0, st>>>(P); (*launches)++;
         k_surface<<<grid, SHADE_THREADS, 0, st>>>(sc, fr, P);
         if (th) th->end(4, st);
         if (th) th->begin(1, st);

@@ -18,7 +18,6 @@ static inline int emulWarpActive() {
 }
 #define OHB_WARP_ACTIVE() emulWarpActive()
 static unsigned long long g_statNodes = 0, g_statTris = 0;
-static int g_emulFusedShade = 0;
 #define OHB_STAT_NODE() (g_statNodes++)
 #define OHB_STAT_TRI() (g_statTris++)
 #include "../../ohao_engine_b200/csrc/ohb_bvh.h"
@@ -198,7 +197,6 @@ void emul_svgf_guides(const float* surf, uint32_t W, uint32_t H, const float* vi
 }
 uint16_t emul_f2h(float f) { return f2h(f); }
 float emul_h2f(uint16_t h) { return h2f(h); }
-void emul_set_fused_shade(int on) { g_emulFusedShade = on; }
 void emul_trav_stats(unsigned long long* nodes, unsigned long long* tris, int reset) { *nodes = g_statNodes; *tris = g_statTris; if (reset) { g_statNodes = 0; g_statTris = 0; } }
 void emul_set_warp_noise(unsigned on) { g_emulWarpNoise = on; g_emulWarpState = 12345u; }
 
@@ -269,16 +267,9 @@ int emul_render_offline(void* h, emul_render_args* a) {
     for (uint32_t it = 0; it < iters; it++) {
         uint32_t n = *P.countIn;
         for (uint32_t i = 0; i < n; i++) { uint32_t p = OHB_Q_PATH(P.queueIn[i]); P.hit[p] = traceClosest(sc, xyz(P.rayO[p]), xyz(P.rayD[p]), 0.001f, 10000.0f); counters[3] += P.hit[p].prim != OHB_MISS; }
-        if (g_emulFusedShade) {                                                                                                         // k_shade
-            for (uint32_t i = 0; i < n; i++) { uint32_t e = shadePath(sc, fr, P, P.queueIn[i]); if (e != OHB_Q_NONE) P.queueOut[(*P.countOut)++] = e; }
-        } else {
-            sortCount[0] = sortCount[1] = 0;
-            for (uint32_t i = 0; i < n; i++) {                                                                                           // k_surface
-                uint32_t e = P.queueIn[i];
-                if (surfacePath(sc, fr, P, OHB_Q_PATH(e))) P.queueSorted[sortCount[0]++] = e; else P.queueSorted[n - 1u - sortCount[1]++] = e | OHB_Q_MISS;
-            }
-            for (uint32_t i = 0; i < n; i++) { uint32_t e = bouncePath(sc, fr, P, P.queueSorted[i]); if (e != OHB_Q_NONE) P.queueOut[(*P.countOut)++] = e; }   // k_bounce
-        }
+        sortCount[0] = sortCount[1] = 0;                                                                                                 // k_sort_hits
+        for (uint32_t i = 0; i < n; i++) { uint32_t e = P.queueIn[i]; if (P.hit[OHB_Q_PATH(e)].prim != OHB_MISS) P.queueSorted[sortCount[0]++] = e; else P.queueSorted[n - 1u - sortCount[1]++] = e | OHB_Q_MISS; }
+        for (uint32_t i = 0; i < n; i++) { uint32_t e = shadePath(sc, fr, P, P.queueSorted[i]); if (e != OHB_Q_NONE) P.queueOut[(*P.countOut)++] = e; }   // k_shade
         uint32_t ns = *P.shCount;
         for (uint32_t i = 0; i < ns; i++) {
             f4 o = P.shO[i], d = P.shD[i];

@@ -43,7 +43,6 @@ def lib():
         _LIB.emul_accel_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
         _LIB.emul_accel_levels.argtypes = [C.c_void_p]; _LIB.emul_accel_levels.restype = C.c_uint32
         _LIB.emul_set_warp_noise.argtypes = [C.c_uint]
-        _LIB.emul_set_fused_shade.argtypes = [C.c_int]
         _LIB.emul_svgf_dispatch.argtypes = [C.POINTER(O.SvgfArgs)]
         _LIB.emul_svgf_guides.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_uint32, C.c_void_p, C.c_void_p]
         _LIB.emul_f2h.restype = C.c_uint16; _LIB.emul_f2h.argtypes = [C.c_float]
@@ -150,11 +149,6 @@ def svgf_guides(surf, view, proj, prev_view_proj, frame_index):
 def set_warp_noise(on: bool):
     """Pseudo-random active-lane counts: drives triangle postponing and pause/resume in the host emulator."""
     lib().emul_set_warp_noise(1 if on else 0)
-
-
-def set_fused_shade(on: bool):
-    """Offline wavefront through shadePath (k_shade: surface + bounce fused, payload in registers) instead of k_surface + k_bounce."""
-    lib().emul_set_fused_shade(1 if on else 0)
 
 
 def trav_stats(reset=True):

@@ -29,19 +29,13 @@ def test_oracle_bvh_equals_brute_force(cornell):
     assert np.array_equal(a["prim"], b["prim"]) and np.array_equal(a["t"], b["t"])
 
 
-@pytest.mark.parametrize("fused", [False, True], ids=["split", "fused"])
 @pytest.mark.parametrize("which,res,spp", [("cornell", (96, 54), 4), ("helmet_small", (80, 45), 3), ("synthetic_small", (80, 45), 3)])
-def test_offline_samples_match_oracle(which, res, spp, fused, request):
-    """fused = k_shade (surface + bounce in one kernel, payload in registers); split = k_surface -> k_bounce."""
+def test_offline_samples_match_oracle(which, res, spp, request):
     ps, cam = request.getfixturevalue(which)
     W, H = res
     osc, esc = O.OracleScene(ps), E.EmulScene(ps)
     ro = osc.render_offline(cam.view(), cam.proj(W, H), W, H, spp, dump=True, want_aov=True)
-    E.set_fused_shade(fused)
-    try:
-        re = esc.render_offline(cam.view(), cam.proj(W, H), W, H, spp, dump=True)
-    finally:
-        E.set_fused_shade(False)
+    re = esc.render_offline(cam.view(), cam.proj(W, H), W, H, spp, dump=True)
     bad, worst = util.sample_parity(ro["samples"], re["samples"])
     assert bad < 2e-3 and worst < 2e-3, (bad, worst)
     for k in ("closest_rays", "shadow_rays"):
