@@ -4,8 +4,9 @@
 // ohb_traverse.h / ohb_integrator.h.  Scheduling choices (DESIGN.md "Kernels"):
 //   * traversal kernels are persistent: gridDim = SMs x resident blocks, each warp pulls 32 rays at
 //     a time from a global work counter, so the tail of an incoherent wavefront does not idle SMs;
-//   * queue pushes are warp-aggregated (one atomic per warp), no host round trip between the
-//     iterations of a wavefront: queue sizes live in device memory and kernels read them;
+//   * path queues are emitted stable at tile granularity (TileEmit: 1024 entries staged in shared memory, one atomic
+//     per tile; shadow-ray pushes are warp-aggregated), no host round trip between the iterations of a wavefront:
+//     queue sizes live in device memory and kernels read them;
 //   * the radix sort ranks keys with __match_any_sync per warp-private digit counters (stable,
 //     no shared-memory atomics in the scatter loop).
 #include "ohb_device.h"
