@@ -319,7 +319,7 @@ def main():
                        "frames_per_s": (args.steps / (ms * 1e-3)) if realtime else None, "treelet_passes": int(st.treelet_passes),
                        "bvh_nodes": int(st.num_nodes), "bvh_sah": round(float(st.sah_cost), 2), "bvh_build_ms": round(float(st.build_ms), 3),
                        "parallelism": f"spp-shard x{world}" if world > 1 else "single GPU",
-                       "l2": "path-state working set %.1f GB per step >> 126 MB L2 (no explicit flush)" % (W * H * min(spp, 16) * 352 / 1e9)},
+                       "l2": "path-state working set %.1f GB per step >> 126 MB L2 (no explicit flush)" % (W * H * min(spp, 16) * (337 if realtime else 273) / 1e9)},
             "rays": {"per_sample": (tot["closest_rays"] + tot["shadow_rays"]) / max(tot["samples"], 1),
                      "closest_per_sample": tot["closest_rays"] / max(tot["samples"], 1), "shadow_per_sample": tot["shadow_rays"] / max(tot["samples"], 1),
                      "mrays_per_s": (tot["closest_rays"] + tot["shadow_rays"]) / (ms * 1e-3) / 1e6,

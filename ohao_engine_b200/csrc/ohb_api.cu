@@ -85,7 +85,7 @@ struct ohb_ctx {
     DevBuf activeTris, wtri, primLo, primHi, boundsBits, keys, vals, keysTmp, valsTmp, sortTemp, left, right, parentInner, parentLeaf,
            nodeLo, nodeHi, visit, wideCounters, wideItemsA, wideItemsB, sah, wnodes, tris;
     // paths (device)
-    DevBuf rayO, rayD, hit, thr, rad, pendA, pendB, meta, fh0, fh1, fh2, fh3, pay0, pay1, pay2, pay3, shO, shD, queueA, queueB, queueS, hitFlag, sobolTab, smallCounters, devCounters;
+    DevBuf rayO, rayD, hit, thr, rad, pendA, pendB, meta, fh0, fh1, fh2, pay0, pay1, pay2, pay3, shO, shD, queueA, queueB, queueS, hitFlag, sobolTab, smallCounters, devCounters;
     uint32_t pathCapacity = 0;
     // film
     DevBuf accum, ldr, albedoAOV, normalAOV, sampleDump;
@@ -181,7 +181,7 @@ void ohb_destroy(ohb_ctx* c) {
                      &c->tex, &c->lights, &c->env, &c->marg, &c->cond, &c->rowTotal, &c->integral, &c->activeTris, &c->wtri, &c->primLo, &c->primHi, &c->boundsBits,
                      &c->keys, &c->vals, &c->keysTmp, &c->valsTmp, &c->sortTemp, &c->left, &c->right, &c->parentInner, &c->parentLeaf,
                      &c->nodeLo, &c->nodeHi, &c->visit, &c->wideCounters, &c->wideItemsA, &c->wideItemsB, &c->sah, &c->wnodes, &c->tris, &c->rayO, &c->rayD, &c->hit, &c->thr, &c->rad,
-                     &c->pendA, &c->pendB, &c->meta, &c->fh0, &c->fh1, &c->fh2, &c->fh3, &c->pay0, &c->pay1, &c->pay2, &c->pay3, &c->shO, &c->shD, &c->queueA, &c->queueB, &c->queueS, &c->hitFlag, &c->sobolTab, &c->smallCounters, &c->devCounters,
+                     &c->pendA, &c->pendB, &c->meta, &c->fh0, &c->fh1, &c->fh2, &c->pay0, &c->pay1, &c->pay2, &c->pay3, &c->shO, &c->shD, &c->queueA, &c->queueB, &c->queueS, &c->hitFlag, &c->sobolTab, &c->smallCounters, &c->devCounters,
                      &c->accum, &c->ldr, &c->albedoAOV, &c->normalAOV, &c->sampleDump, &c->hookRays, &c->hookOut, &c->hookAux,
                      &c->accumPrev, &c->surf[0], &c->surf[1], &c->shad[0], &c->shad[1], &c->res[0][0], &c->res[0][1], &c->res[0][2],
                      &c->res[1][0], &c->res[1][1], &c->res[1][2], &c->rtDump[0], &c->rtDump[1], &c->rtDump[2],
@@ -460,8 +460,10 @@ int ensurePaths(ohb_ctx* c, uint32_t cap) {
     size_t n = cap;
     CU(c, c->rayO.reserve(n * 16)); CU(c, c->rayD.reserve(n * 16)); CU(c, c->hit.reserve(n * 16)); CU(c, c->thr.reserve(n * 16)); CU(c, c->rad.reserve(n * 16));
     CU(c, c->pendA.reserve(n * 16)); CU(c, c->pendB.reserve(n * 16)); CU(c, c->meta.reserve(n * 16));
-    CU(c, c->fh0.reserve(n * 16)); CU(c, c->fh1.reserve(n * 16)); CU(c, c->fh2.reserve(n * 16)); CU(c, c->fh3.reserve(n * 16));
-    CU(c, c->pay0.reserve(n * 16)); CU(c, c->pay1.reserve(n * 16)); CU(c, c->pay2.reserve(n * 16)); CU(c, c->pay3.reserve(n * 16));
+    CU(c, c->fh0.reserve(n * 16)); CU(c, c->fh1.reserve(n * 16)); CU(c, c->fh2.reserve(n * 16));
+    if (c->profile == OHB_PROFILE_REALTIME) {   // the payload goes through memory only between k_surface and k_bounce_rt; the offline k_shade keeps it in registers
+        CU(c, c->pay0.reserve(n * 16)); CU(c, c->pay1.reserve(n * 16)); CU(c, c->pay2.reserve(n * 16)); CU(c, c->pay3.reserve(n * 16));
+    }
     CU(c, c->shO.reserve(n * 32)); CU(c, c->shD.reserve(n * 32)); CU(c, c->queueA.reserve(n * 4)); CU(c, c->queueB.reserve(n * 4)); CU(c, c->queueS.reserve(n * 4)); CU(c, c->hitFlag.reserve(n));
     c->pathCapacity = cap;
     return 0;
@@ -485,7 +487,7 @@ static void fillPaths(ohb_ctx* c, PathArrays& P) {
     uint32_t* small = c->smallCounters.as<uint32_t>();
     P.rayO = c->rayO.as<f4>(); P.rayD = c->rayD.as<f4>(); P.hit = c->hit.as<ohb_hit>(); P.thr = c->thr.as<f4>(); P.rad = c->rad.as<f4>();
     P.pendA = c->pendA.as<f4>(); P.pendB = c->pendB.as<f4>(); P.meta = c->meta.as<u4>();
-    P.fh0 = c->fh0.as<f4>(); P.fh1 = c->fh1.as<f4>(); P.fh2 = c->fh2.as<f4>(); P.fh3 = c->fh3.as<f4>();
+    P.fh0 = c->fh0.as<f4>(); P.fh1 = c->fh1.as<f4>(); P.fh2 = c->fh2.as<f4>();
     P.pay0 = c->pay0.as<f4>(); P.pay1 = c->pay1.as<f4>(); P.pay2 = c->pay2.as<f4>(); P.pay3 = c->pay3.as<f4>();
     P.shO = c->shO.as<f4>(); P.shD = c->shD.as<f4>();
     P.queueIn = c->queueA.as<uint32_t>(); P.queueOut = c->queueB.as<uint32_t>();

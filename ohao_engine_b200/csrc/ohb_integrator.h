@@ -44,8 +44,8 @@ struct PathArrays {
     f4* rad;                       // radiance.xyz of this sample so far
     f4* pendA; f4* pendB;          // parked light-NEE / env-NEE contributions (zeroed by k_trace_shadow when occluded)
     u4* meta;                      // x = px | py << 16, y = sampleIdx, z = dimIdx, w = state bits
-    f4* fh0; f4* fh1; f4* fh2; f4* fh3;   // first hit kept for the Stage C set-up: (pos, rough) (N, metal) (albedo, -) (rayDir, -)
-    f4* pay0; f4* pay1; f4* pay2; f4* pay3;   // RayPayload of the last query: (hitPos|color, hitDist) (N, att.x | envPdf) (albedo, att.y) (emission, att.z)
+    f4* fh0; f4* fh1; f4* fh2;            // first hit kept for the Stage C set-up: (pos, rough) (N, metal) (albedo, -)
+    f4* pay0; f4* pay1; f4* pay2; f4* pay3;   // (realtime profile only; the offline k_shade keeps it in registers) RayPayload of the last query: (hitPos|color, hitDist) (N, att.x | envPdf) (albedo, att.y) (emission, att.z)
     f4* shO; f4* shD;              // visibility-ray queue: (origin, tmax) (dir, bits(path << 1 | slot))
     uint32_t* shCount;
     uint32_t* queueIn; uint32_t* queueOut; uint32_t* countIn; uint32_t* countOut;
@@ -528,7 +528,7 @@ OHB_HD uint32_t bounceBody(const SceneDev& sc, const FrameParams& fr, const Path
                 lastPdf = (1.0f - specProb) * fmaxf(dot(nextD, N), 0.0f) / OHB_PI; lastDelta = false;
             }
             if (primary) {
-                P.fh0[p] = mk4(hp, rough); P.fh1[p] = mk4(N, metal); P.fh2[p] = mk4(albedo, 0.0f); P.fh3[p] = mk4(d, 0.0f);
+                P.fh0[p] = mk4(hp, rough); P.fh1[p] = mk4(N, metal); P.fh2[p] = mk4(albedo, 0.0f);
                 if (fr.maxBounces >= 1u) { stage = ST_CHAIN_B; bounce = 1u; }
                 else { startC = true; fhPos = hp; fhN = N; fhAlbedo = albedo; stage = ST_CHAIN_B; }
             } else if (bounce >= fr.maxBounces) chainEnds = true;

@@ -232,7 +232,7 @@ OHB_HD bool bouncePathRT(const SceneDev& sc, const FrameParams& fr, const PathAr
                 thr = F * smithG2overG1GGX(NdotV, NdotL, alpha);
                 lastPdf = smithG1GGX(NdotV, alpha) * ggxDiso(NdotH, alpha) / (4.0f * NdotV) + 1e-6f; lastDelta = false;
             }
-            P.fh0[p] = mk4(hp, rough); P.fh1[p] = mk4(N, metal); P.fh2[p] = mk4(albedo, q0.w); P.fh3[p] = mk4(d, 0.0f);
+            P.fh0[p] = mk4(hp, rough); P.fh1[p] = mk4(N, metal); P.fh2[p] = mk4(albedo, q0.w);
             if (fr.maxBounces >= 1u) { stage = ST_CHAIN_B; bounce = 1u; } else chainEnds = true;
         } else {
             bool killed = false;

@@ -246,7 +246,7 @@ int emul_render_offline(void* h, emul_render_args* a) {
     fr.tileX = a->tile_x; fr.tileY = a->tile_y; fr.tileW = a->tile_w ? a->tile_w : a->width; fr.tileH = a->tile_h ? a->tile_h : a->height;
     uint32_t tilesX = (fr.tileW + 7u) / 8u, tilesY = (fr.tileH + 3u) / 4u, numPixels = tilesX * tilesY * 32u;
     uint32_t total = numPixels * a->nsamples;
-    std::vector<f4> rayO(total), rayD(total), thr(total), rad(total), pendA(total), pendB(total), fh0(total), fh1(total), fh2(total), fh3(total), pay0(total), pay1(total), pay2(total), pay3(total), shO(size_t(total) * 2), shD(size_t(total) * 2);
+    std::vector<f4> rayO(total), rayD(total), thr(total), rad(total), pendA(total), pendB(total), fh0(total), fh1(total), fh2(total), pay0(total), pay1(total), pay2(total), pay3(total), shO(size_t(total) * 2), shD(size_t(total) * 2);
     std::vector<ohb_hit> hit(total); std::vector<u4> meta(total); std::vector<uint32_t> qa(total), qb(total);
     uint32_t small[4] = {0, 0, 0, 0}; unsigned long long counters[8] = {0};
     size_t npx = size_t(a->width) * a->height;
@@ -258,7 +258,7 @@ int emul_render_offline(void* h, emul_render_args* a) {
     PathArrays P{};
     P.sobolTab = sobolTab.data(); P.queueSorted = qs.data(); P.sortCount = sortCount;
     P.rayO = rayO.data(); P.rayD = rayD.data(); P.hit = hit.data(); P.thr = thr.data(); P.rad = rad.data(); P.pendA = pendA.data(); P.pendB = pendB.data(); P.meta = meta.data();
-    P.fh0 = fh0.data(); P.fh1 = fh1.data(); P.fh2 = fh2.data(); P.fh3 = fh3.data(); P.pay0 = pay0.data(); P.pay1 = pay1.data(); P.pay2 = pay2.data(); P.pay3 = pay3.data(); P.shO = shO.data(); P.shD = shD.data();
+    P.fh0 = fh0.data(); P.fh1 = fh1.data(); P.fh2 = fh2.data(); P.pay0 = pay0.data(); P.pay1 = pay1.data(); P.pay2 = pay2.data(); P.pay3 = pay3.data(); P.shO = shO.data(); P.shD = shD.data();
     P.queueIn = qa.data(); P.queueOut = qb.data(); P.countIn = &small[0]; P.countOut = &small[1]; P.shCount = &small[2]; P.counters = counters;
     P.albedoAOV = albedo.data(); P.normalAOV = normal.data(); P.numPixels = numPixels; P.samplesInBatch = a->nsamples; P.firstSampleIndex = a->first_sample_index;
     for (uint32_t p = 0; p < total; p++) { raygenPath(fr, P, p); if (OHB_ST_STAGE(P.meta[p].w) != ST_DONE) P.queueIn[(*P.countIn)++] = p | OHB_Q_PRIMARY; }
@@ -314,7 +314,7 @@ int emul_render_realtime(void* h, emul_rt_args* a) {
     uint32_t spf = a->settings.samples_per_frame; spf = spf < 1u ? 1u : (spf > 64u ? 64u : spf);
     fr.frameIdx = a->frame_index; fr.historyCount = a->history_count; fr.viewChanged = a->view_changed; fr.spf = spf; fr.jitterSobol = sobolQuad(fr.frameIdx);
     uint32_t tilesX = (fr.tileW + 7u) / 8u, tilesY = (fr.tileH + 3u) / 4u, numPixels = tilesX * tilesY * 32u, total = numPixels * spf;
-    std::vector<f4> rayO(total), rayD(total), thr(total), rad(total), pendA(total), pendB(total), fh0(total), fh1(total), fh2(total), fh3(total),
+    std::vector<f4> rayO(total), rayD(total), thr(total), rad(total), pendA(total), pendB(total), fh0(total), fh1(total), fh2(total),
         pay0(total), pay1(total), pay2(total), pay3(total), shO(size_t(total) * 2), shD(size_t(total) * 2);
     std::vector<ohb_hit> hit(total); std::vector<u4> meta(total); std::vector<uint32_t> qa(total), qb(total), qs(total);
     uint32_t small[4] = {0, 0, 0, 0}, sortCount[2] = {0, 0}; unsigned long long counters[8] = {0};
@@ -323,7 +323,7 @@ int emul_render_realtime(void* h, emul_rt_args* a) {
     std::vector<uint32_t> ldr(npx);
     PathArrays P{};
     P.rayO = rayO.data(); P.rayD = rayD.data(); P.hit = hit.data(); P.thr = thr.data(); P.rad = rad.data(); P.pendA = pendA.data(); P.pendB = pendB.data(); P.meta = meta.data();
-    P.fh0 = fh0.data(); P.fh1 = fh1.data(); P.fh2 = fh2.data(); P.fh3 = fh3.data(); P.pay0 = pay0.data(); P.pay1 = pay1.data(); P.pay2 = pay2.data(); P.pay3 = pay3.data();
+    P.fh0 = fh0.data(); P.fh1 = fh1.data(); P.fh2 = fh2.data(); P.pay0 = pay0.data(); P.pay1 = pay1.data(); P.pay2 = pay2.data(); P.pay3 = pay3.data();
     P.shO = shO.data(); P.shD = shD.data(); P.queueIn = qa.data(); P.queueOut = qb.data(); P.queueSorted = qs.data(); P.sortCount = sortCount;
     P.countIn = &small[0]; P.countOut = &small[1]; P.shCount = &small[2]; P.counters = counters;
     P.albedoAOV = reinterpret_cast<f4*>(a->albedo); P.normalAOV = reinterpret_cast<f4*>(a->normal);
