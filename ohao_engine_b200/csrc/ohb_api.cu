@@ -570,8 +570,9 @@ int ohb_render(ohb_ctx* c, const float view[16], const float proj[16], uint32_t 
     if (c->settings.profile == OHB_PROFILE_REALTIME) return renderRealtime(c, view, proj, nsamples);
     FrameParams fr{}; fillFrameCommon(c, view, proj, fr);
     uint32_t tilesX = (c->tileW + 7u) / 8u, tilesY = (c->tileH + 3u) / 4u;
+    if (uint64_t(tilesX) * tilesY * 32u > (1ull << 28)) OHB_FAIL(c, "ohb_render: more than 2^28 pixels in one tile (queue entries hold a 28-bit path index): render in tiles with ohb_set_tile");
     uint32_t numPixels = tilesX * tilesY * 32u;
-    static const uint32_t maxPaths = []() { const char* e = getenv("OHB_MAX_PATHS"); uint32_t v = e ? uint32_t(strtoul(e, nullptr, 10)) : 0u; return v ? v : (32u << 20); }();
+    static const uint32_t maxPaths = []() { const char* e = getenv("OHB_MAX_PATHS"); uint32_t v = e ? uint32_t(strtoul(e, nullptr, 10)) : 0u; return v ? std::min(v, 1u << 28) : (32u << 20); }();   // queue entries hold a 28-bit path index (OHB_Q_PATH)
     uint32_t spb = std::max(1u, std::min(nsamples, maxPaths / std::max(numPixels, 1u)));
     if (ensurePaths(c, numPixels * spb)) return 1;
     CU(c, c->sobolTab.reserve(size_t(spb) * 16));
