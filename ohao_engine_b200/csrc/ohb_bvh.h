@@ -12,8 +12,8 @@
 //   -> bottom-up sweep (atomic visit counters): AABB refit + triangle counts + SAH cost
 //   -> 3 passes of SAH treelet restructuring (7-leaf treelets, gamma = 7, 14, 28; Karras & Aila 2013)
 //   -> top-down collapse, one launch per level: greedy 8-wide nodes (subtrees of <= 3 triangles become leaf
-//      children), octant slot assignment, 8-bit outward quantisation -> 80-B nodes + 48-B triangles,
-//      every subtree's triangles contiguous.
+//      children), octant slot assignment, bf16 outward-rounded plane offsets -> 128-B nodes + 48-B transposed
+//      triangles, every subtree's triangles contiguous.
 #pragma once
 #include "ohb_traverse.h"
 
@@ -39,7 +39,7 @@ struct BuildArrays {
     uint32_t* wideCounters;                  // 4 : {wide nodes allocated, items of level A, items of level B, -}
     float* sah;                              // 2 : {wide-node area sum, leaf area*count sum}
     // outputs
-    u4* wnodes; f4* tris;                    // 5 x u4 per wide node (ohb_traverse.h), 3 x f4 per triangle
+    u4* wnodes; f4* tris;                    // 8 x u4 per wide node, 3 x f4 (transposed) per triangle (ohb_traverse.h)
 };
 
 OHB_HD uint32_t floatOrdered(float f) { uint32_t u = f2u(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
@@ -297,22 +297,13 @@ OHB_HD void padBox(f3& lo, f3& hi) {
 // a binary node: the child with the largest surface area that still holds more than OHB_MAX_LEAF triangles
 // is replaced by its two children until 8 children exist or only leaf-sized subtrees remain.  Children are
 // placed in the 8 slots so that (slot ^ ray octant) approximates a front-to-back order (greedy assignment on
-// dot(child centre - node centre, octant sign), Ylitie et al. 2017 §3.2).  Child boxes are quantised outward
-// to 8 bits on the node's own power-of-two grid; the rounding is verified in fp64.
+// dot(child centre - node centre, octant sign), Ylitie et al. 2017 §3.2).  Child planes are stored as bf16 offsets
+// from the node's min corner, rounded outward; the rounding is verified in fp64.
 // Triangle layout: a node's leaf triangles first (<= 24, slot order), then the block of each inner child in
 // slot order — every subtree is one contiguous range, computed top-down from the subtree triangle counts.
 // ---------------------------------------------------------------------------------------------
 struct WideItem { int32_t bvh2; uint32_t wide, triStart, pad; };
 
-OHB_HD float exp2i(int e) { return u2f(uint32_t(e + 127) << 23); }     // -126 <= e <= 127
-// smallest-ish e with 255 * 2^e >= ext (any e that satisfies the fp64 check of the caller is valid)
-OHB_HD int gridExponent(float ext) {
-    float v = ext / 255.0f;
-    int e = int((f2u(v) >> 23) & 0xFFu) - 127 + 1;
-    if (!(v > 0.0f) || e < -100) e = -100;
-    if (e > 126) e = 126;
-    return e;
-}
 // append the triangles of the leaf-sized binary subtree `c` to the triangle array, returns how many
 OHB_HD uint32_t emitLeafTris(const BuildArrays& b, int c, uint32_t dst) {
     int st[4]; int sp = 0; st[sp++] = c; uint32_t k = 0;
@@ -320,9 +311,11 @@ OHB_HD uint32_t emitLeafTris(const BuildArrays& b, int c, uint32_t dst) {
         int x = st[--sp];
         if (x < 0) {
             uint32_t a = b.vals[~x];
-            b.tris[size_t(dst + k) * 3 + 0] = b.wtri[size_t(a) * 3 + 0];
-            b.tris[size_t(dst + k) * 3 + 1] = b.wtri[size_t(a) * 3 + 1];
-            b.tris[size_t(dst + k) * 3 + 2] = b.wtri[size_t(a) * 3 + 2];
+            // transposed record (x0 x1 x2 id)(y0 y1 y2 id)(z0 z1 z2 id): the ray's axis permutation becomes a row address
+            const f4 v0 = b.wtri[size_t(a) * 3 + 0], v1 = b.wtri[size_t(a) * 3 + 1], v2 = b.wtri[size_t(a) * 3 + 2];
+            b.tris[size_t(dst + k) * 3 + 0] = mk4(v0.x, v1.x, v2.x, v0.w);
+            b.tris[size_t(dst + k) * 3 + 1] = mk4(v0.y, v1.y, v2.y, v0.w);
+            b.tris[size_t(dst + k) * 3 + 2] = mk4(v0.z, v1.z, v2.z, v0.w);
             k++;
         } else { st[sp++] = b.right[x]; st[sp++] = b.left[x]; }
     }
@@ -374,28 +367,35 @@ OHB_HD void emitWideNode(const BuildArrays& b, const WideItem& it, WideItem* out
         }
         slotOf[bk] = bs; childAt[bs] = bk;
     }
-    // quantisation grid
-    int e[3] = {gridExponent(nhi.x - nlo.x), gridExponent(nhi.y - nlo.y), gridExponent(nhi.z - nlo.z)};
-    uint32_t qlo[3][8], qhi[3][8];
+    // bf16 plane offsets from the node's min corner p, rounded outward and verified in fp64 against the padded child
+    // boxes.  p sits a second pad below the node box, so every lo offset is >= 1e-30: far above the < 9.2e-41 of junk
+    // the even slot's bits add below an odd slot's bf16 when the traversal uses the whole word as the fp32 operand.
+    float pmin[3]; uint32_t qlo[3][8], qhi[3][8]; float extMax = 0.0f;
     for (int ax = 0; ax < 3; ax++) {
-        const double p = double(comp(nlo, ax));
-        for (;;) {
-            bool ok = true; const double step = double(exp2i(e[ax]));
-            for (int s = 0; s < 8; s++) {
-                int k = childAt[s];
-                if (k < 0) { qlo[ax][s] = 255u; qhi[ax][s] = 0u; continue; }
-                const double l = double(comp(lo[k], ax)), h = double(comp(hi[k], ax));
-                double ql = floor((l - p) / step), qh = ceil((h - p) / step);
-                while (ql > 0.0 && p + ql * step > l) ql -= 1.0;
-                while (p + qh * step < h) qh += 1.0;
-                if (ql < 0.0) ql = 0.0;
-                if (qh > 255.0) { ok = false; break; }
-                qlo[ax][s] = uint32_t(ql); qhi[ax][s] = uint32_t(qh);
-            }
-            if (ok) break;
-            e[ax]++;
+        const float nl = comp(nlo, ax);
+        const float pf = nl - (fabsf(nl) * 9.5367431640625e-7f + 1e-30f);
+        pmin[ax] = pf;
+        const double p = double(pf);
+        extMax = fmaxf(extMax, float((double(comp(nhi, ax)) - p) * 1.000001));
+        for (int s = 0; s < 8; s++) {
+            int k = childAt[s];
+            if (k < 0) { qlo[ax][s] = OHB_EMPTY_LO; qhi[ax][s] = 0u; continue; }
+            const double l = double(comp(lo[k], ax)), h = double(comp(hi[k], ax));
+            uint32_t ql = f2u(float(l - p)) >> 16;                       // truncation = round toward zero (the offset is positive)
+            while (ql > 0u && p + double(u2f(ql << 16)) > l) ql--;
+            uint32_t fh = f2u(float(h - p)), qh = (fh >> 16) + ((fh & 0xFFFFu) ? 1u : 0u);
+            while (p + double(u2f(qh << 16)) < h) qh++;
+            qlo[ax][s] = ql; qhi[ax][s] = qh;
+        }
+        // odd slots of the lo planes are read as the whole word: bf16 << 16 | (even slot's bf16)
+        for (int s = 1; s < 8; s += 2) {
+            int k = childAt[s];
+            if (k < 0) continue;
+            const double l = double(comp(lo[k], ax));
+            while (qlo[ax][s] > 0u && p + double(u2f((qlo[ax][s] << 16) | qlo[ax][s - 1])) > l) qlo[ax][s]--;
         }
     }
+    uint32_t ext16 = (f2u(extMax) >> 16) + 1u;
     // children: inner ones get consecutive wide-node indices in slot order, leaves their triangle offsets
     uint32_t imask = 0u, numInner = 0u;
     for (int s = 0; s < 8; s++) { int k = childAt[s]; if (k >= 0 && cnt[k] > OHB_MAX_LEAF) { imask |= 1u << s; numInner++; } }
@@ -423,15 +423,15 @@ OHB_HD void emitWideNode(const BuildArrays& b, const WideItem& it, WideItem* out
         rank++; sub += cnt[k];
     }
     auto pack4 = [](const uint32_t* v) { return v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24); };
-    u4 w0, w1, w2, w3, w4;
-    w0.x = f2u(nlo.x); w0.y = f2u(nlo.y); w0.z = f2u(nlo.z);
-    w0.w = uint32_t(e[0] + 127) | (uint32_t(e[1] + 127) << 8) | (uint32_t(e[2] + 127) << 16) | (imask << 24);
+    auto pack8 = [](const uint32_t* v) { u4 r; r.x = v[0] | (v[1] << 16); r.y = v[2] | (v[3] << 16); r.z = v[4] | (v[5] << 16); r.w = v[6] | (v[7] << 16); return r; };
+    u4 w0, w1;
+    w0.x = f2u(pmin[0]); w0.y = f2u(pmin[1]); w0.z = f2u(pmin[2]);
+    w0.w = imask | (ext16 << 16);
     w1.x = childBase; w1.y = it.triStart; w1.z = pack4(meta); w1.w = pack4(meta + 4);
-    w2.x = pack4(qlo[0]); w2.y = pack4(qlo[0] + 4); w2.z = pack4(qlo[1]); w2.w = pack4(qlo[1] + 4);
-    w3.x = pack4(qlo[2]); w3.y = pack4(qlo[2] + 4); w3.z = pack4(qhi[0]); w3.w = pack4(qhi[0] + 4);
-    w4.x = pack4(qhi[1]); w4.y = pack4(qhi[1] + 4); w4.z = pack4(qhi[2]); w4.w = pack4(qhi[2] + 4);
     u4* np = b.wnodes + size_t(it.wide) * OHB_WNODE_VECS;
-    np[0] = w0; np[1] = w1; np[2] = w2; np[3] = w3; np[4] = w4;
+    const uint32_t swz = OHB_NODE_SWZ(it.wide);                  // bank swizzle of the four 32-B pieces (ohb_traverse.h)
+    np[2u * (0u ^ swz)] = w0; np[2u * (0u ^ swz) + 1u] = w1;
+    for (uint32_t ax = 0; ax < 3; ax++) { np[2u * ((1u + ax) ^ swz)] = pack8(qlo[ax]); np[2u * ((1u + ax) ^ swz) + 1u] = pack8(qhi[ax]); }
 }
 
 }  // namespace ohb

@@ -268,6 +268,7 @@ static TraceKnobs traceKnobs() {
         auto geti = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
         TraceKnobs r; r.minActive = geti("OHB_TRACE_MIN_ACTIVE", 20); r.postponeDen = geti("OHB_POSTPONE_DEN", OHB_POSTPONE_DEN_DEFAULT);
         if (r.postponeDen == 1) r.postponeDen = 2;      // 1 would postpone every triangle forever; 0 = never postpone
+        r.postponeDen = (r.postponeDen & 0xFF) | (geti("OHB_TRACE_PREFETCH", 0) << 8);      // prefetch mode rides in bits 8.. (travRun)
         return r;
     }();
     return k;
@@ -307,8 +308,9 @@ struct PathClosestIO {
     }
     __device__ __forceinline__ void store(uint32_t i, Trav& t) {
         uint32_t p = OHB_Q_PATH(P.queueIn[i]);
-        bool hit = t.best.prim != OHB_MISS;
-        reinterpret_cast<float4*>(P.hit)[p] = make_float4(hit ? t.best.t : -1.0f, t.best.u, t.best.v, __uint_as_float(t.best.prim));
+        const ohb_hit h = travResult(t);
+        const bool hit = h.prim != OHB_MISS;
+        reinterpret_cast<float4*>(P.hit)[p] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
         P.hitFlag[i] = hit ? 1u : 0u;
         hits += hit;
     }
@@ -337,24 +339,26 @@ __global__ void __launch_bounds__(TRACE_THREADS, MINB) k_trace_shadow(SceneDev s
     PathShadowIO io{P};
     persistentTrace<true>(sc, *P.shCount, work, io, minActive, postponeDen);
 }
-// resident CTAs per SM the traversal kernels are compiled for: 8 -> 64 registers, 9 -> 56, 10 -> 48, 12 -> 40, 16 -> 32.
-// 9 is the measured optimum with the 8-wide BVH (profiles/r1f_sweep.txt, r1g_sweep.txt).
+// resident CTAs per SM the traversal kernels are compiled for: 5 -> 96 registers, 6 -> 80, 7 -> 72, 8 -> 64, 9 -> 56, 10 -> 48.
+#ifndef OHB_TRACE_OCC_DEFAULT
+#define OHB_TRACE_OCC_DEFAULT 8
+#endif
 static int traceOcc() {
-    static const int v = []() { const char* e = getenv("OHB_TRACE_OCC"); int o = e ? atoi(e) : 9; return o >= 16 ? 16 : (o >= 12 ? 12 : (o >= 10 ? 10 : (o >= 9 ? 9 : 8))); }();
+    static const int v = []() { const char* e = getenv("OHB_TRACE_OCC"); int o = e ? atoi(e) : OHB_TRACE_OCC_DEFAULT; return o >= 10 ? 10 : (o <= 5 ? 5 : o); }();
     return v;
 }
 static void launchTraceClosest(unsigned smGrid8, const SceneDev& sc, const PathArrays& P, uint32_t* work, cudaStream_t st) {
     const int o = traceOcc(); const unsigned grid = smGrid8 / 8u * unsigned(o);
     const TraceKnobs k = traceKnobs();
 #define OHB_LAUNCH_TC(OCC) k_trace_closest<OCC><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work, k.minActive, k.postponeDen)
-    if (o == 16) OHB_LAUNCH_TC(16); else if (o == 12) OHB_LAUNCH_TC(12); else if (o == 10) OHB_LAUNCH_TC(10); else if (o == 9) OHB_LAUNCH_TC(9); else OHB_LAUNCH_TC(8);
+    if (o == 10) OHB_LAUNCH_TC(10); else if (o == 9) OHB_LAUNCH_TC(9); else if (o == 8) OHB_LAUNCH_TC(8); else if (o == 7) OHB_LAUNCH_TC(7); else if (o == 6) OHB_LAUNCH_TC(6); else OHB_LAUNCH_TC(5);
 #undef OHB_LAUNCH_TC
 }
 static void launchTraceShadow(unsigned smGrid8, const SceneDev& sc, const PathArrays& P, uint32_t* work, cudaStream_t st) {
     const int o = traceOcc(); const unsigned grid = smGrid8 / 8u * unsigned(o);
     const TraceKnobs k = traceKnobs();
 #define OHB_LAUNCH_TS(OCC) k_trace_shadow<OCC><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work, k.minActive, k.postponeDen)
-    if (o == 16) OHB_LAUNCH_TS(16); else if (o == 12) OHB_LAUNCH_TS(12); else if (o == 10) OHB_LAUNCH_TS(10); else if (o == 9) OHB_LAUNCH_TS(9); else OHB_LAUNCH_TS(8);
+    if (o == 10) OHB_LAUNCH_TS(10); else if (o == 9) OHB_LAUNCH_TS(9); else if (o == 8) OHB_LAUNCH_TS(8); else if (o == 7) OHB_LAUNCH_TS(7); else if (o == 6) OHB_LAUNCH_TS(6); else OHB_LAUNCH_TS(5);
 #undef OHB_LAUNCH_TS
 }
 #define SHADE_THREADS 128
@@ -622,7 +626,7 @@ struct HookIO {
         ohb_ray r = rays[i]; o = mk3(r.origin[0], r.origin[1], r.origin[2]); d = mk3(r.dir[0], r.dir[1], r.dir[2]); tmin = r.tmin; tmax = r.tmax;
     }
     __device__ __forceinline__ void store(uint32_t i, Trav& t) {
-        if (hits) { ohb_hit h = t.best; if (h.prim == OHB_MISS) h.t = -1.0f; hits[i] = h; }
+        if (hits) hits[i] = travResult(t);
         else occ[i] = t.anyHit ? 1 : 0;
     }
 };

@@ -132,8 +132,9 @@ void buildBvh(Scene& s);
 
 // ---------------------------------------------------------------------------------------------
 // Ray / triangle.  The arithmetic below is the SPEC both the oracle and the CUDA kernels follow
-// (DESIGN.md "Intersection arithmetic"): Woop-Benthin-Wald watertight test, fp32, one rounding
-// per operation (no FMA contraction), fp64 fallback for zero edge functions, two-sided,
+// (DESIGN.md "Intersection arithmetic"): Woop-Benthin-Wald watertight test, fp32, a fixed operation
+// order (explicit IEEE fma in the shear and in T, two products + one subtraction in the edge
+// functions, nothing contracted by the compiler), fp64 fallback for zero edge functions, two-sided,
 // accept tmin < t < tmax, ties on t resolved toward the lower global triangle id.
 // The traversal itself lives in the Vulkan driver for the reference (traceRayEXT,
 // pt_raygen_offline.rgen:198); there is no reference source to follow for it.
@@ -163,9 +164,12 @@ static inline RayPrep prepRay(V3 o, V3 d, float tmin) {
 static inline bool intersectTri(const RayPrep& r, V3 p0, V3 p1, V3 p2, float tmax, float& t, float& bu, float& bv) {
     V3 A = p0 - r.o, B = p1 - r.o, C = p2 - r.o;
     float Akz = get(A, r.kz), Bkz = get(B, r.kz), Ckz = get(C, r.kz);
-    float Ax = get(A, r.kx) - r.Sx * Akz, Ay = get(A, r.ky) - r.Sy * Akz;
-    float Bx = get(B, r.kx) - r.Sx * Bkz, By = get(B, r.ky) - r.Sy * Bkz;
-    float Cx = get(C, r.kx) - r.Sx * Ckz, Cy = get(C, r.ky) - r.Sy * Ckz;
+    // shear: ONE rounding per coordinate (IEEE fma); a per-vertex function, so shared vertices stay shared
+    float Ax = std::fmaf(-r.Sx, Akz, get(A, r.kx)), Ay = std::fmaf(-r.Sy, Akz, get(A, r.ky));
+    float Bx = std::fmaf(-r.Sx, Bkz, get(B, r.kx)), By = std::fmaf(-r.Sy, Bkz, get(B, r.ky));
+    float Cx = std::fmaf(-r.Sx, Ckz, get(C, r.kx)), Cy = std::fmaf(-r.Sy, Ckz, get(C, r.ky));
+    // edge functions: two rounded products and one subtraction, NEVER an fma — rn(a*b) - rn(c*d) changes sign exactly
+    // when the shared edge is seen from the neighbouring triangle, which is what makes the test watertight
     float U = Cx * By - Cy * Bx;
     float V = Ax * Cy - Ay * Cx;
     float W = Bx * Ay - By * Ax;
@@ -177,8 +181,7 @@ static inline bool intersectTri(const RayPrep& r, V3 p0, V3 p1, V3 p2, float tma
     if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
     float det = (U + V) + W;
     if (det == 0.0f) return false;
-    float Az = r.Sz * Akz, Bz = r.Sz * Bkz, Cz = r.Sz * Ckz;
-    float T = (U * Az + V * Bz) + W * Cz;
+    float T = std::fmaf(W, Ckz, std::fmaf(V, Bkz, U * Akz)) * r.Sz;
     float tt = T / det;
     if (!(tt > r.tmin && tt < tmax)) return false;
     t = tt; bu = V / det; bv = W / det;

@@ -131,7 +131,55 @@ void* emul_scene_create(const emul_scene_desc* d) {
         for (uint32_t i = 0; i < n; i++) { k2[i] = keys[order[i]]; v2[i] = vals[order[i]]; }
         keys.swap(k2); vals.swap(v2); b.keys = keys.data(); b.vals = vals.data();
     }
-    if (n >= 2) {
+    if (n >= 2 && getenv("EMUL_SAH_BUILD")) {
+        // EXPERIMENT (tree-quality ceiling): top-down binned SAH over all three axes instead of the Karras hierarchy; the
+        // product's refit sweep, treelet passes and 8-wide collapse then run on this topology unchanged.
+        struct Bx { f3 lo, hi; };
+        auto grow = [](Bx& a, f3 lo, f3 hi) { a.lo = vmin(a.lo, lo); a.hi = vmax(a.hi, hi); };
+        auto area = [](const Bx& a) { f3 e = a.hi - a.lo; return e.x < 0 ? 0.0f : 2.0f * (e.x * e.y + e.y * e.z + e.z * e.x); };
+        std::vector<uint32_t> ord(n); std::iota(ord.begin(), ord.end(), 0u);       // positions -> prim index (becomes vals)
+        std::vector<f3> cen(n); for (uint32_t i = 0; i < n; i++) cen[i] = (xyz(primLo[i]) + xyz(primHi[i])) * 0.5f;
+        int nextNode = 0;
+        struct Job { uint32_t first, count; int node; };
+        std::vector<Job> jobs; jobs.push_back({0, n, nextNode++}); pin[0] = -1;
+        const int NB = 32;
+        while (!jobs.empty()) {
+            Job j = jobs.back(); jobs.pop_back();
+            Bx cb{mk3(3e38f), mk3(-3e38f)};
+            for (uint32_t i = j.first; i < j.first + j.count; i++) grow(cb, cen[ord[i]], cen[ord[i]]);
+            float best = 3e38f; int bAxis = -1, bk = -1;
+            for (int ax = 0; ax < 3; ax++) {
+                float cmin = comp(cb.lo, ax), cext = comp(cb.hi, ax) - cmin; if (!(cext > 0)) continue;
+                Bx bb[NB]; int bc[NB]; for (int k = 0; k < NB; k++) { bb[k] = Bx{mk3(3e38f), mk3(-3e38f)}; bc[k] = 0; }
+                for (uint32_t i = j.first; i < j.first + j.count; i++) { uint32_t t = ord[i]; int k = std::min(NB - 1, int(NB * ((comp(cen[t], ax) - cmin) / cext))); grow(bb[k], xyz(primLo[t]), xyz(primHi[t])); bc[k]++; }
+                float lA[NB], rA[NB]; int lC[NB], rC[NB]; Bx acc{mk3(3e38f), mk3(-3e38f)}; int c = 0;
+                for (int k = 0; k < NB; k++) { grow(acc, bb[k].lo, bb[k].hi); c += bc[k]; lA[k] = area(acc); lC[k] = c; }
+                acc = Bx{mk3(3e38f), mk3(-3e38f)}; c = 0;
+                for (int k = NB - 1; k >= 0; k--) { grow(acc, bb[k].lo, bb[k].hi); c += bc[k]; rA[k] = area(acc); rC[k] = c; }
+                for (int k = 0; k < NB - 1; k++) { if (!lC[k] || !rC[k + 1]) continue; float cost = lA[k] * lC[k] + rA[k + 1] * rC[k + 1]; if (cost < best) { best = cost; bAxis = ax; bk = k; } }
+            }
+            uint32_t mid = j.first + j.count / 2;
+            if (bAxis >= 0) {
+                float cmin = comp(cb.lo, bAxis), cext = comp(cb.hi, bAxis) - cmin;
+                auto it = std::partition(ord.begin() + j.first, ord.begin() + j.first + j.count, [&](uint32_t t) { return std::min(NB - 1, int(NB * ((comp(cen[t], bAxis) - cmin) / cext))) <= bk; });
+                mid = uint32_t(it - ord.begin());
+            }
+            if (mid == j.first || mid == j.first + j.count) mid = j.first + j.count / 2;
+            uint32_t cnts[2] = {mid - j.first, j.first + j.count - mid}, firsts[2] = {j.first, mid}; int ch[2];
+            for (int h = 0; h < 2; h++) {
+                if (cnts[h] == 1) { ch[h] = ~int(firsts[h]); pleaf[firsts[h]] = j.node; }
+                else { ch[h] = nextNode++; pin[ch[h]] = j.node; jobs.push_back({firsts[h], cnts[h], ch[h]}); }
+            }
+            left[j.node] = ch[0]; right[j.node] = ch[1];
+        }
+        for (uint32_t i = 0; i < n; i++) vals[i] = ord[i];
+        for (uint32_t i = 0; i < n; i++) sweepFromLeaf(b, i, 0u);
+        const char* tp = getenv("OHB_TREELET_PASSES"); uint32_t passes = tp ? uint32_t(atoi(tp)) : 3u;
+        for (uint32_t pass = 0, gamma = OHB_TREELET_LEAVES; pass < passes; pass++, gamma *= 2u) {
+            std::fill(visit.begin(), visit.end(), 0u);
+            for (uint32_t i = 0; i < n; i++) sweepFromLeaf(b, i, gamma);
+        }
+    } else if (n >= 2) {
         for (uint32_t i = 0; i + 1 < n; i++) buildHierarchyNode(b, int(i));
         for (uint32_t i = 0; i < n; i++) sweepFromLeaf(b, i, 0u);
         const char* tp = getenv("OHB_TREELET_PASSES"); uint32_t passes = tp ? uint32_t(atoi(tp)) : 3u;
