@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <cfloat>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -89,6 +90,7 @@ enum class LightType { Sphere = 0, Directional = 1, Spot = 2, AreaRect = 3 };
 struct Light { LightType type = LightType::Sphere; vec3 color{1, 1, 1}; float intensity = 1.0f, radius = 0.5f; vec3 direction{0, -1, 0}; float innerCone = 30, outerCone = 45; vec3 edge1{1, 0, 0}, edge2{0, 0, 1}; };
 struct Actor {
     std::string name; vec3 position{0, 0, 0}, scale{1, 1, 1}; bool visible = true;
+    bool yaw180 = false;             // TransformComponent rotation quat(radians(0, 180, 0)) — the only rotation the examples set (turntable.cpp:133)
     std::shared_ptr<Model> model; Material material; bool hasLight = false; Light light;
 };
 class Scene {
@@ -167,12 +169,48 @@ inline void packLight(const Actor& a, uint8_t* out) {     // GPULight, 80 B (ren
     else v[15] = l.outerCone;
     std::memcpy(out, v, 80);
 }
-inline void packLights(SceneArrays& a, bool haveEnv, float envIntensity) {    // light_upload.cpp:254-283
-    size_t n = a.lightActors.size();
+// One auto-generated sphere light per mesh actor whose material has an emissive texture (light_upload.cpp:183-247):
+// centre = world position of the model's bounding-box centre, radius = 0.3 x |bbox diagonal| (object space, like the
+// reference), colour = mean of the "bright" texels (luminance > 0.05), intensity = min(0.1 x summed luminance, 20).
+inline bool emissiveMeshLight(const Actor& act, uint8_t* out) {
+    const Image8& e = act.material.emissiveTex;
+    if (!act.model || e.empty()) return false;
+    vec3 bmin{FLT_MAX, FLT_MAX, FLT_MAX}, bmax{-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (const Vertex& v : act.model->vertices) {
+        bmin = vec3{std::min(bmin.x, v.position[0]), std::min(bmin.y, v.position[1]), std::min(bmin.z, v.position[2])};
+        bmax = vec3{std::max(bmax.x, v.position[0]), std::max(bmax.y, v.position[1]), std::max(bmax.z, v.position[2])};
+    }
+    const vec3 mid{(bmin.x + bmax.x) * 0.5f, (bmin.y + bmax.y) * 0.5f, (bmin.z + bmax.z) * 0.5f}, d{bmax.x - bmin.x, bmax.y - bmin.y, bmax.z - bmin.z};
+    const float ry = act.yaw180 ? -1.0f : 1.0f;
+    const vec3 center{ry * act.scale.x * mid.x + act.position.x, act.scale.y * mid.y + act.position.y, ry * act.scale.z * mid.z + act.position.z};
+    const float radius = std::sqrt(dot(d, d)) * 0.3f;
+    double r = 0, g = 0, b = 0; int bright = 0; float power = 0.0f;
+    for (size_t p = 0; p < size_t(e.w) * e.h; p++) {
+        const float pr = e.rgba[p * 4 + 0] / 255.0f, pg = e.rgba[p * 4 + 1] / 255.0f, pb = e.rgba[p * 4 + 2] / 255.0f;
+        const float lum = pr * 0.2126f + pg * 0.7152f + pb * 0.0722f;
+        if (lum > 0.05f) { r += pr; g += pg; b += pb; bright++; power += lum; }
+    }
+    if (!(power > 0.1f)) return false;
+    float v[20] = {0};
+    v[0] = center.x; v[1] = center.y; v[2] = center.z; v[3] = 0.0f;                                   // sphere
+    v[4] = bright ? float(r / bright) : 1.0f; v[5] = bright ? float(g / bright) : 1.0f; v[6] = bright ? float(b / bright) : 1.0f;
+    v[7] = std::min(power * 0.1f, 20.0f);
+    v[8] = 0.0f; v[9] = -1.0f; v[10] = 0.0f; v[11] = radius;
+    std::memcpy(out, v, 80);
+    return true;
+}
+inline void packLights(SceneArrays& a, bool haveEnv, float envIntensity) {    // light_upload.cpp:153-283
+    std::vector<uint8_t> recs(a.lightActors.size() * 80);
+    for (size_t i = 0; i < a.lightActors.size(); i++) packLight(*a.lightActors[i], recs.data() + i * 80);
+    for (Actor* m : a.meshActors) {                                             // after the explicit lights, in actor order
+        uint8_t rec[80];
+        if (emissiveMeshLight(*m, rec)) recs.insert(recs.end(), rec, rec + 80);
+    }
+    const size_t n = recs.size() / 80;
     a.lightSSBO.assign(16 + n * 80, 0xFF);
     uint32_t cnt = uint32_t(n); std::memcpy(a.lightSSBO.data(), &cnt, 4); std::memcpy(a.lightSSBO.data() + 8, &envIntensity, 4);
     if (haveEnv && n > 0) { uint32_t idx = a.layers; std::memcpy(a.lightSSBO.data() + 4, &idx, 4); }    // env only wired when >= 1 light exists (Q13)
-    for (size_t i = 0; i < n; i++) packLight(*a.lightActors[i], a.lightSSBO.data() + 16 + i * 80);
+    if (n) std::memcpy(a.lightSSBO.data() + 16, recs.data(), recs.size());
 }
 inline void packMaterials(SceneArrays& a, const std::vector<std::array<int, 4>>& layerIdx) {   // rt_build.cpp:188-389
     a.matColors.clear();
@@ -203,7 +241,8 @@ inline PackedScene packScene(Scene& scene, bool haveEnv, float envIntensity) {
         for (uint32_t i : m.indices) a.indices.push_back(i + voff);
         a.matIds.insert(a.matIds.end(), nt, mi);
         ohb_instance in{}; in.first_tri = toff; in.tri_count = nt; in.mask = 0xFF;
-        float x[12] = {act->scale.x, 0, 0, act->position.x, 0, act->scale.y, 0, act->position.y, 0, 0, act->scale.z, act->position.z};
+        const float ry = act->yaw180 ? -1.0f : 1.0f;                       // T * R_y(180) * S
+        float x[12] = {ry * act->scale.x, 0, 0, act->position.x, 0, act->scale.y, 0, act->position.y, 0, 0, ry * act->scale.z, act->position.z};
         std::memcpy(in.xform, x, 48);
         a.instances.push_back(in);
         auto layer = [&](const Image8& t) -> int { if (t.empty()) return -1; layers.push_back(t); return int(layers.size()) - 1; };

@@ -179,6 +179,12 @@ int ohb_synchronize(ohb_ctx*);
 void*  ohb_accum_dev_ptr(ohb_ctx*, size_t* bytes);
 int    ohb_set_accum_mode(ohb_ctx*, int sum_mode);
 int    ohb_resolve(ohb_ctx*);   /* sum mode: divide by count + tonemap into the LDR image */
+/* Zero the accumulation image.  A sum-mode render only overwrites the pixels of the tiles it renders
+ * (history 0) and adds to them afterwards; a context reused for a second sharded image must start from
+ * zero, or pixels outside this rank's tiles would carry the previous image into the next reduce.  (The
+ * Vulkan path has no counterpart: PathTracer::resetAccumulation relies on frame 0 overwriting the
+ * whole image, path_tracer.cpp:189-211.) */
+int    ohb_clear_accum(ohb_ctx*);
 
 /* ---- parity / measurement hooks ---------------------------------------------------------- */
 /* Closest-hit and any-hit queries on caller-supplied rays (host buffers, copies included). */
@@ -195,7 +201,7 @@ int ohb_get_timing(ohb_ctx*, float* trace_ms, float* shade_ms, float* total_ms);
 int ohb_enable_timing(ohb_ctx*, int enable);
 /* Per-category device time and launch count: [0] closest-hit traversal, [1] bounce (raygen body: NEE, MIS,
  * lobe sampling), [2] any-hit traversal, [3] film, [4] surface (closest-hit / miss shaders), [5] realtime per-pixel pass
- * (ReSTIR GI + EMA), [6] SVGF denoiser, [7] reserved. */
+ * (ReSTIR GI + EMA), [6] SVGF denoiser, [7] hit/miss queue sort (k_sort_hits). */
 int ohb_get_timing_detail(ohb_ctx*, float ms[8], uint64_t launches[8]);
 /* Realtime-profile parity hooks.  ohb_set_realtime_dump: the next ohb_render also copies, per pixel, the N-spp mean
  * radiance after the x0.75 clamp (pt_raygen_realtime.rgen:1552-1556), the diffuse ReSTIR GI term (:1755-1764) and the

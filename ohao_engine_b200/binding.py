@@ -20,6 +20,7 @@ PROFILE_OFFLINE, PROFILE_REALTIME = 0, 1
 DENOISE_NONE, DENOISE_ATROUS = 0, 4      # DenoiseMode values (denoise_types.hpp:13-19)
 FLAG_AOVS, FLAG_INTERNAL_DENOISE, FLAG_FIREFLY = 1, 2, 4
 FLAG_GOLDEN_COMPAT = 1 << 16
+SAMPLER_PCG, SAMPLER_SOBOL = 0, 1             # GLSL SAMPLER_PCG / SAMPLER_SOBOL (sampler_api.glsl:12-13)
 
 RAY_DTYPE = np.dtype([("origin", "<f4", (3,)), ("tmin", "<f4"), ("dir", "<f4", (3,)), ("tmax", "<f4")])
 HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4")])
@@ -73,7 +74,7 @@ ABI = {
     "ohb_synchronize": (_I, [_VP]),
     "ohb_accum_dev_ptr": (_VP, [_VP, C.POINTER(C.c_size_t)]),
     "ohb_set_accum_mode": (_I, [_VP, _I]),
-    "ohb_resolve": (_I, [_VP]),
+    "ohb_resolve": (_I, [_VP]), "ohb_clear_accum": (_I, [_VP]),
     "ohb_trace_batch": (_I, [_VP, _VP, _U32, _VP]),
     "ohb_occluded_batch": (_I, [_VP, _VP, _U32, _VP]),
     "ohb_set_sample_dump": (_I, [_VP, _VP, C.c_size_t]),
@@ -199,6 +200,7 @@ class Renderer:
     def set_tile(self, x0, y0, w, h): self._ck(self.lib.ohb_set_tile(self.h, x0, y0, w, h), "ohb_set_tile")
     def set_accum_mode(self, sum_mode: bool): self._ck(self.lib.ohb_set_accum_mode(self.h, int(sum_mode)), "ohb_set_accum_mode")
     def resolve(self): self._ck(self.lib.ohb_resolve(self.h), "ohb_resolve")
+    def clear_accum(self): self._ck(self.lib.ohb_clear_accum(self.h), "ohb_clear_accum")
     def resize(self, w, h):
         self._ck(self.lib.ohb_resize(self.h, w, h), "ohb_resize"); self.width, self.height = w, h
 
@@ -304,5 +306,5 @@ class Renderer:
     def timing(self) -> dict:
         ms = (C.c_float * 8)(); cnt = (C.c_uint64 * 8)()
         self._ck(self.lib.ohb_get_timing_detail(self.h, C.byref(ms), C.byref(cnt)), "ohb_get_timing_detail")
-        names = ("trace_closest", "bounce", "trace_shadow", "film", "surface", "rt_pixel", "svgf")
+        names = ("trace_closest", "bounce", "trace_shadow", "film", "surface", "rt_pixel", "svgf", "sort_hits")
         return {n: dict(ms=float(ms[i]), launches=int(cnt[i])) for i, n in enumerate(names)}

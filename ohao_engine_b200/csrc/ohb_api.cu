@@ -73,7 +73,7 @@ struct ohb_ctx {
     std::string err;
     uint64_t launches = 0;
     // scene (host metadata)
-    uint32_t nverts = 0, ntris = 0, nmat = 0; uint64_t posStride = 0;
+    uint32_t nverts = 0, ntris = 0, nmat = 0, maxMatId = 0; uint64_t posStride = 0;
     std::vector<ohb_instance> instances;
     uint32_t lightCount = 0, envMapTexIdx = 0xFFFFFFFFu; float envIntensity = 1.0f;
     uint32_t texW = 0, texH = 0, texLayers = 0, envW = 0, envH = 0; float envIntegral = 0.0f;
@@ -214,6 +214,9 @@ int ohb_set_geometry(ohb_ctx* c, const void* positions, size_t stride_bytes, uin
     if (ntris >= (1u << 29)) OHB_FAIL(c, "ohb_set_geometry: too many triangles (leaf refs hold 29 bits)");
     cudaSetDevice(c->device);
     for (size_t i = 0; i < size_t(ntris) * 3; i++) if (idx[i] >= nverts) OHB_FAIL(c, "ohb_set_geometry: index out of range");
+    uint32_t maxMat = 0u;
+    for (size_t i = 0; i < ntris; i++) maxMat = std::max(maxMat, mat_ids[i]);
+    c->maxMatId = maxMat;             // checked against the material count by ohb_set_materials / ohb_render (closest-hit reads matColors[matID*3..] unchecked)
     c->nverts = nverts; c->ntris = ntris; c->posStride = stride_bytes; c->accelValid = false;
     CU(c, c->positions.reserve(size_t(nverts) * stride_bytes)); CU(c, c->indices.reserve(size_t(ntris) * 12));
     CU(c, c->normals.reserve(size_t(nverts) * 16)); CU(c, c->uvs.reserve(size_t(nverts) * 8)); CU(c, c->matIds.reserve(size_t(ntris) * 4));
@@ -236,6 +239,7 @@ int ohb_set_instances(ohb_ctx* c, const ohb_instance* inst, uint32_t n) {
 int ohb_set_materials(ohb_ctx* c, const float* mc, uint32_t nmat) {
     if (!c) return 1;
     if (!mc || !nmat) OHB_FAIL(c, "ohb_set_materials: empty");
+    if (c->ntris && c->maxMatId >= nmat) OHB_FAIL(c, "ohb_set_materials: fewer material records than the geometry's material ids address");
     cudaSetDevice(c->device);
     c->nmat = nmat;
     CU(c, c->matColors.reserve(size_t(nmat) * 48));
@@ -300,7 +304,7 @@ int ohb_get_env_cdf(ohb_ctx* c, float* marg, float* cond, float* integral) {
 
 static void fillScene(ohb_ctx* c, SceneDev& s) {
     memset(&s, 0, sizeof(s));
-    s.wnodes = c->wnodes.as<u4>(); s.tris = c->tris.as<f4>(); s.numTris = c->accelValid ? c->numActive : 0u;
+    s.wnodes = c->wnodes.as<u4>(); s.tris = c->tris.as<f4>(); s.numTris = c->accelValid ? c->numActive : 0u; s.numWideNodes = c->accelValid ? c->stats.num_nodes : 0u;
     s.indices = c->indices.as<uint32_t>(); s.normals = c->normals.as<f4>(); s.uvs = c->uvs.as<f2>(); s.matIds = c->matIds.as<uint32_t>();
     s.triInst = c->triInst.as<uint32_t>(); s.instNormalMat = c->instNormalMat.as<f4>(); s.instInv = c->instInv.as<f4>();
     s.matColors = c->matColors.as<f4>();
@@ -314,6 +318,8 @@ static void fillScene(ohb_ctx* c, SceneDev& s) {
 int ohb_env_sample_batch(ohb_ctx* c, const float* u12, uint32_t n, float* dir_pdf, float* pdf_of_dir) {
     if (!c) return 1;
     if (!c->envW) OHB_FAIL(c, "ohb_env_sample_batch: no environment map");
+    if (!u12 || !dir_pdf) OHB_FAIL(c, "ohb_env_sample_batch: null array");
+    if (n == 0) return 0;
     cudaSetDevice(c->device);
     CU(c, c->hookRays.reserve(size_t(n) * 8)); CU(c, c->hookOut.reserve(size_t(n) * 16)); CU(c, c->hookAux.reserve(size_t(n) * 4));
     CU(c, cudaMemcpyAsync(c->hookRays.p, u12, size_t(n) * 8, cudaMemcpyHostToDevice, c->stream));
@@ -431,6 +437,10 @@ int ohb_get_accel_stats(ohb_ctx* c, ohb_accel_stats* s) { if (!c || !s) return 1
 int ohb_set_settings(ohb_ctx* c, const ohb_settings* s) {
     if (!c || !s) return 1;
     if ((s->max_bounces & 0xFFFFu) > 15u) OHB_FAIL(c, "ohb_set_settings: max_bounces > 15");
+    if (s->profile != OHB_PROFILE_OFFLINE && s->profile != OHB_PROFILE_REALTIME) OHB_FAIL(c, "ohb_set_settings: unknown profile");
+    if (s->sampler_type != OHB_SAMPLER_PCG && s->sampler_type != OHB_SAMPLER_SOBOL) OHB_FAIL(c, "ohb_set_settings: unknown sampler_type");
+    // the offline raygen's in-shader a-trous (pt_raygen_offline.rgen:1264) is not built: refuse rather than ignore the bit
+    if (s->profile == OHB_PROFILE_OFFLINE && (s->flags & OHB_FLAG_ENABLE_INTERNAL_DENOISE)) OHB_FAIL(c, "ohb_set_settings: OHB_FLAG_ENABLE_INTERNAL_DENOISE is implemented for the realtime profile only");
     if (s->profile == OHB_PROFILE_REALTIME && c->profile != OHB_PROFILE_REALTIME) OHB_FAIL(c, "ohb_set_settings: realtime settings need a context created with OHB_PROFILE_REALTIME");
     if (s->denoise_mode != OHB_DENOISE_NONE && s->denoise_mode != OHB_DENOISE_ATROUS) OHB_FAIL(c, "ohb_set_settings: denoise_mode must be OHB_DENOISE_NONE or OHB_DENOISE_ATROUS (OIDN / NRD / DLSS-RR are not part of this library)");
     if (s->denoise_mode == OHB_DENOISE_ATROUS && s->profile != OHB_PROFILE_REALTIME) OHB_FAIL(c, "ohb_set_settings: OHB_DENOISE_ATROUS (SVGF) runs in the realtime profile only");
@@ -565,6 +575,7 @@ int ohb_render(ohb_ctx* c, const float view[16], const float proj[16], uint32_t 
     if (!view || !proj) OHB_FAIL(c, "ohb_render: null matrix");
     if (!c->accelValid) { c->err = "ohb_render: no acceleration structure (call ohb_build_accel)"; return 1; }   // reference: silent return (path_tracer_render.cpp:42)
     if (!c->nmat) OHB_FAIL(c, "ohb_render: no materials");
+    if (c->maxMatId >= c->nmat) OHB_FAIL(c, "ohb_render: a triangle's material id is out of range of the material buffer");
     if (nsamples == 0) return 0;
     cudaSetDevice(c->device);
     if (c->settings.profile == OHB_PROFILE_REALTIME) return renderRealtime(c, view, proj, nsamples);
@@ -631,6 +642,12 @@ int ohb_read_hdr(ohb_ctx* c, float* accum, float* albedo, float* normal) {
 }
 void* ohb_accum_dev_ptr(ohb_ctx* c, size_t* bytes) { if (!c) return nullptr; if (bytes) *bytes = size_t(c->W) * c->H * 16; return c->accum.p; }
 int ohb_set_accum_mode(ohb_ctx* c, int sum_mode) { if (!c) return 1; c->sumMode = sum_mode ? 1 : 0; return 0; }
+int ohb_clear_accum(ohb_ctx* c) {
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    CU(c, cudaMemsetAsync(c->accum.p, 0, size_t(c->W) * c->H * 16, c->stream));
+    return 0;
+}
 int ohb_resolve(ohb_ctx* c) {
     if (!c) return 1;
     cudaSetDevice(c->device);
@@ -727,7 +744,11 @@ void ohb_reset_counters(ohb_ctx* c) {
     cudaMemsetAsync(c->devCounters.p, 0, 64, c->stream);
     c->launches = 0; c->timing.reset();
 }
-int ohb_enable_timing(ohb_ctx* c, int enable) { if (!c) return 1; c->timingOn = enable != 0; return 0; }
+int ohb_enable_timing(ohb_ctx* c, int enable) {
+    if (!c) return 1;
+    if (!enable && c->timingOn) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); c->timing.collect(); }
+    c->timingOn = enable != 0; return 0;
+}
 int ohb_get_timing(ohb_ctx* c, float* trace_ms, float* shade_ms, float* total_ms) {
     if (!c) return 1;
     cudaSetDevice(c->device);

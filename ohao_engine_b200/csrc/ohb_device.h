@@ -10,12 +10,14 @@ namespace ohb {
 
 // CUDA-event timing of kernel categories on the launching stream (bench.py roofline line):
 // 0 = closest-hit traversal, 1 = bounce (raygen body), 2 = any-hit traversal, 3 = film, 4 = surface (hit/miss shaders),
-// 5 = realtime per-pixel pass, 6 = SVGF denoiser, 7 spare.
+// 5 = realtime per-pixel pass, 6 = SVGF denoiser, 7 = hit/miss queue sort (k_sort_hits).
 struct TimingHooks {
     struct Span { cudaEvent_t a, b; int cat; };
     std::vector<Span> spans; size_t used = 0; 
     double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0}; uint64_t count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    static constexpr size_t kMaxSpans = 8192;     // a caller that never reads the timing must not grow the event pool without bound
     void begin(int cat, cudaStream_t st) {
+        if (used == kMaxSpans) { cudaStreamSynchronize(st); collect(); }
         if (used == spans.size()) { Span s; cudaEventCreate(&s.a); cudaEventCreate(&s.b); s.cat = cat; spans.push_back(s); }
         spans[used].cat = cat; cudaEventRecord(spans[used].a, st);
     }

@@ -12,6 +12,7 @@
 #include "ohb_device.h"
 #include <cuda_runtime.h>
 #include <cstdlib>
+#include <type_traits>
 
 namespace ohb {
 
@@ -277,10 +278,26 @@ static TraceKnobs traceKnobs() {
 // (warp-aggregated atomic); a lane that finishes its ray waits at the reconvergence point of the `have`
 // block until the traversing lanes either finish or drop below TRACE_MIN_ACTIVE, then all idle lanes are
 // refilled together.  IO = { load(i, o, d, tmin, tmax), store(i, Trav&) }.
-template <bool ANY, class IO>
+// VAR (compile-time A/B variants, selected by OHB_TRACE_VAR): bit 0 = the first OHB_SMEM_STACK stack entries of every thread
+// in shared memory, bit 1 = the top OHB_SMEM_TOP wide nodes (levels 0-2 of the tree) staged in shared memory per CTA.
+#define OHB_SMEM_STACK 8
+#define OHB_SMEM_TOP 73u
+template <bool ANY, int VAR, class IO>
 __device__ __forceinline__ void persistentTrace(const SceneDev& sc, uint32_t n, uint32_t* work, IO& io, int minActive, int postponeDen) {
     const uint32_t lane = threadIdx.x & 31u;
-    Trav t; TravStackEntry stack[OHB_STACK_SIZE]; uint32_t idx = 0; bool have = false, exhausted = false;
+    __shared__ TravStackEntry sStack[(VAR & 1) ? OHB_SMEM_STACK * TRACE_THREADS : 1];
+    __shared__ u4 sTop[(VAR & 2) ? OHB_SMEM_TOP * OHB_WNODE_VECS : 1];
+    TopNodes top{nullptr, 0u};
+    if (VAR & 2) {
+        const uint32_t cnt = sc.numWideNodes < OHB_SMEM_TOP ? sc.numWideNodes : OHB_SMEM_TOP;
+        for (uint32_t i = threadIdx.x; i < cnt * OHB_WNODE_VECS; i += TRACE_THREADS) sTop[i] = sc.wnodes[i];
+        __syncthreads();
+        top.top = sTop; top.count = cnt;
+    }
+    typename std::conditional<(VAR & 1) != 0, SharedStack<OHB_SMEM_STACK, TRACE_THREADS>, ArrayStack>::type stack;
+    TravStackEntry localMem[(VAR & 1) ? 1 : OHB_STACK_SIZE];
+    if constexpr ((VAR & 1) != 0) stack.sh = sStack + threadIdx.x; else stack.p = localMem;
+    Trav t; uint32_t idx = 0; bool have = false, exhausted = false;
     for (;;) {
         unsigned need = __ballot_sync(0xffffffffu, !have && !exhausted);
         if (need) {
@@ -295,7 +312,7 @@ __device__ __forceinline__ void persistentTrace(const SceneDev& sc, uint32_t n, 
         }
         if (!__any_sync(0xffffffffu, have)) break;
         bool done = false;
-        if (have) done = travRun<ANY>(t, stack, sc, minActive, postponeDen);
+        if (have) done = travRun<ANY>(t, stack, sc, top, minActive, postponeDen);
         __syncwarp();
         if (done) { io.store(idx, t); have = false; }
     }
@@ -315,10 +332,10 @@ struct PathClosestIO {
         hits += hit;
     }
 };
-template <int MINB>
+template <int MINB, int VAR>
 __global__ void __launch_bounds__(TRACE_THREADS, MINB) k_trace_closest(SceneDev sc, PathArrays P, uint32_t* work, int minActive, int postponeDen) {
     PathClosestIO io{P, 0u};
-    persistentTrace<false>(sc, *P.countIn, work, io, minActive, postponeDen);
+    persistentTrace<false, VAR>(sc, *P.countIn, work, io, minActive, postponeDen);
     uint32_t hits = __reduce_add_sync(0xffffffffu, io.hits);
     if ((threadIdx.x & 31u) == 0 && hits) atomicAdd(P.counters + 3, (unsigned long long)hits);
 }
@@ -334,32 +351,45 @@ struct PathShadowIO {
         pend[tag >> 1] = mk4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 };
-template <int MINB>
+template <int MINB, int VAR>
 __global__ void __launch_bounds__(TRACE_THREADS, MINB) k_trace_shadow(SceneDev sc, PathArrays P, uint32_t* work, int minActive, int postponeDen) {
     PathShadowIO io{P};
-    persistentTrace<true>(sc, *P.shCount, work, io, minActive, postponeDen);
+    persistentTrace<true, VAR>(sc, *P.shCount, work, io, minActive, postponeDen);
 }
 // resident CTAs per SM the traversal kernels are compiled for: 5 -> 96 registers, 6 -> 80, 7 -> 72, 8 -> 64, 9 -> 56, 10 -> 48.
 #ifndef OHB_TRACE_OCC_DEFAULT
 #define OHB_TRACE_OCC_DEFAULT 8
 #endif
+#ifndef OHB_TRACE_VAR_DEFAULT
+#define OHB_TRACE_VAR_DEFAULT 0
+#endif
 static int traceOcc() {
     static const int v = []() { const char* e = getenv("OHB_TRACE_OCC"); int o = e ? atoi(e) : OHB_TRACE_OCC_DEFAULT; return o >= 10 ? 10 : (o <= 5 ? 5 : o); }();
     return v;
 }
+static int traceVar() {
+    static const int v = []() { const char* e = getenv("OHB_TRACE_VAR"); int o = e ? atoi(e) : OHB_TRACE_VAR_DEFAULT; return o & 3; }();
+    return v;
+}
+// occupancy variants 5..10 exist for VAR 0; the shared-memory variants (VAR 1..3) are built for 7 and 8 CTAs per SM
+#define OHB_TRACE_DISPATCH(KERNEL, ...) do { \
+    const int o = traceOcc(), v = traceVar(); const unsigned grid = smGrid8 / 8u * unsigned(v ? (o >= 8 ? 8 : 7) : o); \
+    if (v == 0) { \
+        if (o == 10) KERNEL<10, 0><<<grid, TRACE_THREADS, 0, st>>>(__VA_ARGS__); else if (o == 9) KERNEL<9, 0><<<grid, TRACE_THREADS, 0, st>>>(__VA_ARGS__); \
+        else if (o == 8) KERNEL<8, 0><<<grid, TRACE_THREADS, 0, st>>>(__VA_ARGS__); else if (o == 7) KERNEL<7, 0><<<grid, TRACE_THREADS, 0, st>>>(__VA_ARGS__); \
+        else if (o == 6) KERNEL<6, 0><<<grid, TRACE_THREADS, 0, st>>>(__VA_ARGS__); else KERNEL<5, 0><<<grid, TRACE_THREADS, 0, st>>>(__VA_ARGS__); \
+    } else if (o >= 8) { \
+        if (v == 1) KERNEL<8, 1><<<grid, TRACE_THREADS, 0, st>>>(__VA_ARGS__); else if (v == 2) KERNEL<8, 2><<<grid, TRACE_THREADS, 0, st>>>(__VA_ARGS__); else KERNEL<8, 3><<<grid, TRACE_THREADS, 0, st>>>(__VA_ARGS__); \
+    } else { \
+        if (v == 1) KERNEL<7, 1><<<grid, TRACE_THREADS, 0, st>>>(__VA_ARGS__); else if (v == 2) KERNEL<7, 2><<<grid, TRACE_THREADS, 0, st>>>(__VA_ARGS__); else KERNEL<7, 3><<<grid, TRACE_THREADS, 0, st>>>(__VA_ARGS__); \
+    } } while (0)
 static void launchTraceClosest(unsigned smGrid8, const SceneDev& sc, const PathArrays& P, uint32_t* work, cudaStream_t st) {
-    const int o = traceOcc(); const unsigned grid = smGrid8 / 8u * unsigned(o);
     const TraceKnobs k = traceKnobs();
-#define OHB_LAUNCH_TC(OCC) k_trace_closest<OCC><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work, k.minActive, k.postponeDen)
-    if (o == 10) OHB_LAUNCH_TC(10); else if (o == 9) OHB_LAUNCH_TC(9); else if (o == 8) OHB_LAUNCH_TC(8); else if (o == 7) OHB_LAUNCH_TC(7); else if (o == 6) OHB_LAUNCH_TC(6); else OHB_LAUNCH_TC(5);
-#undef OHB_LAUNCH_TC
+    OHB_TRACE_DISPATCH(k_trace_closest, sc, P, work, k.minActive, k.postponeDen);
 }
 static void launchTraceShadow(unsigned smGrid8, const SceneDev& sc, const PathArrays& P, uint32_t* work, cudaStream_t st) {
-    const int o = traceOcc(); const unsigned grid = smGrid8 / 8u * unsigned(o);
     const TraceKnobs k = traceKnobs();
-#define OHB_LAUNCH_TS(OCC) k_trace_shadow<OCC><<<grid, TRACE_THREADS, 0, st>>>(sc, P, work, k.minActive, k.postponeDen)
-    if (o == 10) OHB_LAUNCH_TS(10); else if (o == 9) OHB_LAUNCH_TS(9); else if (o == 8) OHB_LAUNCH_TS(8); else if (o == 7) OHB_LAUNCH_TS(7); else if (o == 6) OHB_LAUNCH_TS(6); else OHB_LAUNCH_TS(5);
-#undef OHB_LAUNCH_TS
+    OHB_TRACE_DISPATCH(k_trace_shadow, sc, P, work, k.minActive, k.postponeDen);
 }
 #define SHADE_THREADS 128
 // ---- queue emission, STABLE AT TILE GRANULARITY ------------------------------------------------------------------
@@ -499,8 +529,9 @@ void launchOfflineBatch(const SceneDev& sc, const FrameParams& fr, PathArrays P,
         if (th) th->begin(0, st);
         launchTraceClosest(traceGrid, sc, P, work, st);
         if (th) th->end(0, st);
-        if (th) th->begin(1, st);
+        if (th) th->begin(7, st);
         k_sort_hits<<<shadeGrid, SHADE_THREADS, 0, st>>>(P);
+        if (th) { th->end(7, st); th->begin(1, st); }
         if (bounceOcc >= 8) k_shade<8><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P); else k_shade<6><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P);
         if (th) th->end(1, st);
         if (th) th->begin(2, st);
@@ -555,8 +586,9 @@ void launchRealtimeFrame(const SceneDev& sc, const FrameParams& fr, PathArrays P
         if (th) th->begin(0, st);
         launchTraceClosest(grid, sc, P, work, st);
         if (th) th->end(0, st);
-        if (th) th->begin(4, st);
+        if (th) th->begin(7, st);
         k_sort_hits<<<grid, SHADE_THREADS, 0, st>>>(P); (*launches)++;
+        if (th) { th->end(7, st); th->begin(4, st); }
         k_surface<<<grid, SHADE_THREADS, 0, st>>>(sc, fr, P);
         if (th) th->end(4, st);
         if (th) th->begin(1, st);
@@ -632,11 +664,11 @@ struct HookIO {
 };
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_batch(SceneDev sc, const ohb_ray* rays, uint32_t n, ohb_hit* hits, uint32_t* work, int minActive, int postponeDen) {
     HookIO io{rays, hits, nullptr};
-    persistentTrace<false>(sc, n, work, io, minActive, postponeDen);
+    persistentTrace<false, 0>(sc, n, work, io, minActive, postponeDen);
 }
 __global__ void __launch_bounds__(TRACE_THREADS) k_occluded_batch(SceneDev sc, const ohb_ray* rays, uint32_t n, uint8_t* occ, uint32_t* work, int minActive, int postponeDen) {
     HookIO io{rays, nullptr, occ};
-    persistentTrace<true>(sc, n, work, io, minActive, postponeDen);
+    persistentTrace<true, 0>(sc, n, work, io, minActive, postponeDen);
 }
 void launchTraceBatch(const SceneDev& sc, const ohb_ray* rays, uint32_t n, ohb_hit* hits, uint8_t* occ, uint32_t* work, int numSMs, cudaStream_t st, uint64_t* launches) {
     k_zero_u32<<<1, 32, 0, st>>>(work, 2);

@@ -194,6 +194,24 @@ struct Trav {
     u2 G, Gt; int sp; uint32_t octinv; bool anyHit;
 };
 typedef u2 TravStackEntry;
+// Traversal stack.  ArrayStack: a per-thread array (local memory on the device).  SharedStack<SH, STRIDE>: the first SH
+// entries of every thread live in shared memory (entry k of thread t at sh[k * STRIDE + t]: a warp's accesses to one
+// level are 32 consecutive 8-B words, conflict-free), deeper entries in local memory.  The 8-wide tree keeps at most
+// one entry per level, so 8 shared entries hold the whole stack of almost every ray of a 2 M-triangle scene.
+struct ArrayStack {
+    TravStackEntry* p;
+    OHB_HD void push(int sp, TravStackEntry v) { p[sp] = v; }
+    OHB_HD TravStackEntry pop(int sp) const { return p[sp]; }
+};
+template <int SH, int STRIDE>
+struct SharedStack {
+    TravStackEntry* sh; TravStackEntry loc[OHB_STACK_SIZE - SH];
+    OHB_HD void push(int sp, TravStackEntry v) { if (sp < SH) sh[sp * STRIDE] = v; else loc[sp - SH] = v; }
+    OHB_HD TravStackEntry pop(int sp) const { return sp < SH ? sh[sp * STRIDE] : loc[sp - SH]; }
+};
+// Top of the tree staged in shared memory (north_star: "shared-memory staging of the top tree levels"): the builder
+// allocates wide nodes level by level, so nodes [0, count) are the top levels.  top == nullptr: everything from global.
+struct TopNodes { const u4* top; uint32_t count; };
 
 OHB_HD void travInit(Trav& t, const SceneDev& s, f3 o, f3 d, float tmin, float tmax) {
     t.r = prepRay(o, d, tmin); t.tlim = tmax;
@@ -225,12 +243,21 @@ OHB_HD ohb_hit travResult(const Trav& t) {
 // origin to the far side of the node (|p - o| + ext on the worst axis), converted to ray-parameter units: that
 // covers the 5e-7 of arithmetic error above and leaves 7e-7 (a dozen ulp) for the placement error.
 #define OHB_NODE_SWZ(i) ((i) & 3u)
-OHB_HD uint32_t intersectWideNode(const Trav& t, const u4* np, uint32_t swz, float thi, uint32_t& childBase, uint32_t& triBase, uint32_t& imask) {
+OHB_HD u8v ldsu8(const u4* p) { u8v r; r.lo = p[0]; r.hi = p[1]; return r; }
+OHB_HD uint32_t intersectWideNode(const Trav& t, const u4* gnodes, const TopNodes& tn8, uint32_t idx, float thi, uint32_t& childBase, uint32_t& triBase, uint32_t& imask) {
     const RayPrep& r = t.r;
+    const uint32_t swz = OHB_NODE_SWZ(idx);
     // the four 32-B pieces of node i sit at positions k ^ (i & 3) of its 128-B line (OHB_NODE_SWZ): all lanes of a warp
     // read "piece k of my node" in the same instruction, and with every node laid out alike they would all hit the same
     // 8 of the 32 L1 data banks — measured 1.0 lane-loads/clk/SM against 1.8-2.9 with rotated offsets (tools/ubench/l1.cu)
-    const u8v hdr = ldu8(np + 2u * (0u ^ swz)), px8 = ldu8(np + 2u * (1u ^ swz)), py8 = ldu8(np + 2u * (2u ^ swz)), pz8 = ldu8(np + 2u * (3u ^ swz));
+    u8v hdr, px8, py8, pz8;
+    if (tn8.top && idx < tn8.count) {
+        const u4* np = tn8.top + size_t(idx) * OHB_WNODE_VECS;
+        hdr = ldsu8(np + 2u * (0u ^ swz)); px8 = ldsu8(np + 2u * (1u ^ swz)); py8 = ldsu8(np + 2u * (2u ^ swz)); pz8 = ldsu8(np + 2u * (3u ^ swz));
+    } else {
+        const u4* np = gnodes + size_t(idx) * OHB_WNODE_VECS;
+        hdr = ldu8(np + 2u * (0u ^ swz)); px8 = ldu8(np + 2u * (1u ^ swz)); py8 = ldu8(np + 2u * (2u ^ swz)); pz8 = ldu8(np + 2u * (3u ^ swz));
+    }
     OHB_STAT_NODE();
     const u4 w0 = hdr.lo, w1 = hdr.hi;
     // near / far planes by ray sign: 24 word selects (the 16-B vectors would be selectable by address, but only as
@@ -311,8 +338,8 @@ OHB_HD uint32_t nextChildOf(const u2& G, uint32_t octinv) {
 // postponeDen carries the prefetch mode in bits 8.. : bits 8-9 = prefetch the NEXT SIBLING when a group with children left
 // is pushed (the node a later stack pop will want; 1 = L2, 2 = L1), bits 10-11 = prefetch the FIRST HIT CHILD right after
 // the box tests, before the leaf triangles of this node are tested, bit 12 = four prefetches per node
-template <bool ANY>
-OHB_HD bool travRun(Trav& t, TravStackEntry* stack, const SceneDev& s, int minActive, int postponeDenAndPf) {
+template <bool ANY, class Stack>
+OHB_HD bool travRun(Trav& t, Stack& stack, const SceneDev& s, const TopNodes& top, int minActive, int postponeDenAndPf) {
     const int postponeDen = postponeDenAndPf & 0xFF, pfSib = (postponeDenAndPf >> 8) & 3, pfKid = (postponeDenAndPf >> 10) & 3, pf4 = (postponeDenAndPf >> 8) & 16;
     for (;;) {
         if (t.G.y & 0xFF000000u) {
@@ -322,11 +349,11 @@ OHB_HD bool travRun(Trav& t, TravStackEntry* stack, const SceneDev& s, int minAc
             t.G.y &= ~(1u << bit);
             const uint32_t idx = t.G.x + popc32(t.G.y & 0xFFu & ((1u << slot) - 1u));
             if (t.G.y & 0xFF000000u) {
-                stack[t.sp++] = t.G;
+                stack.push(t.sp++, t.G);
                 if (pfSib) prefetchNode(s.wnodes + size_t(nextChildOf(t.G, t.octinv)) * OHB_WNODE_VECS, pfSib | pf4);
             }
             uint32_t childBase, triBase, imask;
-            const uint32_t hits = intersectWideNode(t, s.wnodes + size_t(idx) * OHB_WNODE_VECS, OHB_NODE_SWZ(idx), t.tlim, childBase, triBase, imask);
+            const uint32_t hits = intersectWideNode(t, s.wnodes, top, idx, t.tlim, childBase, triBase, imask);
             t.G.x = childBase; t.G.y = (hits & 0xFF000000u) | imask;
             t.Gt.x = triBase; t.Gt.y = hits & 0x00FFFFFFu;
             if (pfKid && (t.G.y & 0xFF000000u) && t.Gt.y) prefetchNode(s.wnodes + size_t(nextChildOf(t.G, t.octinv)) * OHB_WNODE_VECS, pfKid | pf4);
@@ -336,7 +363,7 @@ OHB_HD bool travRun(Trav& t, TravStackEntry* stack, const SceneDev& s, int minAc
         // leaf triangles; when most lanes of the warp have none left, the rest postpone theirs (Ylitie et al. §4.3)
         const int entered = postponeDen ? OHB_WARP_ACTIVE() : 0;
         while (t.Gt.y) {
-            if (postponeDen && OHB_WARP_ACTIVE() * postponeDen < entered && t.sp < OHB_POSTPONE_SLOTS) { stack[t.sp++] = t.Gt; t.Gt.y = 0u; break; }
+            if (postponeDen && OHB_WARP_ACTIVE() * postponeDen < entered && t.sp < OHB_POSTPONE_SLOTS) { stack.push(t.sp++, t.Gt); t.Gt.y = 0u; break; }
             // TWO triangles per round, both fetched before either is tested: the kernels wait on memory, not on issue
             // slots (r2j: 22 % of all samples sat on the triangle loads), and the register file is half empty here —
             // the node phase, not this loop, sets the kernel's register count
@@ -364,7 +391,7 @@ OHB_HD bool travRun(Trav& t, TravStackEntry* stack, const SceneDev& s, int minAc
         }
         if (!(t.G.y & 0xFF000000u)) {
             if (t.sp == 0) return true;
-            t.G = stack[--t.sp];
+            t.G = stack.pop(--t.sp);
         }
         if (OHB_WARP_ACTIVE() < minActive) return false;
     }
@@ -372,14 +399,14 @@ OHB_HD bool travRun(Trav& t, TravStackEntry* stack, const SceneDev& s, int minAc
 
 // Closest hit.  Returns prim == OHB_MISS and t = -1 on miss.
 OHB_HD ohb_hit traceClosest(const SceneDev& s, f3 o, f3 d, float tmin, float tmax) {
-    Trav t; TravStackEntry stack[OHB_STACK_SIZE]; travInit(t, s, o, d, tmin, tmax);
-    if (t.G.y) while (!travRun<false>(t, stack, s, 0, OHB_POSTPONE_DEN_DEFAULT)) {}
+    Trav t; TravStackEntry mem[OHB_STACK_SIZE]; ArrayStack stack{mem}; const TopNodes top{nullptr, 0u}; travInit(t, s, o, d, tmin, tmax);
+    if (t.G.y) while (!travRun<false>(t, stack, s, top, 0, OHB_POSTPONE_DEN_DEFAULT)) {}
     return travResult(t);
 }
 // Any hit in (tmin, tmax): TerminateOnFirstHit | SkipClosestHit.
 OHB_HD bool traceAny(const SceneDev& s, f3 o, f3 d, float tmin, float tmax) {
-    Trav t; TravStackEntry stack[OHB_STACK_SIZE]; travInit(t, s, o, d, tmin, tmax);
-    if (t.G.y) while (!travRun<true>(t, stack, s, 0, OHB_POSTPONE_DEN_DEFAULT)) {}
+    Trav t; TravStackEntry mem[OHB_STACK_SIZE]; ArrayStack stack{mem}; const TopNodes top{nullptr, 0u}; travInit(t, s, o, d, tmin, tmax);
+    if (t.G.y) while (!travRun<true>(t, stack, s, top, 0, OHB_POSTPONE_DEN_DEFAULT)) {}
     return t.anyHit;
 }
 

@@ -95,6 +95,20 @@ def trs(position=(0, 0, 0), scale=(1, 1, 1)) -> np.ndarray:
 
 # ------------------------------------------------------------------------------------------
 @dataclasses.dataclass
+class SubMaterial:
+    """One material of a multi-material model (a glTF material): Model::materialColors / materialMetallic and the
+    per-material texture tables of model_gltf.cpp:373-541."""
+    base_color: tuple = (0.8, 0.8, 0.8)
+    roughness: float = 0.5
+    metallic: float = 0.0
+    albedo_tex: Optional[np.ndarray] = None
+    normal_tex: Optional[np.ndarray] = None
+    rough_metal_tex: Optional[np.ndarray] = None
+    emissive_tex: Optional[np.ndarray] = None
+    name: str = "material"
+
+
+@dataclasses.dataclass
 class Mesh:
     positions: np.ndarray            # (n,3) f32
     normals: np.ndarray              # (n,3) f32
@@ -110,6 +124,15 @@ class Mesh:
     rough_metal_tex: Optional[np.ndarray] = None
     emissive_tex: Optional[np.ndarray] = None
     name: str = "mesh"
+    # multi-material models (glTF): one SubMaterial per material and one index per triangle (Model::materialPerTriangle);
+    # when absent the mesh is one material described by the fields above (the MaterialComponent path)
+    materials: Optional[List[SubMaterial]] = None
+    material_per_triangle: Optional[np.ndarray] = None
+
+    def sub_materials(self) -> List[SubMaterial]:
+        if self.materials:
+            return self.materials
+        return [SubMaterial(self.base_color, self.roughness, self.metallic, self.albedo_tex, self.normal_tex, self.rough_metal_tex, self.emissive_tex, self.name)]
 
 
 @dataclasses.dataclass
@@ -200,25 +223,31 @@ def pack_scene(meshes: List[Mesh], lights: List[Light], env: Optional[np.ndarray
         nv = m.positions.shape[0]; nt = m.indices.shape[0] // 3
         pos_l.append(m.positions.astype(f32)); nrm_l.append(m.normals.astype(f32)); uv_l.append(m.uvs.astype(f32))
         idx_l.append(m.indices.astype(np.uint32) + np.uint32(voff))
-        mat_l.append(np.full(nt, mi, np.uint32))
+        subs = m.sub_materials()
+        color_offset = len(mat_colors) // 3                 # rt_build.cpp:208: material ids are offset by the materials packed so far
+        if m.material_per_triangle is not None:
+            mat_l.append(np.asarray(m.material_per_triangle, np.uint32) + np.uint32(color_offset))
+        else:
+            mat_l.append(np.full(nt, color_offset, np.uint32))
         rec = np.zeros(1, INSTANCE_DTYPE)
         rec["first_tri"] = toff; rec["tri_count"] = nt; rec["xform"] = m.xform; rec["mask"] = 0xFF
         inst.append(rec)
-        # texture layers in the reference's order: diffuse (or 1x1 solid), normal, roughMetal, emissive
+        # texture layers in the reference's order: diffuse (or 1x1 solid), normal, roughMetal, emissive — per material
         def layer(t):
             if t is None: return -1
             tex_sources.append(np.ascontiguousarray(t, np.uint8)); return len(tex_sources) - 1
-        if m.albedo_tex is not None:
-            d_idx = layer(m.albedo_tex)
-        else:
-            solid = np.array([[[ _linear_to_srgb8(m.base_color[0]), _linear_to_srgb8(m.base_color[1]),
-                                 _linear_to_srgb8(m.base_color[2]), 255]]], np.uint8)
-            d_idx = layer(solid)
-        n_idx = layer(m.normal_tex); rm_idx = layer(m.rough_metal_tex); e_idx = layer(m.emissive_tex)
         def bits(i): return np.array([NO_TEX if i < 0 else i], "<u4").view("<f4")[0]
-        mat_colors.append([m.base_color[0], m.base_color[1], m.base_color[2], bits(d_idx)])
-        mat_colors.append([m.roughness, m.metallic, bits(n_idx), bits(e_idx)])
-        mat_colors.append([bits(rm_idx), 0.0, 0.0, 0.0])
+        for sm in subs:
+            if sm.albedo_tex is not None:
+                d_idx = layer(sm.albedo_tex)
+            else:
+                solid = np.array([[[ _linear_to_srgb8(sm.base_color[0]), _linear_to_srgb8(sm.base_color[1]),
+                                     _linear_to_srgb8(sm.base_color[2]), 255]]], np.uint8)
+                d_idx = layer(solid)
+            n_idx = layer(sm.normal_tex); rm_idx = layer(sm.rough_metal_tex); e_idx = layer(sm.emissive_tex)
+            mat_colors.append([sm.base_color[0], sm.base_color[1], sm.base_color[2], bits(d_idx)])
+            mat_colors.append([sm.roughness, sm.metallic, bits(n_idx), bits(e_idx)])
+            mat_colors.append([bits(rm_idx), 0.0, 0.0, 0.0])
         voff += nv; toff += nt
     nverts = voff
     positions = np.zeros((nverts, VERTEX_STRIDE // 4), f32)
@@ -242,6 +271,31 @@ def pack_scene(meshes: List[Mesh], lights: List[Light], env: Optional[np.ndarray
                        mat_ids=np.concatenate(mat_l), instances=np.concatenate(inst), mat_colors=mc,
                        textures=textures, light_ssbo=np.frombuffer(ssbo, np.uint8).copy(),
                        env=None if env is None else np.ascontiguousarray(env, f32), name=name)
+
+
+def emissive_mesh_lights(meshes: List[Mesh]) -> List[Light]:
+    """One auto-generated sphere light per mesh whose first emissive-textured material is bright enough
+    (light_upload.cpp:183-247): centre = world position of the bounding-box centre, radius = 0.3 x |bbox diagonal| in
+    object space, colour = mean of the texels with luminance > 0.05, intensity = min(0.1 x their summed luminance, 20)."""
+    out: List[Light] = []
+    for m in meshes:
+        for sm in m.sub_materials():
+            if sm.emissive_tex is None:
+                continue
+            px = np.asarray(sm.emissive_tex, np.uint8)[..., :3].reshape(-1, 3).astype(f32) / f32(255.0)
+            lum = px[:, 0] * f32(0.2126) + px[:, 1] * f32(0.7152) + px[:, 2] * f32(0.0722)
+            mask = lum > f32(0.05)
+            power = float(np.cumsum(lum[mask], dtype=f32)[-1]) if mask.any() else 0.0        # sequential fp32 sum like the reference
+            if power > 0.1:
+                col = px[mask].astype(np.float64).sum(0) / int(mask.sum())
+                bmin, bmax = m.positions.min(0).astype(f32), m.positions.max(0).astype(f32)
+                mid = (bmin + bmax) * f32(0.5)
+                x = np.asarray(m.xform, f32).reshape(3, 4)
+                center = x[:, :3] @ mid + x[:, 3]
+                out.append(Light(position=tuple(float(v) for v in center), color=tuple(float(f32(v)) for v in col), intensity=min(power * 0.1, 20.0),
+                                 radius=float(np.linalg.norm(bmax - bmin) * f32(0.3)), direction=(0.0, -1.0, 0.0)))
+            break                                        # one light per actor
+    return out
 
 
 # ------------------------------------------------------------------------------------------

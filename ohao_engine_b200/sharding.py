@@ -66,6 +66,7 @@ def jobs_for_rank(njobs: int, world: int, rank: int) -> List[int]:
 def render_plan(renderer, items: Sequence[WorkItem], view, proj, max_batch: int = 64):
     """Run a rank's work list on a ``binding.Renderer`` in sum mode."""
     renderer.set_accum_mode(True)
+    renderer.clear_accum()          # pixels outside this rank's tiles must be zero when the images are summed
     for it in items:
         renderer.set_tile(*it.tile)
         renderer.set_render_seed(it.first_sample)          # also resets the per-context history counter ...

@@ -43,7 +43,7 @@ struct EmulScene {
     std::vector<u4> wnodes; std::vector<f4> tris; uint32_t numActive = 0, numNodes = 0, levels = 0; float sah = 0;
     SceneDev dev() const {
         SceneDev s; memset(&s, 0, sizeof(s));
-        s.wnodes = wnodes.data(); s.tris = tris.data(); s.numTris = numActive;
+        s.wnodes = wnodes.data(); s.tris = tris.data(); s.numTris = numActive; s.numWideNodes = numNodes;
         s.indices = indices.data(); s.normals = normals.data(); s.uvs = uvs.data(); s.matIds = matIds.data(); s.triInst = triInst.data();
         s.instNormalMat = instNormalMat.data(); s.instInv = instInv.data(); s.matColors = matColors.data();
         s.tex = tex.data(); s.texW = texW; s.texH = texH; s.texLayers = texLayers;

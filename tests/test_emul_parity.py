@@ -43,6 +43,19 @@ def test_offline_samples_match_oracle(which, res, spp, request):
     assert np.abs(ro["albedo"] - re["albedo"]).max() < 1e-4 and np.abs(ro["normal"] - re["normal"]).max() < 1e-4
 
 
+def test_pcg_sampler_samples_match_oracle(cornell):
+    """SAMPLER_PCG (sampler_pcg.glsl:9-29) — dead in the reference's pipelines (quirk Q3), still part of the sampler API."""
+    ps, cam = cornell
+    W, H, spp = 64, 36, 3
+    osc, esc = O.OracleScene(ps), E.EmulScene(ps)
+    ro = osc.render_offline(cam.view(), cam.proj(W, H), W, H, spp, dump=True, settings=O.offline_settings(sampler=0))
+    re = esc.render_offline(cam.view(), cam.proj(W, H), W, H, spp, dump=True, settings=O.offline_settings(sampler=0))
+    bad, worst = util.sample_parity(ro["samples"], re["samples"])
+    assert bad < 2e-3 and worst < 2e-3, (bad, worst)
+    rs = osc.render_offline(cam.view(), cam.proj(W, H), W, H, spp, dump=True)
+    assert util.sample_parity(rs["samples"], re["samples"])[0] > 0.5      # and it is not the Sobol sequence
+
+
 def test_accumulation_continues_across_calls(cornell):
     ps, cam = cornell
     W, H = 64, 36

@@ -1,0 +1,207 @@
+"""Parity at BASELINE scale: the scenes every published number is quoted on (helmet-class 50 K triangles with
+5 x 2048^2 textures under a 1024x512 HDRI, and the full 2 M-triangle scene), at 1920x1080 and 3840x2160, through
+the C ABI against the CPU oracle.  Plus the builder / traversal edge cases of tests/test_emul_parity.py on the
+hardware (warp-vote refill and __activemask()-dependent postponing only exist there) and the PCG sampler.
+
+Sizes: the C++ oracle builds its 2 M-triangle SAH tree in ~1.5 s and traces 1 M rays in ~1.5 s on 8 host threads.
+Tie counts (same t, different primitive id) are printed; a tie is a mismatch here because both sides resolve
+equal-t candidates toward the lower global id.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from ohao_engine_b200 import binding as B
+from ohao_engine_b200 import scenes
+from oracle import oracle_py as O
+from tests import util
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def helmet_full():
+    ps, cam = scenes.helmet_class(), scenes.helmet_camera()
+    r = B.Renderer(1920, 1080); r.set_scene(ps)
+    return ps, cam, O.OracleScene(ps), r
+
+
+@pytest.fixture(scope="module")
+def synthetic_full():
+    ps, cam = scenes.synthetic_2m(), scenes.synthetic_camera()
+    r = B.Renderer(1920, 1080); r.set_scene(ps)
+    return ps, cam, O.OracleScene(ps), r
+
+
+FULL = {"helmet_full": (-3.0, 3.0), "synthetic_full": (-60.0, 60.0)}
+TILE = (832, 476, 256, 128)          # a 256x128 tile around the middle of the 1080p frame
+
+
+@pytest.mark.parametrize("which", list(FULL))
+def test_million_random_rays_bit_exact(which, request):
+    ps, cam, osc, r = request.getfixturevalue(which)
+    lo, hi = FULL[which]
+    rays = util.random_rays(1 << 20, lo, hi, seed=101)
+    ref, got = osc.trace(rays), r.trace(rays)
+    mism, ties = util.compare_hits(ref, got)
+    st = r.accel_stats()
+    print(f"\n[{which}] {st.num_tris} tris, {st.num_nodes} wide nodes, {st.levels} levels: {len(rays)} random rays, "
+          f"hit rate {np.mean(ref['prim'] != 0xFFFFFFFF):.3f}, mismatches {mism}, ties {ties}")
+    assert mism == 0, (mism, ties)
+    for k in ("t", "u", "v"):
+        assert np.array_equal(ref[k], got[k]), k
+    n = 1 << 18
+    assert np.array_equal(osc.occluded(rays[:n]), r.occluded(rays[:n]))
+
+
+@pytest.mark.parametrize("which", list(FULL))
+def test_recorded_path_rays_1080p_bit_exact(which, request):
+    """Primary, bounce and shadow rays the integrator itself generates on a 1080p tile, recorded by the oracle."""
+    ps, cam, osc, r = request.getfixturevalue(which)
+    W, H = 1920, 1080
+    rays, hits, kinds = osc.record_rays(cam.view(), cam.proj(W, H), W, H, 2, tile=TILE, cap=1 << 21)
+    closest = kinds == 0
+    assert closest.sum() > 60000 and (~closest).sum() > 20000
+    got = r.trace(rays[closest])
+    mism, ties = util.compare_hits(hits[closest], got)
+    print(f"\n[{which}] recorded {closest.sum()} closest + {(~closest).sum()} shadow rays: mismatches {mism}, ties {ties}")
+    assert mism == 0, (mism, ties)
+    assert np.array_equal(hits[closest]["t"], got["t"])
+    occ = r.occluded(rays[~closest])
+    assert np.array_equal(occ != 0, hits[~closest]["prim"] != 0xFFFFFFFF)
+
+
+@pytest.mark.parametrize("which", list(FULL))
+def test_per_sample_radiance_1080p_tile(which, request):
+    ps, cam, osc, r = request.getfixturevalue(which)
+    W, H, spp = 1920, 1080, 2
+    x0, y0, w, h = TILE
+    ro = osc.render_offline(cam.view(), cam.proj(W, H), W, H, spp, tile=TILE, dump=True)
+    r.reset_accumulation(); r.set_tile(*TILE); r.reset_counters()
+    try:
+        got = r.render(cam.view(), cam.proj(W, H), spp, dump=True)
+    finally:
+        r.set_tile(0, 0, W, H)
+    a = ro["samples"][:, y0:y0 + h, x0:x0 + w]; b = got[:, y0:y0 + h, x0:x0 + w]
+    assert np.abs(a[..., :3]).max() > 0
+    bad, worst = util.sample_parity(a, b)
+    print(f"\n[{which}] 1080p tile {w}x{h} x {spp} spp: {bad:.2e} of samples beyond 2e-3, worst of the rest {worst:.2e}")
+    assert bad < 2e-3 and worst < 2e-3, (bad, worst)
+    c = r.counters()
+    assert c["samples"] == w * h * spp
+    for k in ("closest_rays", "shadow_rays", "closest_hits"):
+        assert abs(ro["counters"][k] - c[k]) <= max(8, ro["counters"][k] // 2000), (k, ro["counters"][k], c[k])
+    acc, _, _ = r.readback_hdr_buffers(want_aov=False)
+    ref = ro["accum"][y0:y0 + h, x0:x0 + w, :3]
+    mre = np.abs(acc[y0:y0 + h, x0:x0 + w, :3] - ref).mean() / max(ref.mean(), 1e-6)
+    assert mre < 1e-3, mre
+
+
+def test_4k_tile_matches_oracle(helmet_full):
+    """Config 4's resolution: one 256x256 tile of the 3840x2160 frame via ohb_set_tile (the sharded render's work item)."""
+    ps, cam, osc, _ = helmet_full
+    W, H, spp = 3840, 2160, 1
+    tile = (1792, 896, 256, 256)
+    x0, y0, w, h = tile
+    ro = osc.render_offline(cam.view(), cam.proj(W, H), W, H, spp, tile=tile, dump=True)
+    r = B.Renderer(W, H); r.set_scene(ps); r.set_tile(*tile)
+    got = r.render(cam.view(), cam.proj(W, H), spp, dump=True)
+    bad, worst = util.sample_parity(ro["samples"][:, y0:y0 + h, x0:x0 + w], got[:, y0:y0 + h, x0:x0 + w])
+    print(f"\n[helmet_full] 4K tile {w}x{h}: {bad:.2e} of samples beyond 2e-3, worst of the rest {worst:.2e}")
+    assert bad < 2e-3 and worst < 2e-3, (bad, worst)
+    acc, _, _ = r.readback_hdr_buffers(want_aov=False)
+    outside = acc.copy(); outside[y0:y0 + h, x0:x0 + w] = 0
+    assert not outside.any()                                      # nothing outside the tile is touched
+
+
+# ---- builder / traversal edge cases on the hardware (tests/test_emul_parity.py:96-150 on the emulator) -----------
+def _soup(tris):
+    tris = np.asarray(tris, np.float32); n = len(tris)
+    m = scenes.Mesh(positions=tris.reshape(-1, 3), normals=np.tile(np.array([0, 1, 0], np.float32), (3 * n, 1)), uvs=np.zeros((3 * n, 2), np.float32),
+                    indices=np.arange(3 * n, dtype=np.uint32))
+    return scenes.pack_scene([m], [scenes.Light(position=(0, 5, 0))], name="soup")
+
+
+def _same_hits(ps, rays):
+    osc = O.OracleScene(ps); r = B.Renderer(32, 32); r.set_scene(ps)
+    ref, got = osc.trace(rays), r.trace(rays)
+    for k in ("prim", "t", "u", "v"):
+        assert np.array_equal(ref[k], got[k]), k
+    assert np.array_equal(osc.occluded(rays), r.occluded(rays))
+    return r, ref
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 9, 25])
+def test_tiny_scenes(n):
+    rng = np.random.default_rng(n)
+    r, ref = _same_hits(_soup(rng.uniform(-1, 1, (n, 3, 3))), util.random_rays(4000, -2, 2, seed=n))
+    assert (ref["prim"] != 0xFFFFFFFF).any() and r.accel_stats().levels <= 3
+
+
+def test_coincident_and_flat_geometry():
+    base = np.array([[-1, 0, -1], [1, 0, -1], [0, 0, 1]], np.float32)
+    tris = np.concatenate([np.tile(base, (40, 1, 1)), np.tile(base + np.array([0.5, 0, 0.25], np.float32), (23, 1, 1))])
+    _, ref = _same_hits(_soup(tris), util.random_rays(60000, -1.5, 1.5, seed=2))
+    hit = ref["prim"] != 0xFFFFFFFF
+    assert hit.sum() > 5000 and set(np.unique(ref["prim"][hit])) <= {0, 40}      # equal-t ties resolve to the lowest id of each stack
+
+
+def test_far_from_origin_and_mixed_scales():
+    rng = np.random.default_rng(9)
+    c = np.array([1.0e4, -2.0e3, 5.0e3], np.float32)
+    small = c + rng.uniform(-0.5, 0.5, (300, 1, 3)) + rng.uniform(-2e-3, 2e-3, (300, 3, 3))
+    big = c + np.array([[[-50, -1, -50], [50, -1, -50], [0, -1, 60]]], np.float32)
+    tris = np.concatenate([small, big]).astype(np.float32)
+    rays = util.random_rays(80000, -1.0, 1.0, seed=4)
+    rays["origin"] += c
+    k = 30000
+    tgt = small[rng.integers(0, 300, k)].mean(1)
+    d = tgt - rays["origin"][:k]; rays["dir"][:k] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    _, ref = _same_hits(_soup(tris), rays)
+    assert (ref["prim"][:k] < 300).sum() > 10000
+
+
+_KNOB_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+from ohao_engine_b200 import binding as B, scenes
+from tests import util
+ps = scenes.synthetic_2m(nblobs=24, tris_per_blob=800, env_size=(128, 64))
+r = B.Renderer(32, 32); r.set_scene(ps)
+rays = util.random_rays(300000, -60, 60, seed=21)
+h = r.trace(rays); o = r.occluded(rays)
+np.savez(sys.argv[2], prim=h["prim"], t=h["t"], u=h["u"], v=h["v"], occ=o)
+"""
+
+
+def test_postponing_and_refill_schedules_do_not_change_hits(tmp_path):
+    """The scheduling knobs (triangle postponing threshold, lane-refill threshold, occupancy variant) only move work
+    between warps: every schedule must return identical hits.  The knobs are read once per process, hence subprocesses."""
+    outs = []
+    for i, env in enumerate([{}, {"OHB_POSTPONE_DEN": "0", "OHB_TRACE_MIN_ACTIVE": "0"}, {"OHB_POSTPONE_DEN": "2", "OHB_TRACE_MIN_ACTIVE": "31", "OHB_TRACE_OCC": "5"}]):
+        out = str(tmp_path / f"k{i}.npz")
+        subprocess.check_call([sys.executable, "-c", _KNOB_SCRIPT, ROOT, out], env={**os.environ, **env})
+        outs.append(np.load(out))
+    for o in outs[1:]:
+        for k in ("prim", "t", "u", "v", "occ"):
+            assert np.array_equal(outs[0][k], o[k]), k
+    assert (outs[0]["prim"] != 0xFFFFFFFF).sum() > 50000
+
+
+def test_pcg_sampler_samples_match_oracle(cornell):
+    """SAMPLER_PCG (sampler_pcg.glsl:9-29): dead in the reference's pipelines (quirk Q3) but part of the sampler API."""
+    ps, cam = cornell
+    W, H, spp = 160, 90, 3
+    osc = O.OracleScene(ps)
+    ro = osc.render_offline(cam.view(), cam.proj(W, H), W, H, spp, dump=True, settings=O.offline_settings(sampler=0))
+    rs = osc.render_offline(cam.view(), cam.proj(W, H), W, H, spp, dump=True)
+    r = B.Renderer(W, H); r.set_scene(ps)
+    st = r.get_settings(); st.sampler_type = B.SAMPLER_PCG; r.set_rt_render_settings(st)
+    got = r.render(cam.view(), cam.proj(W, H), spp, dump=True)
+    bad, worst = util.sample_parity(ro["samples"], got)
+    assert bad < 2e-3 and worst < 2e-3, (bad, worst)
+    assert util.sample_parity(rs["samples"], got)[0] > 0.5          # and it is not the Sobol sequence

@@ -61,3 +61,28 @@ def test_turntable_and_inverse_fit_binaries(tmp_path):
     r = subprocess.run([os.path.join(HOST, "inverse_fit"), "--backend", "pt", "--preset", "lantern", "--quality", "draft", "--iters", "6", "--tris", "3000"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr                         # exit 0 <=> the fit reduced the loss
     assert "probes/s" in r.stdout
+
+
+def test_cpp_host_ingests_the_real_assets_like_the_python_packer(tmp_path):
+    """host/asset_io.hpp (loadGLB + side-car textures, loadHDR) and the C++ packer against ohao_engine_b200/assets.py on
+    DamagedHelmet.glb: `turntable <glb> env --dump-scene` writes the packed §3.2 arrays without needing a GPU."""
+    import shutil, struct
+    from ohao_engine_b200 import assets
+    _build()
+    glb = str(tmp_path / "DamagedHelmet.glb"); shutil.copy(os.path.join(ROOT, "tests", "assets", "DamagedHelmet.glb"), glb)
+    assets.bake_textures(glb)
+    dump = str(tmp_path / "scene.bin")
+    r = subprocess.run([os.path.join(HOST, "turntable"), glb, "env", "4", "1", "--hdr", os.path.join(ROOT, "tests", "assets", "env_outdoor.hdr"), "--dump-scene", dump], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = open(dump, "rb").read(); assert raw[:4] == b"OHBS"
+    off, rec = 4, {}
+    while off < len(raw):
+        tag, n = struct.unpack_from("<IQ", raw, off); off += 12; rec[tag] = raw[off:off + n]; off += n
+    ps = assets.turntable_env_scene(glb, os.path.join(ROOT, "tests", "assets", "env_outdoor.hdr"))
+    assert np.array_equal(np.frombuffer(rec[1], np.float32).reshape(-1, 25)[:, :3], ps.positions[:, :3])
+    assert np.array_equal(np.frombuffer(rec[2], np.uint32), ps.indices) and np.array_equal(np.frombuffer(rec[3], np.uint32), ps.mat_ids)
+    assert np.array_equal(np.frombuffer(rec[4], np.float32).reshape(-1, 4), ps.normals) and np.array_equal(np.frombuffer(rec[5], np.float32).reshape(-1, 2), ps.uvs)
+    assert np.array_equal(np.frombuffer(rec[6], np.uint32), np.asarray(ps.mat_colors, np.float32).view(np.uint32).reshape(-1))      # incl. the texture-mean base colour
+    assert np.frombuffer(rec[7], ps.instances.dtype).tobytes() == ps.instances.tobytes()                                            # T * R_y(180) * S
+    assert rec[8] == ps.light_ssbo.tobytes()                                                                                        # key light + emissive-mesh auto light + env index
+    assert tuple(np.frombuffer(rec[9], np.uint32)) == (2048, 2048, 4) and np.array_equal(np.frombuffer(rec[10], np.uint8).reshape(ps.textures.shape), ps.textures)

@@ -3,7 +3,7 @@
 TAG=$1; IFS=';' read -ra CFGS <<< "$2"; WLS=${3:-"helmet synthetic2m"}
 O=gpurun_out; : > $O/${TAG}_sweep.txt
 for WL in $WLS; do for C in "${CFGS[@]}"; do
-  L=$(env $C timeout 300 python bench.py --workload $WL --steps 6 --warmup 3 --no-cpu-baseline 2>>$O/${TAG}_sweep.err)
+  L=$(env $C timeout 300 python bench.py --workload $WL --steps 6 --warmup 3 --no-cpu-baseline --no-workloads 2>>$O/${TAG}_sweep.err)
   echo "$L" | python -c "
 import sys, json
 d = json.loads(sys.stdin.read()); k = d['kernels']
