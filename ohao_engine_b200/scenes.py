@@ -293,7 +293,7 @@ def emissive_mesh_lights(meshes: List[Mesh]) -> List[Light]:
                 x = np.asarray(m.xform, f32).reshape(3, 4)
                 center = x[:, :3] @ mid + x[:, 3]
                 out.append(Light(position=tuple(float(v) for v in center), color=tuple(float(f32(v)) for v in col), intensity=min(power * 0.1, 20.0),
-                                 radius=float(np.linalg.norm(bmax - bmin) * f32(0.3)), direction=(0.0, -1.0, 0.0)))
+                                 radius=float(np.linalg.norm(bmax - bmin) * f32(0.3)), direction=(0.0, -1.0, 0.0), outer_cone=0.0))   # gl.extra = vec4(0)
             break                                        # one light per actor
     return out
 
@@ -484,7 +484,7 @@ def helmet_class(ntris: int = 50000, tex_size: int = 2048, env_size=(1024, 512),
         bmin, bmax = P.min(0), P.max(0)
         center = (bmin + bmax) * 0.5 + np.array([0.0, 1.15, 0.0], np.float32)
         lights.append(Light(position=tuple(float(v) for v in center), color=tuple(float(v) for v in col), intensity=inten,
-                            radius=float(np.linalg.norm(bmax - bmin) * 0.3)))
+                            radius=float(np.linalg.norm(bmax - bmin) * 0.3), outer_cone=0.0))
     env = procedural_env(env_size[0], env_size[1])
     return pack_scene([hero, ground], lights, env=env, name=f"helmet_class_{I.size // 3 + 2}")
 
