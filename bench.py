@@ -155,7 +155,7 @@ def measured_profile(workload: str, integrator: str, kernel: str):
             "thr_per_inst": e.get("thr_per_inst"), "l2_hit_pct": e.get("l2_hit_pct"), "issue_active_pct": e.get("issue_active_pct"), "source": e.get("source")}
 
 
-def measure(r, ps, cam, workload, integrator, denoise, W, H, spp, steps, warmup, world=1, rank=0, local=0, dist=None, torch=None, sample_clocks=True):
+def measure(r, ps, cam, workload, integrator, denoise, W, H, spp, steps, warmup, world=1, rank=0, local=0, dist=None, torch=None, sample_clocks=True, strong=False):
     """Warm-up, the device-timed region, the e2e region; returns the pieces of the JSON line (rank 0 assembles them)."""
     from ohao_engine_b200 import binding as B
     import copy, math as _m
@@ -168,9 +168,11 @@ def measure(r, ps, cam, workload, integrator, denoise, W, H, spp, steps, warmup,
         radius = _m.hypot(base_cam.position[0], base_cam.position[2]); ang0 = _m.atan2(base_cam.position[2], base_cam.position[0])
     v, p = cam.view(), cam.proj(W, H)
     block = (warmup + steps) * spp                      # sample indices per rank: contiguous block, rank-major
-    if world > 1:
+    if world > 1 or strong:
         r.set_accum_mode(True)
     r.set_render_seed(rank * block)
+    ldr_img = np.empty((H, W, 4), np.uint8)
+    image_no = [0]
     accum_t = None
     if world > 1:
         ptr, nbytes = r.accum_dev_ptr()
@@ -186,7 +188,17 @@ def measure(r, ps, cam, workload, integrator, denoise, W, H, spp, steps, warmup,
         if torch is not None: torch.cuda.synchronize()
 
     def step():
-        """One pass of the hot path: offline = spp samples per pixel; realtime = one frame of the orbit."""
+        """One pass of the hot path: offline = spp samples per pixel; realtime = one frame of the orbit.
+        Strong scaling: one step = one COMPLETE image of spp x world samples per pixel — this rank renders its block of
+        sample indices into a cleared sum image, ONE NCCL reduce, resolve and the RGBA8 readback on rank 0, all inside."""
+        if strong:
+            r.clear_accum(); r.set_render_seed(image_no[0] * spp * world + rank * spp); image_no[0] += 1
+            r.render(v, p, spp)
+            if world > 1:
+                r.synchronize(); dist.reduce(accum_t, dst=0, op=dist.ReduceOp.SUM); torch.cuda.synchronize()
+            if rank == 0:
+                r.resolve(); r.get_pixels(ldr_img)
+            return
         if not realtime:
             r.render(v, p, spp); return
         a = ang0 + _m.radians(0.5 * frame_no[0]); frame_no[0] += 1
@@ -204,7 +216,7 @@ def measure(r, ps, cam, workload, integrator, denoise, W, H, spp, steps, warmup,
     r.timer_start()
     for _ in range(steps):
         step()
-    if world > 1:
+    if world > 1 and not strong:
         r.synchronize()
         dist.reduce(accum_t, dst=0, op=dist.ReduceOp.SUM)       # NCCL over NVLink: one reduce per image
         torch.cuda.synchronize()
@@ -232,6 +244,7 @@ def measure(r, ps, cam, workload, integrator, denoise, W, H, spp, steps, warmup,
     for _ in range(steps):
         r.update_rt_material_params(mat); r.update_rt_light_params(lights)      # updateRTMaterialParams / updateRTLightParams
         step()
+        if strong: continue                                                        # reduce + resolve + readback are part of a strong-scaling step
         if world > 1: r.resolve()
         r.get_pixels(ldr)                                                          # getPixelSpan(): blocking readback
     barrier()
@@ -324,6 +337,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bounded CPU-baseline sample (rank 0, N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-workloads", action="store_true", help="skip the `workloads` array (the other single-GPU BASELINE configs)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong: every step is one fixed image of --image-spp samples per pixel split over the N GPUs (reduce + resolve + readback inside the step)")
+    ap.add_argument("--image-spp", type=int, default=256, help="strong scaling: samples per pixel of the fixed image (configs[1]: 256)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.spp_step is None: args.spp_step = 1 if args.integrator == "realtime" else 16
@@ -365,18 +381,23 @@ def main():
     r.build_accel()                                   # second build: the first carries module load + allocation (bvh_build_ms)
     st = r.accel_stats()
     spp = args.spp_step
-    m = measure(r, ps, cam, args.workload, args.integrator, args.denoise, Wd, Hd, spp, args.steps, args.warmup, world, rank, local, dist, torch)
+    strong = args.scaling == "strong"
+    if strong:
+        if realtime or args.image_spp % world: raise SystemExit("bench.py: --scaling strong needs the offline integrator and --image-spp divisible by the GPU count")
+        spp = args.image_spp // world                       # this rank's share of every image
+    m = measure(r, ps, cam, args.workload, args.integrator, args.denoise, Wd, Hd, spp, args.steps, args.warmup, world, rank, local, dist, torch, strong=strong)
     ms, tot = m["ms"], m["tot"]
 
     if rank == 0:
         kern, roof = kernel_table(m, st, args.workload, args.integrator, Wd, Hd, spp, args.steps, torch.cuda.get_device_properties(local).multi_processor_count)
         out = {
             "metric": METRIC, "value": m["value"], "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": describe(desc, args.integrator, args.denoise), "resolution": [Wd, Hd], "spp_per_step": spp, "integrator": args.integrator, "tris": int(st.num_tris),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": describe(desc, args.integrator, args.denoise), "resolution": [Wd, Hd], "spp_per_step": spp * (world if strong else 1), "spp_per_gpu_per_step": spp, "integrator": args.integrator, "tris": int(st.num_tris),
                        "frames_per_s": (args.steps / (ms * 1e-3)) if realtime else None, "treelet_passes": int(st.treelet_passes),
                        "bvh_nodes": int(st.num_nodes), "bvh_sah": round(float(st.sah_cost), 2), "bvh_build_ms": round(float(st.build_ms), 3),
-                       "parallelism": f"spp-shard x{world}" if world > 1 else "single GPU",
+                       "parallelism": (f"one fixed {args.image_spp}-spp image per step, sample-index blocks over {world} GPU(s), NCCL reduce + resolve + RGBA8 readback inside the step" if strong
+                                       else (f"spp-shard x{world}" if world > 1 else "single GPU")),
                        "l2": "path-state working set %.1f GB per step >> 126 MB L2 (no explicit flush)" % (Wd * Hd * min(spp, 16) * (337 if realtime else 273) / 1e9)},
             "rays": rays_block(tot, ms),
             "kernels": kern,
@@ -385,7 +406,7 @@ def main():
             "gpu_launches": int(m["cnt"]["kernel_launches"]),
             "clocks": m["clk"],
         }
-        if world == 1 and not args.no_workloads:
+        if world == 1 and not args.no_workloads and not strong:
             # the other single-GPU configurations of BASELINE.json, same process, same box (each a few seconds)
             del r
             out["workloads"] = []

@@ -1,9 +1,13 @@
 // host/cornell_box.cpp — the reference's examples/cornell_box.cpp:57-170 on the B200 path tracer.
-//   cornell_box [out.png] [spp] [--denoise=none] [--width W --height H] [--realtime] [--device N] [--seed S]
+//   cornell_box [out.png] [spp] [--denoise=none] [--width W --height H] [--realtime] [--device N] [--seed S] [--gpus N]
+// --gpus N (offline): the spp are split into N contiguous sample-index blocks, one GPU each, summed by ONE ncclReduce (multi_gpu.hpp).
 // Same scene, camera and call sequence; differences: resolution is a flag (the reference hard-codes 1920x1080, quirk Q11)
 // and `spp` render() calls are made instead of spp+3 (the Vulkan readback ring lags 3 frames, Q10; getPixelSpan here is
 // current), so the image holds exactly `spp` samples in both.
 #include "ohao_b200_host.hpp"
+#ifdef OHB_HOST_NCCL
+#include "multi_gpu.hpp"
+#endif
 #include <chrono>
 using namespace ohao;
 
@@ -21,9 +25,8 @@ int main(int argc, char** argv) {
     const bool realtime = hasFlag(argc, argv, "realtime");
     std::cout << "OHAO Cornell Box — " << W << "x" << H << " @ " << samples << " spp\n";
 
-    Renderer renderer(W, H, int(flagValue(argc, argv, "device", 0)));
-    if (!renderer.initialize()) { std::cerr << "FATAL: renderer init failed\n"; return 1; }
-
+    const int gpus = int(flagValue(argc, argv, "gpus", 1));
+    const DenoiseMode denoise = denoiseFlag(argc, argv, realtime ? DenoiseMode::Atrous : DenoiseMode::None);   // Atrous = the SVGF denoiser (realtime profile)
     auto scene = std::make_unique<Scene>("Cornell Box");
     const float S = 5.0f;
     const vec3 white{0.73f, 0.73f, 0.73f}, red{0.65f, 0.05f, 0.05f}, green{0.12f, 0.45f, 0.15f};
@@ -49,11 +52,32 @@ int main(int argc, char** argv) {
         l->hasLight = true; l->light.type = LightType::Sphere; l->light.color = lightColors[i]; l->light.intensity = 5.0f; l->light.radius = 0.3f;
         l->position = {lightPositions[i][0], lightPositions[i][1], lightPositions[i][2]};
     }
-    renderer.setScene(scene.get());
-    auto& camera = renderer.getCamera();
-    camera.setPosition({0.0f, 0.0f, 13.0f}); camera.setFov(38.0f); camera.setRotation(0.0f, -90.0f);
-    renderer.setRenderMode(realtime ? RenderMode::RTRealtime : RenderMode::RTOffline);
-    renderer.setDenoiseMode(denoiseFlag(argc, argv, realtime ? DenoiseMode::Atrous : DenoiseMode::None));   // Atrous = the SVGF denoiser (realtime profile)
+    // scene / camera / mode wiring shared by the one-GPU path and every rank of the sharded path (the Scene is read-only after this)
+    auto wire = [&](Renderer& r) {
+        r.setScene(scene.get());
+        auto& camera = r.getCamera();
+        camera.setPosition({0.0f, 0.0f, 13.0f}); camera.setFov(38.0f); camera.setRotation(0.0f, -90.0f);
+        r.setRenderMode(realtime ? RenderMode::RTRealtime : RenderMode::RTOffline);
+        r.setDenoiseMode(denoise);
+        return true;
+    };
+    if (gpus > 1) {
+#ifdef OHB_HOST_NCCL
+        if (realtime) { std::cerr << "FATAL: --gpus shards the offline profile (the realtime profile's ReSTIR reuse reads neighbouring pixels of the previous frame)\n"; return 1; }
+        ShardedResult sr = renderSharded(gpus, W, H, uint32_t(samples), uint32_t(flagValue(argc, argv, "seed", 0)), wire);
+        if (!sr.ok) { std::cerr << "FATAL: sharded render failed\n"; return 1; }
+        std::cout << "Done: " << long(sr.totalMs) << " ms on " << gpus << " GPUs (render " << sr.renderMs << " ms, ncclReduce + sync " << sr.reduceMs << " ms; "
+                  << double(W) * H * samples / (sr.totalMs * 1e3) << " Msamples/s incl. reduce + readback)\n";
+        if (!writePNG(output, sr.pixels.data(), W, H)) { std::cerr << "FATAL: cannot write " << output << "\n"; return 1; }
+        std::cout << "Saved " << output << "\n";
+        return 0;
+#else
+        std::cerr << "FATAL: built without NCCL (make NCCL=1)\n"; return 1;
+#endif
+    }
+    Renderer renderer(W, H, int(flagValue(argc, argv, "device", 0)));
+    if (!renderer.initialize()) { std::cerr << "FATAL: renderer init failed\n"; return 1; }
+    wire(renderer);
     renderer.setRenderSeed(uint32_t(flagValue(argc, argv, "seed", 0)));
     if (!renderer.updateSceneBuffers()) { std::cerr << "FATAL: scene upload failed\n"; return 1; }
 

@@ -149,6 +149,14 @@ int ohb_env_sample_batch(ohb_ctx*, const float* u12, uint32_t n, float* dir_pdf,
 /* Parity hook: pdfEnvMap (env_sampling.glsl:79-94) for n caller-supplied unit directions dirs3[3n]. */
 int ohb_env_pdf_batch(ohb_ctx*, const float* dirs3, uint32_t n, float* pdf);
 
+/* NRD front-end packing (shaders/includes/rt/nrd_frontend.glsl:11-41 nrdPackRadianceHitDist / nrdLinearToYCoCg /
+ * nrdNormHitDist / nrdYCoCgToLinear, pt_raygen_offline.rgen:106-127 nrdPackNormalRoughness) evaluated on the device for n
+ * items: rad_hd_vz_rough[6n] = (radiance.rgb, hitDist, viewZ, roughness), normal_rough[4n] = (unit normal, roughness) ->
+ * packed_radiance[4n] = (Y, Co, Cg, normalised hit distance), packed_normal[4n] = R10G10B10A2 operands before quantisation,
+ * unpacked_rgb[3n] = nrdYCoCgToLinear(packed_radiance.xyz).  AOV arithmetic only: NRD itself is a third-party library. */
+int ohb_nrd_pack_batch(ohb_ctx*, const float* rad_hd_vz_rough, const float* normal_rough, uint32_t n,
+                       float* packed_radiance, float* packed_normal, float* unpacked_rgb);
+
 /* ---- acceleration structure: createBLAS + buildTLAS (rt_acceleration_structure.cpp:205-535) -- */
 int ohb_build_accel(ohb_ctx*);                         /* LBVH (Morton + radix sort) + SAH treelets */
 int ohb_get_accel_stats(ohb_ctx*, ohb_accel_stats*);

@@ -75,6 +75,7 @@ ABI = {
     "ohb_accum_dev_ptr": (_VP, [_VP, C.POINTER(C.c_size_t)]),
     "ohb_set_accum_mode": (_I, [_VP, _I]),
     "ohb_resolve": (_I, [_VP]), "ohb_clear_accum": (_I, [_VP]),
+    "ohb_nrd_pack_batch": (_I, [_VP, _VP, _VP, C.c_uint32, _VP, _VP, _VP]),
     "ohb_trace_batch": (_I, [_VP, _VP, _U32, _VP]),
     "ohb_occluded_batch": (_I, [_VP, _VP, _U32, _VP]),
     "ohb_set_sample_dump": (_I, [_VP, _VP, C.c_size_t]),
@@ -255,6 +256,12 @@ class Renderer:
     def env_pdf(self, dirs):
         d = np.ascontiguousarray(dirs, np.float32); pd = np.zeros(len(d), np.float32)
         self._ck(self.lib.ohb_env_pdf_batch(self.h, _p(d), len(d), _p(pd)), "ohb_env_pdf_batch"); return pd
+
+    def nrd_pack(self, rad_hd_vz_rough, normal_rough):
+        a = np.ascontiguousarray(rad_hd_vz_rough, np.float32); b = np.ascontiguousarray(normal_rough, np.float32); n = len(a)
+        pr = np.zeros((n, 4), np.float32); pn = np.zeros((n, 4), np.float32); back = np.zeros((n, 3), np.float32)
+        self._ck(self.lib.ohb_nrd_pack_batch(self.h, _p(a), _p(b), n, _p(pr), _p(pn), _p(back)), "ohb_nrd_pack_batch")
+        return pr, pn, back
 
     def counters(self) -> dict:
         c = Counters(); self._ck(self.lib.ohb_get_counters(self.h, C.byref(c)), "ohb_get_counters")

@@ -346,6 +346,25 @@ int ohb_env_pdf_batch(ohb_ctx* c, const float* dirs3, uint32_t n, float* pdf) {
     return 0;
 }
 
+int ohb_nrd_pack_batch(ohb_ctx* c, const float* rad_hd_vz_rough, const float* normal_rough, uint32_t n, float* packed_radiance, float* packed_normal, float* unpacked_rgb) {
+    if (!c) return 1;
+    if (!rad_hd_vz_rough || !normal_rough || !packed_radiance || !packed_normal || !unpacked_rgb) OHB_FAIL(c, "ohb_nrd_pack_batch: null array");
+    if (n == 0) return 0;
+    cudaSetDevice(c->device);
+    CU(c, c->hookRays.reserve(size_t(n) * 40)); CU(c, c->hookOut.reserve(size_t(n) * 32)); CU(c, c->hookAux.reserve(size_t(n) * 12));
+    float* in6 = c->hookRays.as<float>(); float* nr4 = in6 + size_t(n) * 6;
+    CU(c, cudaMemcpyAsync(in6, rad_hd_vz_rough, size_t(n) * 24, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(nr4, normal_rough, size_t(n) * 16, cudaMemcpyHostToDevice, c->stream));
+    f4* pr = c->hookOut.as<f4>(); f4* pn = pr + n;
+    launchNrdPack(in6, nr4, n, pr, pn, c->hookAux.as<float>(), c->stream, &c->launches);
+    CU(c, cudaMemcpyAsync(packed_radiance, pr, size_t(n) * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(packed_normal, pn, size_t(n) * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(unpacked_rgb, c->hookAux.p, size_t(n) * 12, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaGetLastError());
+    return 0;
+}
+
 int ohb_build_accel(ohb_ctx* c) {
     if (!c) return 1;
     cudaSetDevice(c->device);

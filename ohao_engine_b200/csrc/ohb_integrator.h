@@ -574,6 +574,32 @@ OHB_HD uint32_t shadePath(const SceneDev& sc, const FrameParams& fr, const PathA
 // (ACES(0.5 x) + gamma 2.2 -> RGBA8).  One thread per pixel walks its samples in index order so
 // the float sequence equals `samplesInBatch` consecutive dispatches of the reference.
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// NRD front-end packing (shaders/includes/rt/nrd_frontend.glsl:11-41, pt_raygen_offline.rgen:106-127): what the raygen
+// applies to its diffuse / specular radiance + hit distance and to the first-hit normal + roughness before they are
+// written to the NRD AOV images.  AOV-only — the beauty path never reads them.
+// ---------------------------------------------------------------------------------------------
+OHB_HD f3 nrdLinearToYCoCg(f3 c) { return mk3(dot(c, mk3(0.25f, 0.5f, 0.25f)), dot(c, mk3(0.5f, 0.0f, -0.5f)), dot(c, mk3(-0.25f, 0.5f, -0.25f))); }
+OHB_HD f3 nrdYCoCgToLinear(f3 c) { float t = c.x - c.z; return vmax(mk3(t + c.y, c.x + c.z, t - c.y), mk3(0.0f)); }
+OHB_HD float nrdNormHitDist(float hitDist, float viewZ, float roughness) {      // saturate(hitDist / ((A + |viewZ| B) mix(C, 1, rough^2))), A=3 B=0.1 C=20
+    float smc = clampf(roughness * roughness, 0.0f, 1.0f);
+    float f = (3.0f + fabsf(viewZ) * 0.1f) * mixf(20.0f, 1.0f, smc);
+    return clampf(hitDist / fmaxf(f, 1e-6f), 0.0f, 1.0f);
+}
+OHB_HD f4 nrdPackRadianceHitDist(f3 rad, float hitDist, float viewZ, float roughness) {
+    return mk4(nrdLinearToYCoCg(vmax(rad, mk3(0.0f))), nrdNormHitDist(fmaxf(hitDist, 0.0f), viewZ, roughness));
+}
+OHB_HD f4 nrdPackNormalRoughness(f3 n, float roughness) {                        // rotated octahedron + sign of n.z smuggled into the roughness channel
+    float l1 = fabsf(n.x) + fabsf(n.y) + fabsf(n.z);
+    n = mk3(n.x / l1, n.y / l1, n.z / l1);
+    f3 r;
+    r.y = n.y * 0.5f + 0.5f; r.x = n.x * 0.5f + r.y; r.y -= n.x * 0.5f;
+    roughness = fmaxf(roughness, 1.5f / 512.0f);
+    float s = (n.z < 0.0f) ? -roughness : roughness;
+    r.z = s * 0.5f + 0.5f;
+    return mk4(r, 0.0f);
+}
+
 OHB_HD f3 ACES(f3 x) {
     f3 n = x * (2.51f * x + mk3(0.03f)), dd = x * (2.43f * x + mk3(0.59f)) + mk3(0.14f);
     f3 r = n / dd;

@@ -256,6 +256,21 @@ void launchEnvPdf(const SceneDev& sc, const float* dirs3, uint32_t n, float* pdf
     k_env_pdf<<<gridFor(n, 128), 128, 0, st>>>(sc, dirs3, n, pdf); (*launches)++;
 }
 
+// NRD front-end packing hook (nrd_frontend.glsl:11-41): in6 = (radiance.rgb, hitDist, viewZ, roughness), nr4 = (normal, roughness)
+__global__ void k_nrd_pack(const float* in6, const float* nr4, uint32_t n, f4* packedRad, f4* packedNormal, float* unpackedRgb) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* a = in6 + size_t(i) * 6u;
+    f4 pr = nrdPackRadianceHitDist(mk3(a[0], a[1], a[2]), a[3], a[4], a[5]);
+    packedRad[i] = pr;
+    packedNormal[i] = nrdPackNormalRoughness(mk3(nr4[4 * i], nr4[4 * i + 1], nr4[4 * i + 2]), nr4[4 * i + 3]);
+    f3 back = nrdYCoCgToLinear(xyz(pr));
+    unpackedRgb[3 * i] = back.x; unpackedRgb[3 * i + 1] = back.y; unpackedRgb[3 * i + 2] = back.z;
+}
+void launchNrdPack(const float* in6, const float* nr4, uint32_t n, f4* packedRad, f4* packedNormal, float* unpackedRgb, cudaStream_t st, uint64_t* launches) {
+    k_nrd_pack<<<gridFor(n, 128), 128, 0, st>>>(in6, nr4, n, packedRad, packedNormal, unpackedRgb); (*launches)++;
+}
+
 // =============================================================================================
 // Traversal kernels (persistent, warp-granular dynamic fetch)
 // =============================================================================================
@@ -392,6 +407,9 @@ static void launchTraceShadow(unsigned smGrid8, const SceneDev& sc, const PathAr
     OHB_TRACE_DISPATCH(k_trace_shadow, sc, P, work, k.minActive, k.postponeDen);
 }
 #define SHADE_THREADS 128
+#ifndef OHB_SHADE_PREFETCH_DEFAULT
+#define OHB_SHADE_PREFETCH_DEFAULT 0
+#endif
 // ---- queue emission, STABLE AT TILE GRANULARITY ------------------------------------------------------------------
 // A CTA walks a contiguous tile of QTILE queue entries (QTILE_ROUNDS rounds of SHADE_THREADS), stages what it emits in
 // shared memory in queue order and claims its output range with ONE atomic per tile.  With per-warp atomics every pass
@@ -472,16 +490,45 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_surface(SceneDev sc, FramePar
 // fused kernel only pays off with the code-size work (shared sampler / texture / env-lookup / anisotropy copies, MUFU
 // reciprocals: 5 800 -> 3 900 SASS instructions) and with hit-only / miss-only warps (k_sort_hits): profiles/r1p, r1u,
 // r1v, r1z sweeps record each step.
+// Software prefetch (pf: 0 off, 1 into L2, 2 into L1; OHB_SHADE_PREFETCH).  k_shade waits on memory, not on issue slots (r2m: long
+// scoreboard 12-31 warps per issue, issue slots 17-36 % busy, DRAM 20 %): a path's shading is a chain of dependent gathers —
+// queue entry -> hit record -> triangle -> vertices / material -> texels, then the path record for the bounce.  Prefetches
+// carry no register and no scoreboard, so they widen that chain for free: the bounce body's record of THIS path and the
+// ray + hit record of the path this thread shades NEXT round are requested before the closest-hit shader starts, and the
+// next path's triangle-level data (indices, instance, material id) once its primitive id has arrived.
+__device__ __forceinline__ void shadePrefetch(const void* p, int pf) {
+    if (pf == 2) asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); else asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
 template <int MINB>
-__global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(SceneDev sc, FrameParams fr, PathArrays P) {
+__global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(SceneDev sc, FrameParams fr, PathArrays P, int pf) {
     OHB_TILE_EMIT(q);
     const uint32_t n = *P.countIn;
     for (uint32_t tile = blockIdx.x * QTILE; tile < n; tile += gridDim.x * QTILE) {
         q.begin();
+        const uint32_t i0 = tile + threadIdx.x;
+        uint32_t eNext = i0 < n ? P.queueSorted[i0] : OHB_Q_NONE;
         for (int r = 0; r < QTILE_ROUNDS; r++) {
-            const uint32_t i = tile + uint32_t(r) * SHADE_THREADS + threadIdx.x;
+            const uint32_t eCur = eNext;
+            const uint32_t iN = tile + uint32_t(r + 1) * SHADE_THREADS + threadIdx.x;
+            eNext = (r + 1 < QTILE_ROUNDS && iN < n) ? P.queueSorted[iN] : OHB_Q_NONE;
+            uint32_t primN = OHB_MISS;
+            if (pf) {
+                if (eCur != OHB_Q_NONE) {
+                    const uint32_t pc = OHB_Q_PATH(eCur);
+                    shadePrefetch(P.meta + pc, pf); shadePrefetch(P.rad + pc, pf);
+                    if (!(eCur & OHB_Q_PRIMARY)) shadePrefetch(P.thr + pc, pf);
+                    if (eCur & OHB_Q_PEND_A) shadePrefetch(P.pendA + pc, pf);
+                    if (eCur & OHB_Q_PEND_B) shadePrefetch(P.pendB + pc, pf);
+                }
+                if (eNext != OHB_Q_NONE) {
+                    const uint32_t pn = OHB_Q_PATH(eNext);
+                    shadePrefetch(P.rayO + pn, pf); shadePrefetch(P.rayD + pn, pf);
+                    primN = P.hit[pn].prim;                       // a real load: needed (much later) for the second-level prefetch
+                }
+            }
             uint32_t e = OHB_Q_NONE;
-            if (i < n) e = shadePath(sc, fr, P, P.queueSorted[i]);
+            if (eCur != OHB_Q_NONE) e = shadePath(sc, fr, P, eCur);
+            if (pf && primN != OHB_MISS) { shadePrefetch(sc.indices + size_t(primN) * 3u, pf); shadePrefetch(sc.triInst + primN, pf); shadePrefetch(sc.matIds + primN, pf); }
             q.round(e != OHB_Q_NONE, e);
         }
         q.flush(P.countOut, P.queueOut, true, 0u);
@@ -525,6 +572,7 @@ void launchOfflineBatch(const SceneDev& sc, const FrameParams& fr, PathArrays P,
     unsigned shadeGrid = unsigned(numSMs) * 8u;
     uint32_t iters = 1u + 2u * fr.maxBounces;
     static const int bounceOcc = []() { const char* e = getenv("OHB_BOUNCE_OCC"); return e ? atoi(e) : 8; }();
+    static const int shadePf = []() { const char* e = getenv("OHB_SHADE_PREFETCH"); int v = e ? atoi(e) : OHB_SHADE_PREFETCH_DEFAULT; return v < 0 ? 0 : (v > 2 ? 2 : v); }();
     for (uint32_t it = 0; it < iters; it++) {
         if (th) th->begin(0, st);
         launchTraceClosest(traceGrid, sc, P, work, st);
@@ -532,7 +580,7 @@ void launchOfflineBatch(const SceneDev& sc, const FrameParams& fr, PathArrays P,
         if (th) th->begin(7, st);
         k_sort_hits<<<shadeGrid, SHADE_THREADS, 0, st>>>(P);
         if (th) { th->end(7, st); th->begin(1, st); }
-        if (bounceOcc >= 8) k_shade<8><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P); else k_shade<6><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P);
+        if (bounceOcc >= 8) k_shade<8><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P, shadePf); else k_shade<6><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P, shadePf);
         if (th) th->end(1, st);
         if (th) th->begin(2, st);
         launchTraceShadow(traceGrid, sc, P, work + 1, st);

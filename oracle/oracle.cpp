@@ -643,6 +643,35 @@ void orc_env_sample_batch(void* h, const float* u12, uint32_t n, float* dir_pdf,
         if (pdf_of_dir) pdf_of_dir[i] = pdfEnvMap(*s, d);
     }
 }
+// NRD front-end packing: shaders/includes/rt/nrd_frontend.glsl:11-41 and pt_raygen_offline.rgen:106-127, line by line.
+static V3 nrdLinearToYCoCg(V3 c) { return {dot(c, V3{0.25f, 0.5f, 0.25f}), dot(c, V3{0.5f, 0.0f, -0.5f}), dot(c, V3{-0.25f, 0.5f, -0.25f})}; }     // :11-16
+static V3 nrdYCoCgToLinear(V3 c) {                                                                                                              // :18-25
+    float t = c.x - c.z; V3 r; r.y = c.x + c.z; r.x = t + c.y; r.z = t - c.y;
+    return {std::max(r.x, 0.0f), std::max(r.y, 0.0f), std::max(r.z, 0.0f)};
+}
+static float nrdNormHitDist(float hitDist, float viewZ, float roughness) {                                                                      // :28-34
+    float smc = roughness * roughness; smc = std::min(std::max(smc, 0.0f), 1.0f);
+    float f = (3.0f + std::fabs(viewZ) * 0.1f) * (20.0f * (1.0f - smc) + 1.0f * smc);
+    return std::min(std::max(hitDist / std::max(f, 1e-6f), 0.0f), 1.0f);
+}
+void orc_nrd_pack_batch(const float* in6, const float* nr4, uint32_t n, float* packedRad, float* packedNormal, float* unpackedRgb) {
+    for (uint32_t i = 0; i < n; i++) {
+        const float* a = in6 + size_t(i) * 6;
+        V3 rad{std::max(a[0], 0.0f), std::max(a[1], 0.0f), std::max(a[2], 0.0f)};                                                                // :37-41
+        V3 y = nrdLinearToYCoCg(rad);
+        float hd = nrdNormHitDist(std::max(a[3], 0.0f), a[4], a[5]);
+        packedRad[4 * i] = y.x; packedRad[4 * i + 1] = y.y; packedRad[4 * i + 2] = y.z; packedRad[4 * i + 3] = hd;
+        V3 nn{nr4[4 * i], nr4[4 * i + 1], nr4[4 * i + 2]}; float rough = nr4[4 * i + 3];                                                        // rgen:111-127
+        float l1 = std::fabs(nn.x) + std::fabs(nn.y) + std::fabs(nn.z);
+        nn = {nn.x / l1, nn.y / l1, nn.z / l1};
+        float ry = nn.y * 0.5f + 0.5f, rx = nn.x * 0.5f + ry; ry -= nn.x * 0.5f;
+        rough = std::max(rough, 1.5f / 512.0f);
+        float sgn = (nn.z < 0.0f) ? -rough : rough;
+        packedNormal[4 * i] = rx; packedNormal[4 * i + 1] = ry; packedNormal[4 * i + 2] = sgn * 0.5f + 0.5f; packedNormal[4 * i + 3] = 0.0f;
+        V3 back = nrdYCoCgToLinear(y);
+        unpackedRgb[3 * i] = back.x; unpackedRgb[3 * i + 1] = back.y; unpackedRgb[3 * i + 2] = back.z;
+    }
+}
 void orc_env_pdf_batch(void* h, const float* dirs3, uint32_t n, float* pdf) {
     Scene* s = (Scene*)h;
     for (uint32_t i = 0; i < n; i++) pdf[i] = pdfEnvMap(*s, V3{dirs3[3 * i], dirs3[3 * i + 1], dirs3[3 * i + 2]});

@@ -145,6 +145,7 @@ def lib() -> C.CDLL:
         _LIB.orc_scene_env_cdf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
         _LIB.orc_env_sample_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         _LIB.orc_env_pdf_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        _LIB.orc_nrd_pack_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         _LIB.orc_set_ray_recorder.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         _LIB.orc_ray_recorder_count.restype = C.c_uint32
         _LIB.orc_scene_set_materials.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
@@ -312,6 +313,13 @@ class OracleScene:
         finally:
             lib().orc_set_ray_recorder(None, None, None, 0)
         return rays[:n].copy(), hits[:n].copy(), kinds[:n].copy()
+
+
+def nrd_pack(rad_hd_vz_rough, normal_rough):
+    a = np.ascontiguousarray(rad_hd_vz_rough, np.float32); b = np.ascontiguousarray(normal_rough, np.float32); n = len(a)
+    pr = np.zeros((n, 4), np.float32); pn = np.zeros((n, 4), np.float32); back = np.zeros((n, 3), np.float32)
+    lib().orc_nrd_pack_batch(_p(a), _p(b), n, _p(pr), _p(pn), _p(back))
+    return pr, pn, back
 
 
 def env_cdf(rgba):

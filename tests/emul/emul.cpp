@@ -248,6 +248,15 @@ float emul_h2f(uint16_t h) { return h2f(h); }
 void emul_trav_stats(unsigned long long* nodes, unsigned long long* tris, int reset) { *nodes = g_statNodes; *tris = g_statTris; if (reset) { g_statNodes = 0; g_statTris = 0; } }
 void emul_set_warp_noise(unsigned on) { g_emulWarpNoise = on; g_emulWarpState = 12345u; }
 
+void emul_nrd_pack_batch(const float* in6, const float* nr4, uint32_t n, f4* packedRad, f4* packedNormal, float* unpackedRgb) {     // k_nrd_pack
+    for (uint32_t i = 0; i < n; i++) {
+        const float* a = in6 + size_t(i) * 6u;
+        f4 pr = nrdPackRadianceHitDist(mk3(a[0], a[1], a[2]), a[3], a[4], a[5]);
+        packedRad[i] = pr; packedNormal[i] = nrdPackNormalRoughness(mk3(nr4[4 * i], nr4[4 * i + 1], nr4[4 * i + 2]), nr4[4 * i + 3]);
+        f3 back = nrdYCoCgToLinear(xyz(pr));
+        unpackedRgb[3 * i] = back.x; unpackedRgb[3 * i + 1] = back.y; unpackedRgb[3 * i + 2] = back.z;
+    }
+}
 void emul_trace_batch(void* h, const ohb_ray* rays, uint32_t n, ohb_hit* hits) {
     SceneDev sc = ((EmulScene*)h)->dev();
     for (uint32_t i = 0; i < n; i++)

@@ -48,6 +48,7 @@ def lib():
         _LIB.emul_f2h.restype = C.c_uint16; _LIB.emul_f2h.argtypes = [C.c_float]
         _LIB.emul_h2f.restype = C.c_float; _LIB.emul_h2f.argtypes = [C.c_uint16]
         _LIB.emul_trav_stats.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.c_int]
+        _LIB.emul_nrd_pack_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     return _LIB
 
 
@@ -154,3 +155,10 @@ def set_warp_noise(on: bool):
 def trav_stats(reset=True):
     """(node visits, triangle tests) since the last reset."""
     a = C.c_ulonglong(); b = C.c_ulonglong(); lib().emul_trav_stats(C.byref(a), C.byref(b), 1 if reset else 0); return a.value, b.value
+
+
+def nrd_pack(rad_hd_vz_rough, normal_rough):
+    a = np.ascontiguousarray(rad_hd_vz_rough, np.float32); b = np.ascontiguousarray(normal_rough, np.float32); n = len(a)
+    pr = np.zeros((n, 4), np.float32); pn = np.zeros((n, 4), np.float32); back = np.zeros((n, 3), np.float32)
+    lib().emul_nrd_pack_batch(_p(a), _p(b), n, _p(pr), _p(pn), _p(back))
+    return pr, pn, back
