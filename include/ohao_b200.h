@@ -157,6 +157,25 @@ int ohb_env_pdf_batch(ohb_ctx*, const float* dirs3, uint32_t n, float* pdf);
 int ohb_nrd_pack_batch(ohb_ctx*, const float* rad_hd_vz_rough, const float* normal_rough, uint32_t n,
                        float* packed_radiance, float* packed_normal, float* unpacked_rgb);
 
+/* ---- hybrid-RT techniques: the other two consumers of the TLAS (rt_shadow_technique.cpp, rt_gi_technique.cpp) ---------- */
+/* Push constants of shaders/rt/rt_shadow.rgen:13-19 (RTShadowTechnique::record, rt_shadow_technique.cpp:503-505). */
+typedef struct ohb_hybrid_shadow_params {
+    float light_dir[3]; float light_radius;    /* direction the light travels; angular radius (directional) or sphere radius (point) */
+    float light_pos[3]; float light_range;
+    uint32_t light_type;                       /* 0 directional, 1 point / spot */
+    uint32_t sample_count;
+    uint32_t _pad[2];
+} ohb_hybrid_shadow_params;
+/* Push constants of shaders/rt/rt_gi.rgen:18-23. */
+typedef struct ohb_hybrid_gi_params { float light_pos[3]; float light_intensity; uint32_t sample_count; uint32_t frame_index; uint32_t _pad[2]; } ohb_hybrid_gi_params;
+/* rt_shadow.rgen: soft-shadow mask (R8_UNORM, W*H bytes) of the context's resolution from the G-buffer world positions
+ * (RGBA32F, all-zero texel = sky) and octahedron-encoded normals (2 floats per pixel in [0,1], encoding.glsl:15-22). */
+int ohb_hybrid_shadow(ohb_ctx*, const float* gbuf_position_rgba, const float* gbuf_normal_rg, const ohb_hybrid_shadow_params*, uint8_t* shadow_mask_r8);
+/* rt_gi.rgen + rt_gi.rchit: one-bounce diffuse GI with the temporal blend, RGBA16F out (W*H*4 fp16 bit patterns).
+ * instance_materials_rgba = materials[gl_InstanceID] of rt_gi.rchit:10-12 (rgb albedo, a >= 0.5 static), one vec4 per instance. */
+int ohb_hybrid_gi(ohb_ctx*, const float* gbuf_position_rgba, const float* gbuf_normal_rg, const float* gbuf_albedo_rgba, const float* gi_history_rgba,
+                  const float* instance_materials_rgba, uint32_t ninstances, const ohb_hybrid_gi_params*, uint16_t* gi_out_rgba16f);
+
 /* ---- acceleration structure: createBLAS + buildTLAS (rt_acceleration_structure.cpp:205-535) -- */
 int ohb_build_accel(ohb_ctx*);                         /* LBVH (Morton + radix sort) + SAH treelets */
 int ohb_get_accel_stats(ohb_ctx*, ohb_accel_stats*);

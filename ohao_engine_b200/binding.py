@@ -75,6 +75,7 @@ ABI = {
     "ohb_accum_dev_ptr": (_VP, [_VP, C.POINTER(C.c_size_t)]),
     "ohb_set_accum_mode": (_I, [_VP, _I]),
     "ohb_resolve": (_I, [_VP]), "ohb_clear_accum": (_I, [_VP]),
+    "ohb_hybrid_shadow": (_I, [_VP, _VP, _VP, _VP, _VP]), "ohb_hybrid_gi": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_uint32, _VP, _VP]),
     "ohb_nrd_pack_batch": (_I, [_VP, _VP, _VP, C.c_uint32, _VP, _VP, _VP]),
     "ohb_trace_batch": (_I, [_VP, _VP, _U32, _VP]),
     "ohb_occluded_batch": (_I, [_VP, _VP, _U32, _VP]),
@@ -256,6 +257,16 @@ class Renderer:
     def env_pdf(self, dirs):
         d = np.ascontiguousarray(dirs, np.float32); pd = np.zeros(len(d), np.float32)
         self._ck(self.lib.ohb_env_pdf_batch(self.h, _p(d), len(d), _p(pd)), "ohb_env_pdf_batch"); return pd
+
+    def hybrid_shadow(self, gpos, gnrm, params) -> np.ndarray:
+        """RTShadowTechnique (rt_shadow.rgen): R8 shadow mask from the G-buffer; params = oracle_py-compatible ctypes struct."""
+        gpos = np.ascontiguousarray(gpos, np.float32); gnrm = np.ascontiguousarray(gnrm, np.float32); mask = np.zeros((self.height, self.width), np.uint8)
+        self._ck(self.lib.ohb_hybrid_shadow(self.h, _p(gpos), _p(gnrm), C.byref(params), _p(mask)), "ohb_hybrid_shadow"); return mask
+
+    def hybrid_gi(self, gpos, gnrm, galbedo, history, inst_mat, params) -> np.ndarray:
+        """RTGITechnique (rt_gi.rgen): RGBA16F one-bounce GI (fp16 bit patterns)."""
+        a = [np.ascontiguousarray(x, np.float32) for x in (gpos, gnrm, galbedo, history, inst_mat)]; out = np.zeros((self.height, self.width, 4), np.uint16)
+        self._ck(self.lib.ohb_hybrid_gi(self.h, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), len(a[4]), C.byref(params), _p(out)), "ohb_hybrid_gi"); return out
 
     def nrd_pack(self, rad_hd_vz_rough, normal_rough):
         a = np.ascontiguousarray(rad_hd_vz_rough, np.float32); b = np.ascontiguousarray(normal_rough, np.float32); n = len(a)

@@ -346,6 +346,53 @@ int ohb_env_pdf_batch(ohb_ctx* c, const float* dirs3, uint32_t n, float* pdf) {
     return 0;
 }
 
+static int hybridUpload(ohb_ctx* c, const float* pos, const float* nrm, const float* albedo, const float* hist, const float* instMat, uint32_t ninst, float** dev) {
+    const size_t n = size_t(c->W) * c->H;
+    CU(c, c->hookRays.reserve(n * (16 + 8 + 16 + 16) + size_t(ninst) * 16 + 64));
+    float* base = c->hookRays.as<float>();
+    dev[0] = base; dev[1] = base + n * 4; dev[2] = dev[1] + n * 2; dev[3] = dev[2] + n * 4; dev[4] = dev[3] + n * 4;
+    CU(c, cudaMemcpyAsync(dev[0], pos, n * 16, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(dev[1], nrm, n * 8, cudaMemcpyHostToDevice, c->stream));
+    if (albedo) CU(c, cudaMemcpyAsync(dev[2], albedo, n * 16, cudaMemcpyHostToDevice, c->stream));
+    if (hist) CU(c, cudaMemcpyAsync(dev[3], hist, n * 16, cudaMemcpyHostToDevice, c->stream));
+    if (instMat) CU(c, cudaMemcpyAsync(dev[4], instMat, size_t(ninst) * 16, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+int ohb_hybrid_shadow(ohb_ctx* c, const float* pos, const float* nrm, const ohb_hybrid_shadow_params* p, uint8_t* mask) {
+    if (!c) return 1;
+    if (!pos || !nrm || !p || !mask) OHB_FAIL(c, "ohb_hybrid_shadow: null argument");
+    if (!c->accelValid) OHB_FAIL(c, "ohb_hybrid_shadow: no acceleration structure");
+    cudaSetDevice(c->device);
+    float* dev[5]; if (hybridUpload(c, pos, nrm, nullptr, nullptr, nullptr, 0, dev)) return 1;
+    const size_t n = size_t(c->W) * c->H;
+    CU(c, c->hookOut.reserve(n));
+    HybridShadowParams pc{}; pc.lightDir = mk3(p->light_dir[0], p->light_dir[1], p->light_dir[2]); pc.lightRadius = p->light_radius;
+    pc.lightPos = mk3(p->light_pos[0], p->light_pos[1], p->light_pos[2]); pc.lightRange = p->light_range; pc.W = c->W; pc.H = c->H; pc.lightType = p->light_type; pc.sampleCount = p->sample_count;
+    SceneDev s; fillScene(c, s);
+    launchHybridShadow(s, pc, reinterpret_cast<const f4*>(dev[0]), reinterpret_cast<const f2*>(dev[1]), c->hookOut.as<uint8_t>(), c->stream, &c->launches);
+    CU(c, cudaMemcpyAsync(mask, c->hookOut.p, n, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream)); CU(c, cudaGetLastError());
+    return 0;
+}
+int ohb_hybrid_gi(ohb_ctx* c, const float* pos, const float* nrm, const float* albedo, const float* hist, const float* instMat, uint32_t ninst, const ohb_hybrid_gi_params* p, uint16_t* out) {
+    if (!c) return 1;
+    if (!pos || !nrm || !albedo || !hist || !instMat || !p || !out) OHB_FAIL(c, "ohb_hybrid_gi: null argument");
+    if (!c->accelValid) OHB_FAIL(c, "ohb_hybrid_gi: no acceleration structure");
+    if (ninst < c->instances.size()) OHB_FAIL(c, "ohb_hybrid_gi: fewer instance materials than instances");
+    cudaSetDevice(c->device);
+    float* dev[5]; if (hybridUpload(c, pos, nrm, albedo, hist, instMat, ninst, dev)) return 1;
+    const size_t n = size_t(c->W) * c->H;
+    CU(c, c->hookOut.reserve(n * 8));
+    HybridGiParams pc{}; pc.lightPos = mk3(p->light_pos[0], p->light_pos[1], p->light_pos[2]); pc.lightIntensity = p->light_intensity; pc.W = c->W; pc.H = c->H;
+    pc.sampleCount = p->sample_count; pc.frameIndex = p->frame_index;
+    SceneDev s; fillScene(c, s);
+    launchHybridGi(s, pc, reinterpret_cast<const f4*>(dev[0]), reinterpret_cast<const f2*>(dev[1]), reinterpret_cast<const f4*>(dev[2]), reinterpret_cast<const f4*>(dev[3]),
+                   reinterpret_cast<const f4*>(dev[4]), c->hookOut.as<h4>(), c->stream, &c->launches);
+    CU(c, cudaMemcpyAsync(out, c->hookOut.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream)); CU(c, cudaGetLastError());
+    return 0;
+}
+
 int ohb_nrd_pack_batch(ohb_ctx* c, const float* rad_hd_vz_rough, const float* normal_rough, uint32_t n, float* packed_radiance, float* packed_normal, float* unpacked_rgb) {
     if (!c) return 1;
     if (!rad_hd_vz_rough || !normal_rough || !packed_radiance || !packed_normal || !unpacked_rgb) OHB_FAIL(c, "ohb_nrd_pack_batch: null array");

@@ -3,6 +3,7 @@
 #include "ohb_bvh.h"
 #include "ohb_integrator.h"
 #include "ohb_realtime.h"
+#include "ohb_hybrid.h"
 #include <cuda_runtime.h>
 #include <vector>
 
@@ -36,6 +37,8 @@ void launchBuild(const BuildArrays& b, uint64_t* keysTmp, uint32_t* valsTmp, uin
                  uint32_t treeletPasses, cudaStream_t st, uint64_t* launches);
 void launchEnvCdf(const f4* env, uint32_t W, uint32_t H, float* cond, float* marg, float* rowTotal, float* integral, cudaStream_t st, uint64_t* launches);
 void launchEnvSample(const SceneDev& sc, const float* u12, uint32_t n, f4* dirPdf, float* pdfOfDir, cudaStream_t st, uint64_t* launches);
+void launchHybridShadow(const SceneDev& sc, const HybridShadowParams& pc, const f4* gPos, const f2* gNrm, uint8_t* mask, cudaStream_t st, uint64_t* launches);
+void launchHybridGi(const SceneDev& sc, const HybridGiParams& pc, const f4* gPos, const f2* gNrm, const f4* gAlbedo, const f4* history, const f4* instMat, h4* out, cudaStream_t st, uint64_t* launches);
 void launchNrdPack(const float* in6, const float* nr4, uint32_t n, f4* packedRad, f4* packedNormal, float* unpackedRgb, cudaStream_t st, uint64_t* launches);
 void launchEnvPdf(const SceneDev& sc, const float* dirs3, uint32_t n, float* pdf, cudaStream_t st, uint64_t* launches);
 void launchOfflineBatch(const SceneDev& sc, const FrameParams& fr, PathArrays P, const FilmArrays& F,

@@ -256,6 +256,22 @@ void launchEnvPdf(const SceneDev& sc, const float* dirs3, uint32_t n, float* pdf
     k_env_pdf<<<gridFor(n, 128), 128, 0, st>>>(sc, dirs3, n, pdf); (*launches)++;
 }
 
+// Hybrid-RT techniques (ohb_hybrid.h): one thread per pixel, 8x8-pixel blocks so that a warp covers an 8x4 patch of neighbouring rays
+__global__ void __launch_bounds__(64) k_hybrid_shadow(SceneDev sc, HybridShadowParams pc, const f4* gPos, const f2* gNrm, uint8_t* mask) {
+    uint32_t x = blockIdx.x * 8u + (threadIdx.x & 7u), y = blockIdx.y * 8u + (threadIdx.x >> 3);
+    if (x < pc.W && y < pc.H) mask[size_t(y) * pc.W + x] = hybridShadowPixel(sc, pc, gPos, gNrm, x, y);
+}
+__global__ void __launch_bounds__(64) k_hybrid_gi(SceneDev sc, HybridGiParams pc, const f4* gPos, const f2* gNrm, const f4* gAlbedo, const f4* history, const f4* instMat, h4* out) {
+    uint32_t x = blockIdx.x * 8u + (threadIdx.x & 7u), y = blockIdx.y * 8u + (threadIdx.x >> 3);
+    if (x < pc.W && y < pc.H) out[size_t(y) * pc.W + x] = hybridGiPixel(sc, pc, gPos, gNrm, gAlbedo, history, instMat, x, y);
+}
+void launchHybridShadow(const SceneDev& sc, const HybridShadowParams& pc, const f4* gPos, const f2* gNrm, uint8_t* mask, cudaStream_t st, uint64_t* launches) {
+    k_hybrid_shadow<<<dim3((pc.W + 7u) / 8u, (pc.H + 7u) / 8u), 64, 0, st>>>(sc, pc, gPos, gNrm, mask); (*launches)++;
+}
+void launchHybridGi(const SceneDev& sc, const HybridGiParams& pc, const f4* gPos, const f2* gNrm, const f4* gAlbedo, const f4* history, const f4* instMat, h4* out, cudaStream_t st, uint64_t* launches) {
+    k_hybrid_gi<<<dim3((pc.W + 7u) / 8u, (pc.H + 7u) / 8u), 64, 0, st>>>(sc, pc, gPos, gNrm, gAlbedo, history, instMat, out); (*launches)++;
+}
+
 // NRD front-end packing hook (nrd_frontend.glsl:11-41): in6 = (radiance.rgb, hitDist, viewZ, roughness), nr4 = (normal, roughness)
 __global__ void k_nrd_pack(const float* in6, const float* nr4, uint32_t n, f4* packedRad, f4* packedNormal, float* unpackedRgb) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -535,6 +535,14 @@ static void tonemapStore(V3 acc, uint8_t* px) {   // pt_raygen_offline.rgen:1339
 
 #include "oracle_realtime.inl"
 #include "oracle_svgf.inl"
+// rows [0, H) over nthreads host threads (dynamic)
+template <class F> static void parallelRows(uint32_t H, int nthreads, F f) {
+    std::atomic<uint32_t> next{0};
+    auto work = [&]() { for (;;) { uint32_t y = next.fetch_add(1); if (y >= H) break; f(y); } };
+    std::vector<std::thread> th; for (int t = 1; t < std::max(nthreads, 1); t++) th.emplace_back(work);
+    work(); for (auto& t : th) t.join();
+}
+#include "oracle_hybrid.inl"
 
 }  // namespace orc
 
@@ -671,6 +679,13 @@ void orc_nrd_pack_batch(const float* in6, const float* nr4, uint32_t n, float* p
         V3 back = nrdYCoCgToLinear(y);
         unpackedRgb[3 * i] = back.x; unpackedRgb[3 * i + 1] = back.y; unpackedRgb[3 * i + 2] = back.z;
     }
+}
+void orc_hybrid_shadow(void* h, uint32_t W, uint32_t H, const float* gPos, const float* gNrm, const orc_hybrid_shadow_params* p, uint8_t* mask, int nthreads) {
+    hybridShadow(*(Scene*)h, W, H, gPos, gNrm, *p, mask, nthreads);
+}
+void orc_hybrid_gi(void* h, uint32_t W, uint32_t H, const float* gPos, const float* gNrm, const float* gAlbedo, const float* history, const float* instMat,
+                   const orc_hybrid_gi_params* p, uint16_t* out, int nthreads) {
+    hybridGi(*(Scene*)h, W, H, gPos, gNrm, gAlbedo, history, instMat, *p, out, nthreads);
 }
 void orc_env_pdf_batch(void* h, const float* dirs3, uint32_t n, float* pdf) {
     Scene* s = (Scene*)h;

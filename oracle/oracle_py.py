@@ -59,6 +59,15 @@ class RTArgs(C.Structure):
                 ("nthreads", C.c_int32), ("counters", Counters)]
 
 
+class HybridShadowParams(C.Structure):   # ohb_hybrid_shadow_params (include/ohao_b200.h)
+    _fields_ = [("light_dir", C.c_float * 3), ("light_radius", C.c_float), ("light_pos", C.c_float * 3), ("light_range", C.c_float),
+                ("light_type", C.c_uint32), ("sample_count", C.c_uint32), ("_pad", C.c_uint32 * 2)]
+
+
+class HybridGiParams(C.Structure):       # ohb_hybrid_gi_params
+    _fields_ = [("light_pos", C.c_float * 3), ("light_intensity", C.c_float), ("sample_count", C.c_uint32), ("frame_index", C.c_uint32), ("_pad", C.c_uint32 * 2)]
+
+
 class SvgfArgs(C.Structure):   # orc_svgf_args (oracle.cpp) == emul_svgf_args (tests/emul/emul.cpp)
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("reset", C.c_int32), ("nthreads", C.c_int32),
                 ("sigma_l", C.c_float), ("sigma_normal", C.c_float), ("sigma_depth", C.c_float), ("_pad", C.c_float),
@@ -145,6 +154,8 @@ def lib() -> C.CDLL:
         _LIB.orc_scene_env_cdf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
         _LIB.orc_env_sample_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         _LIB.orc_env_pdf_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        _LIB.orc_hybrid_shadow.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        _LIB.orc_hybrid_gi.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _LIB.orc_nrd_pack_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         _LIB.orc_set_ray_recorder.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         _LIB.orc_ray_recorder_count.restype = C.c_uint32
@@ -303,6 +314,16 @@ class OracleScene:
         d = np.ascontiguousarray(dirs, np.float32); pd = np.zeros(len(d), np.float32)
         lib().orc_env_pdf_batch(self.h, _p(d), len(d), _p(pd))
         return pd
+
+    def hybrid_shadow(self, W, H, gpos, gnrm, params: HybridShadowParams, nthreads=None):
+        gpos = np.ascontiguousarray(gpos, np.float32); gnrm = np.ascontiguousarray(gnrm, np.float32); mask = np.zeros((H, W), np.uint8)
+        lib().orc_hybrid_shadow(self.h, W, H, _p(gpos), _p(gnrm), C.byref(params), _p(mask), nthreads or (os.cpu_count() or 1))
+        return mask
+
+    def hybrid_gi(self, W, H, gpos, gnrm, galbedo, history, inst_mat, params: HybridGiParams, nthreads=None):
+        a = [np.ascontiguousarray(x, np.float32) for x in (gpos, gnrm, galbedo, history, inst_mat)]; out = np.zeros((H, W, 4), np.uint16)
+        lib().orc_hybrid_gi(self.h, W, H, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), C.byref(params), _p(out), nthreads or (os.cpu_count() or 1))
+        return out
 
     def record_rays(self, view, proj, width, height, nsamples, tile, cap=1 << 20, settings=None, first_sample=0):
         rays = np.zeros(cap, RAY_DTYPE); hits = np.zeros(cap, HIT_DTYPE); kinds = np.zeros(cap, np.uint8)

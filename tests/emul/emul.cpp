@@ -23,6 +23,7 @@ static unsigned long long g_statNodes = 0, g_statTris = 0;
 #include "../../ohao_engine_b200/csrc/ohb_bvh.h"
 #include "../../ohao_engine_b200/csrc/ohb_integrator.h"
 #include "../../ohao_engine_b200/csrc/ohb_realtime.h"
+#include "../../ohao_engine_b200/csrc/ohb_hybrid.h"
 #include <vector>
 #include <algorithm>
 #include <numeric>
@@ -248,6 +249,17 @@ float emul_h2f(uint16_t h) { return h2f(h); }
 void emul_trav_stats(unsigned long long* nodes, unsigned long long* tris, int reset) { *nodes = g_statNodes; *tris = g_statTris; if (reset) { g_statNodes = 0; g_statTris = 0; } }
 void emul_set_warp_noise(unsigned on) { g_emulWarpNoise = on; g_emulWarpState = 12345u; }
 
+void emul_hybrid_shadow(void* h, uint32_t W, uint32_t H, const f4* gPos, const f2* gNrm, const ohb_hybrid_shadow_params* p, uint8_t* mask) {     // k_hybrid_shadow
+    SceneDev sc = ((EmulScene*)h)->dev();
+    HybridShadowParams pc{}; pc.lightDir = mk3(p->light_dir[0], p->light_dir[1], p->light_dir[2]); pc.lightRadius = p->light_radius;
+    pc.lightPos = mk3(p->light_pos[0], p->light_pos[1], p->light_pos[2]); pc.lightRange = p->light_range; pc.W = W; pc.H = H; pc.lightType = p->light_type; pc.sampleCount = p->sample_count;
+    for (uint32_t y = 0; y < H; y++) for (uint32_t x = 0; x < W; x++) mask[size_t(y) * W + x] = hybridShadowPixel(sc, pc, gPos, gNrm, x, y);
+}
+void emul_hybrid_gi(void* h, uint32_t W, uint32_t H, const f4* gPos, const f2* gNrm, const f4* gAlbedo, const f4* hist, const f4* instMat, const ohb_hybrid_gi_params* p, h4* out) {   // k_hybrid_gi
+    SceneDev sc = ((EmulScene*)h)->dev();
+    HybridGiParams pc{}; pc.lightPos = mk3(p->light_pos[0], p->light_pos[1], p->light_pos[2]); pc.lightIntensity = p->light_intensity; pc.W = W; pc.H = H; pc.sampleCount = p->sample_count; pc.frameIndex = p->frame_index;
+    for (uint32_t y = 0; y < H; y++) for (uint32_t x = 0; x < W; x++) out[size_t(y) * W + x] = hybridGiPixel(sc, pc, gPos, gNrm, gAlbedo, hist, instMat, x, y);
+}
 void emul_nrd_pack_batch(const float* in6, const float* nr4, uint32_t n, f4* packedRad, f4* packedNormal, float* unpackedRgb) {     // k_nrd_pack
     for (uint32_t i = 0; i < n; i++) {
         const float* a = in6 + size_t(i) * 6u;

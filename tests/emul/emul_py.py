@@ -48,6 +48,8 @@ def lib():
         _LIB.emul_f2h.restype = C.c_uint16; _LIB.emul_f2h.argtypes = [C.c_float]
         _LIB.emul_h2f.restype = C.c_float; _LIB.emul_h2f.argtypes = [C.c_uint16]
         _LIB.emul_trav_stats.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.c_int]
+        _LIB.emul_hybrid_shadow.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _LIB.emul_hybrid_gi.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _LIB.emul_nrd_pack_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     return _LIB
 
@@ -90,6 +92,14 @@ class EmulScene:
     def occluded(self, rays):
         rays = np.ascontiguousarray(rays, O.RAY_DTYPE); occ = np.zeros(len(rays), np.uint8)
         lib().emul_occluded_batch(self.h, _p(rays), len(rays), _p(occ)); return occ
+
+    def hybrid_shadow(self, W, H, gpos, gnrm, params):
+        gpos = np.ascontiguousarray(gpos, np.float32); gnrm = np.ascontiguousarray(gnrm, np.float32); mask = np.zeros((H, W), np.uint8)
+        lib().emul_hybrid_shadow(self.h, W, H, _p(gpos), _p(gnrm), C.byref(params), _p(mask)); return mask
+
+    def hybrid_gi(self, W, H, gpos, gnrm, galbedo, history, inst_mat, params):
+        a = [np.ascontiguousarray(x, np.float32) for x in (gpos, gnrm, galbedo, history, inst_mat)]; out = np.zeros((H, W, 4), np.uint16)
+        lib().emul_hybrid_gi(self.h, W, H, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), C.byref(params), _p(out)); return out
 
     def env_sample(self, u12):
         u = np.ascontiguousarray(u12, np.float32); n = len(u); dp = np.zeros((n, 4), np.float32); pd = np.zeros(n, np.float32)

@@ -40,6 +40,8 @@ def test_gpu_matches_oracle():
     a, b = _inputs()
     r = B.Renderer(16, 16); r.set_scene(scenes.cornell_box())
     ref, got = O.nrd_pack(a, b), r.nrd_pack(a, b)
-    for x, y in zip(ref, got):
-        assert np.allclose(x, y, rtol=2e-7, atol=1e-7)                    # fp32 mul/add chains (FMA contraction on the device): <= 1 ulp
+    # fp32 mul/add chains, contracted into FMAs on the device: a few ulp of the LARGEST operand (Co / Cg cancel when r ~ b)
+    scale = np.abs(a[:, :3]).max(1, keepdims=True) + 1.0
+    assert (np.abs(ref[0] - got[0]) <= 5e-7 * scale).all() and (np.abs(ref[2] - got[2]) <= 1e-6 * scale).all()
+    assert np.abs(ref[1] - got[1]).max() <= 5e-7
     assert np.array_equal(ref[1][:, 3], got[1][:, 3]) and (np.sign(ref[1][:, 2] - 0.5) == np.sign(got[1][:, 2] - 0.5)).all()
