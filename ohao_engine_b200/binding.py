@@ -37,6 +37,15 @@ class Counters(C.Structure):
                 ("kernel_launches", C.c_uint64), ("_reserved", C.c_uint64 * 3)]
 
 
+class HybridShadowParams(C.Structure):   # ohb_hybrid_shadow_params
+    _fields_ = [("light_dir", C.c_float * 3), ("light_radius", C.c_float), ("light_pos", C.c_float * 3), ("light_range", C.c_float),
+                ("light_type", C.c_uint32), ("sample_count", C.c_uint32), ("_pad", C.c_uint32 * 2)]
+
+
+class HybridGiParams(C.Structure):       # ohb_hybrid_gi_params
+    _fields_ = [("light_pos", C.c_float * 3), ("light_intensity", C.c_float), ("sample_count", C.c_uint32), ("frame_index", C.c_uint32), ("_pad", C.c_uint32 * 2)]
+
+
 class AccelStats(C.Structure):
     _fields_ = [("num_tris", C.c_uint32), ("num_nodes", C.c_uint32), ("levels", C.c_uint32), ("max_leaf_tris", C.c_uint32),
                 ("sah_cost", C.c_float), ("build_ms", C.c_float), ("treelet_passes", C.c_uint32), ("_pad", C.c_uint32)]
@@ -259,7 +268,7 @@ class Renderer:
         self._ck(self.lib.ohb_env_pdf_batch(self.h, _p(d), len(d), _p(pd)), "ohb_env_pdf_batch"); return pd
 
     def hybrid_shadow(self, gpos, gnrm, params) -> np.ndarray:
-        """RTShadowTechnique (rt_shadow.rgen): R8 shadow mask from the G-buffer; params = oracle_py-compatible ctypes struct."""
+        """RTShadowTechnique (rt_shadow.rgen): R8 shadow mask from the G-buffer; params = HybridShadowParams (or any ctypes struct of that layout)."""
         gpos = np.ascontiguousarray(gpos, np.float32); gnrm = np.ascontiguousarray(gnrm, np.float32); mask = np.zeros((self.height, self.width), np.uint8)
         self._ck(self.lib.ohb_hybrid_shadow(self.h, _p(gpos), _p(gnrm), C.byref(params), _p(mask)), "ohb_hybrid_shadow"); return mask
 

@@ -72,7 +72,7 @@ def _check(osc, other, W, H, gpos, gnrm, alb, inst_mat, covered, call_shadow, ca
     im2 = inst_mat.copy(); im2[0, 3] = 0.0; gp.frame_index = 0                                          # instance 0 "animated": its hits count as misses (rt_gi.rchit:20-25)
     ref2, got2 = osc.hybrid_gi(W, H, gpos, gnrm, alb, hist, im2, gp), call_gi(hist, gp, im2)
     assert np.allclose(_h2f(ref2), _h2f(got2), **tol) if exact else (~np.isclose(_h2f(ref2), _h2f(got2), **tol)).mean() < 5e-3
-    assert _h2f(ref2)[..., :3].sum() < 0.9 * a[..., :3].sum()
+    assert _h2f(ref2)[..., :3].sum() < 0.98 * a[..., :3].sum()
 
 
 def test_hybrid_techniques_product_code_matches_oracle_on_the_host(helmet_small):
