@@ -110,7 +110,8 @@ typedef struct ohb_accel_stats {
     uint32_t max_leaf_tris;  /* triangles per leaf child                            */
     float    sah_cost;       /* SAH cost of the final tree (Ct=1, Ci=1)             */
     float    build_ms;       /* device time of the last ohb_build_accel             */
-    uint32_t treelet_passes; uint32_t _pad;
+    uint32_t treelet_passes;
+    float    update_ms;      /* device time of the last ohb_update_instances (MODE_UPDATE refit)   */
 } ohb_accel_stats;
 
 /* ---- lifecycle: PathTracer::{init,destroy,resize} (path_tracer.cpp:73-184,213-260) ---- */
@@ -177,7 +178,17 @@ int ohb_hybrid_gi(ohb_ctx*, const float* gbuf_position_rgba, const float* gbuf_n
                   const float* instance_materials_rgba, uint32_t ninstances, const ohb_hybrid_gi_params*, uint16_t* gi_out_rgba16f);
 
 /* ---- acceleration structure: createBLAS + buildTLAS (rt_acceleration_structure.cpp:205-535) -- */
+/* How ohb_set_instances' BLAS/TLAS interface is realised.  OHB_ACCEL_FLATTEN (default, the static fast path): every instance is
+ * transformed into ONE world-space 8-wide BVH.  OHB_ACCEL_TWO_LEVEL: one object-space BLAS per instance (createBLAS) under a TLAS
+ * over the instances' world boxes (buildTLAS); rays are mapped into object space on descent.  Changing the mode invalidates
+ * the structure (call ohb_build_accel). */
+enum { OHB_ACCEL_FLATTEN = 0, OHB_ACCEL_TWO_LEVEL = 1 };
+int ohb_set_accel_mode(ohb_ctx*, int mode);
 int ohb_build_accel(ohb_ctx*);                         /* LBVH (Morton + radix sort) + SAH treelets */
+/* VK_BUILD_ACCELERATION_STRUCTURE_MODE_UPDATE_KHR (rt_acceleration_structure.cpp:467 ALLOW_UPDATE, :503-512): the same n instances
+ * with new object->world transforms.  Two-level: TLAS boxes refit, BLASes untouched.  Flattened: triangles re-transformed and the
+ * tree refit bottom-up with its topology kept (no sort, no hierarchy build, no treelet pass).  Anything else changed -> rebuild. */
+int ohb_update_instances(ohb_ctx*, const ohb_instance* instances, uint32_t n);
 int ohb_get_accel_stats(ohb_ctx*, ohb_accel_stats*);
 
 /* ---- per-frame: IRTRendererProfile::{setRenderSettings,setRenderSeed,resetAccumulation,

@@ -20,6 +20,7 @@ PROFILE_OFFLINE, PROFILE_REALTIME = 0, 1
 DENOISE_NONE, DENOISE_ATROUS = 0, 4      # DenoiseMode values (denoise_types.hpp:13-19)
 FLAG_AOVS, FLAG_INTERNAL_DENOISE, FLAG_FIREFLY = 1, 2, 4
 FLAG_GOLDEN_COMPAT = 1 << 16
+ACCEL_FLATTEN, ACCEL_TWO_LEVEL = 0, 1
 SAMPLER_PCG, SAMPLER_SOBOL = 0, 1             # GLSL SAMPLER_PCG / SAMPLER_SOBOL (sampler_api.glsl:12-13)
 
 RAY_DTYPE = np.dtype([("origin", "<f4", (3,)), ("tmin", "<f4"), ("dir", "<f4", (3,)), ("tmax", "<f4")])
@@ -48,7 +49,7 @@ class HybridGiParams(C.Structure):       # ohb_hybrid_gi_params
 
 class AccelStats(C.Structure):
     _fields_ = [("num_tris", C.c_uint32), ("num_nodes", C.c_uint32), ("levels", C.c_uint32), ("max_leaf_tris", C.c_uint32),
-                ("sah_cost", C.c_float), ("build_ms", C.c_float), ("treelet_passes", C.c_uint32), ("_pad", C.c_uint32)]
+                ("sah_cost", C.c_float), ("build_ms", C.c_float), ("treelet_passes", C.c_uint32), ("update_ms", C.c_float)]
 
 
 # every symbol include/ohao_b200.h declares: name -> (restype, argtypes)
@@ -84,6 +85,7 @@ ABI = {
     "ohb_accum_dev_ptr": (_VP, [_VP, C.POINTER(C.c_size_t)]),
     "ohb_set_accum_mode": (_I, [_VP, _I]),
     "ohb_resolve": (_I, [_VP]), "ohb_clear_accum": (_I, [_VP]),
+    "ohb_set_accel_mode": (_I, [_VP, C.c_int]), "ohb_update_instances": (_I, [_VP, _VP, C.c_uint32]),
     "ohb_hybrid_shadow": (_I, [_VP, _VP, _VP, _VP, _VP]), "ohb_hybrid_gi": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_uint32, _VP, _VP]),
     "ohb_nrd_pack_batch": (_I, [_VP, _VP, _VP, C.c_uint32, _VP, _VP, _VP]),
     "ohb_trace_batch": (_I, [_VP, _VP, _U32, _VP]),
@@ -189,6 +191,16 @@ class Renderer:
         else:
             e = np.ascontiguousarray(env, np.float32)
             self._ck(self.lib.ohb_set_env(self.h, _p(e), e.shape[1], e.shape[0]), "ohb_set_env")
+
+    def set_accel_mode(self, two_level: bool):
+        """OHB_ACCEL_FLATTEN (default) or OHB_ACCEL_TWO_LEVEL (per-instance BLAS + TLAS); invalidates the structure."""
+        self._ck(self.lib.ohb_set_accel_mode(self.h, ACCEL_TWO_LEVEL if two_level else ACCEL_FLATTEN), "ohb_set_accel_mode")
+
+    def update_instances(self, instances) -> AccelStats:
+        """MODE_UPDATE: same instances, new transforms (TLAS refit, or re-transform + refit of the flattened tree)."""
+        inst = np.ascontiguousarray(instances)
+        self._ck(self.lib.ohb_update_instances(self.h, _p(inst), len(inst)), "ohb_update_instances")
+        return self.accel_stats()
 
     def build_accel(self) -> AccelStats:
         self._ck(self.lib.ohb_build_accel(self.h), "ohb_build_accel")

@@ -78,12 +78,16 @@ struct ohb_ctx {
     uint32_t lightCount = 0, envMapTexIdx = 0xFFFFFFFFu; float envIntensity = 1.0f;
     uint32_t texW = 0, texH = 0, texLayers = 0, envW = 0, envH = 0; float envIntegral = 0.0f;
     bool accelValid = false; uint32_t numActive = 0;
+    int accelMode = OHB_ACCEL_FLATTEN; uint32_t numTlasPrims = 0;
     ohb_accel_stats stats{};
     // scene (device)
     DevBuf positions, indices, normals, uvs, matIds, triInst, instXform, instNormalMat, instInv, matColors, tex, lights, env, marg, cond, rowTotal, integral;
     // accel (device)
     DevBuf activeTris, wtri, primLo, primHi, boundsBits, keys, vals, keysTmp, valsTmp, sortTemp, left, right, parentInner, parentLeaf,
            nodeLo, nodeHi, visit, wideCounters, wideItemsA, wideItemsB, sah, wnodes, tris;
+    // two-level structure: per-instance BLAS tables + the TLAS with its own (persistent) builder state for MODE_UPDATE refits
+    DevBuf blasLo, blasHi, blasInfo, instOfPrim, maxLevels, tlasNodes, tlasLeaves;
+    DevBuf tWtri, tPrimLo, tPrimHi, tBounds, tKeys, tVals, tKeysTmp, tValsTmp, tSortTemp, tLeft, tRight, tParentInner, tParentLeaf, tNodeLo, tNodeHi, tVisit, tWideCounters, tItemsA, tItemsB, tSah;
     // paths (device)
     DevBuf rayO, rayD, hit, thr, rad, pendA, pendB, meta, fh0, fh1, fh2, pay0, pay1, pay2, pay3, shO, shD, queueA, queueB, queueS, hitFlag, sobolTab, smallCounters, devCounters;
     uint32_t pathCapacity = 0;
@@ -185,6 +189,9 @@ void ohb_destroy(ohb_ctx* c) {
                      &c->accum, &c->ldr, &c->albedoAOV, &c->normalAOV, &c->sampleDump, &c->hookRays, &c->hookOut, &c->hookAux,
                      &c->accumPrev, &c->surf[0], &c->surf[1], &c->shad[0], &c->shad[1], &c->res[0][0], &c->res[0][1], &c->res[0][2],
                      &c->res[1][0], &c->res[1][1], &c->res[1][2], &c->rtDump[0], &c->rtDump[1], &c->rtDump[2],
+                     &c->blasLo, &c->blasHi, &c->blasInfo, &c->instOfPrim, &c->maxLevels, &c->tlasNodes, &c->tlasLeaves,
+                     &c->tWtri, &c->tPrimLo, &c->tPrimHi, &c->tBounds, &c->tKeys, &c->tVals, &c->tKeysTmp, &c->tValsTmp, &c->tSortTemp, &c->tLeft, &c->tRight, &c->tParentInner, &c->tParentLeaf,
+                     &c->tNodeLo, &c->tNodeHi, &c->tVisit, &c->tWideCounters, &c->tItemsA, &c->tItemsB, &c->tSah,
                      &c->motionAOV, &c->depthAOV, &c->svgfHistColor[0], &c->svgfHistColor[1], &c->svgfHistMoments[0], &c->svgfHistMoments[1],
                      &c->svgfHistGeom[0], &c->svgfHistGeom[1], &c->svgfColor[0], &c->svgfColor[1], &c->svgfVar[0], &c->svgfVar[1]};
     for (DevBuf* b : all) b->release();
@@ -305,6 +312,9 @@ int ohb_get_env_cdf(ohb_ctx* c, float* marg, float* cond, float* integral) {
 static void fillScene(ohb_ctx* c, SceneDev& s) {
     memset(&s, 0, sizeof(s));
     s.wnodes = c->wnodes.as<u4>(); s.tris = c->tris.as<f4>(); s.numTris = c->accelValid ? c->numActive : 0u; s.numWideNodes = c->accelValid ? c->stats.num_nodes : 0u;
+    s.twoLevel = (c->accelValid && c->accelMode == OHB_ACCEL_TWO_LEVEL) ? 1u : 0u;
+    s.tlasNodes = c->tlasNodes.as<u4>(); s.tlasLeaves = c->tlasLeaves.as<f4>(); s.blasInfo = c->blasInfo.as<u4>();
+    if (s.twoLevel) s.numWideNodes = 0u;
     s.indices = c->indices.as<uint32_t>(); s.normals = c->normals.as<f4>(); s.uvs = c->uvs.as<f2>(); s.matIds = c->matIds.as<uint32_t>();
     s.triInst = c->triInst.as<uint32_t>(); s.instNormalMat = c->instNormalMat.as<f4>(); s.instInv = c->instInv.as<f4>();
     s.matColors = c->matColors.as<f4>();
@@ -412,19 +422,13 @@ int ohb_nrd_pack_batch(ohb_ctx* c, const float* rad_hd_vz_rough, const float* no
     return 0;
 }
 
-int ohb_build_accel(ohb_ctx* c) {
-    if (!c) return 1;
-    cudaSetDevice(c->device);
-    if (!c->ntris) OHB_FAIL(c, "ohb_build_accel: no geometry");
-    // instance tables (normal matrix = transpose(inverse(mat3)), world->object) — pt_closesthit.rchit:66
-    uint32_t ni = uint32_t(c->instances.size());
-    std::vector<uint32_t> triInst(c->ntris, 0xFFFFFFFFu), active;
-    std::vector<float> xf(size_t(ni) * 12 + 12), nm(size_t(ni) * 12 + 12), iv(size_t(ni) * 12 + 12);
-    for (uint32_t i = 0; i < ni; i++) {
-        const ohb_instance& in = c->instances[i];
-        if (uint64_t(in.first_tri) + in.tri_count > c->ntris) OHB_FAIL(c, "ohb_build_accel: instance triangle range out of bounds");
-        memcpy(&xf[size_t(i) * 12], in.xform, 48);
-        const float* a = in.xform;
+// instance tables: object->world rows, normal matrix = transpose(inverse(mat3)) (pt_closesthit.rchit:66), world->object rows
+static void instanceTables(const std::vector<ohb_instance>& insts, std::vector<float>& xf, std::vector<float>& nm, std::vector<float>& iv) {
+    const size_t ni = insts.size();
+    xf.assign(ni * 12 + 12, 0.0f); nm.assign(ni * 12 + 12, 0.0f); iv.assign(ni * 12 + 12, 0.0f);
+    for (size_t i = 0; i < ni; i++) {
+        const float* a = insts[i].xform;
+        memcpy(&xf[i * 12], a, 48);
         float co[3][3];
         co[0][0] = a[5] * a[10] - a[6] * a[9];  co[0][1] = a[6] * a[8] - a[4] * a[10]; co[0][2] = a[4] * a[9] - a[5] * a[8];
         co[1][0] = a[2] * a[9] - a[1] * a[10];  co[1][1] = a[0] * a[10] - a[2] * a[8]; co[1][2] = a[1] * a[8] - a[0] * a[9];
@@ -432,69 +436,205 @@ int ohb_build_accel(ohb_ctx* c) {
         float det = a[0] * co[0][0] + a[1] * co[0][1] + a[2] * co[0][2];
         float id = 1.0f / det;
         for (int r = 0; r < 3; r++) {
-            for (int k = 0; k < 3; k++) nm[size_t(i) * 12 + r * 4 + k] = co[r][k] * id;
-            nm[size_t(i) * 12 + r * 4 + 3] = 0.0f;
+            for (int k = 0; k < 3; k++) nm[i * 12 + r * 4 + k] = co[r][k] * id;
+            nm[i * 12 + r * 4 + 3] = 0.0f;
         }
         for (int r = 0; r < 3; r++) {
-            float* row = &iv[size_t(i) * 12 + r * 4];
-            for (int k = 0; k < 3; k++) row[k] = nm[size_t(i) * 12 + k * 4 + r];
+            float* row = &iv[i * 12 + r * 4];
+            for (int k = 0; k < 3; k++) row[k] = nm[i * 12 + k * 4 + r];
             row[3] = -(row[0] * a[3] + row[1] * a[7] + row[2] * a[11]);
         }
-        if ((in.mask & 0xFFu) == 0u) continue;   // invisible to cullMask 0xFF
-        for (uint32_t t = in.first_tri; t < in.first_tri + in.tri_count; t++) { if (triInst[t] == 0xFFFFFFFFu) active.push_back(t); triInst[t] = i; }
     }
-    uint32_t n = uint32_t(active.size());
-    c->numActive = n;
-    CU(c, c->triInst.reserve(size_t(c->ntris) * 4)); CU(c, c->instXform.reserve(xf.size() * 4)); CU(c, c->instNormalMat.reserve(nm.size() * 4)); CU(c, c->instInv.reserve(iv.size() * 4));
-    CU(c, cudaMemcpyAsync(c->triInst.p, triInst.data(), size_t(c->ntris) * 4, cudaMemcpyHostToDevice, c->stream));
+}
+static int uploadInstanceTables(ohb_ctx* c) {
+    std::vector<float> xf, nm, iv; instanceTables(c->instances, xf, nm, iv);
+    CU(c, c->instXform.reserve(xf.size() * 4)); CU(c, c->instNormalMat.reserve(nm.size() * 4)); CU(c, c->instInv.reserve(iv.size() * 4));
     CU(c, cudaMemcpyAsync(c->instXform.p, xf.data(), xf.size() * 4, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(c->instNormalMat.p, nm.data(), nm.size() * 4, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(c->instInv.p, iv.data(), iv.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    memset(&c->stats, 0, sizeof(c->stats));
-    c->stats.num_tris = n;
-    if (n == 0) { c->accelValid = true; CU(c, cudaStreamSynchronize(c->stream)); return 0; }
-    size_t nn = n;
-    CU(c, c->activeTris.reserve(nn * 4)); CU(c, cudaMemcpyAsync(c->activeTris.p, active.data(), nn * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));        // the staging vectors die here
+    return 0;
+}
+// BuildArrays over the context's main builder buffers (sized for `cap` primitives) — the flattened tree, or one BLAS at a time
+static int mainBuildArrays(ohb_ctx* c, size_t cap, BuildArrays& b) {
+    const size_t nn = cap;
     CU(c, c->wtri.reserve(nn * 48)); CU(c, c->primLo.reserve(nn * 16)); CU(c, c->primHi.reserve(nn * 16)); CU(c, c->boundsBits.reserve(32));
     CU(c, c->keys.reserve(nn * 8)); CU(c, c->vals.reserve(nn * 4)); CU(c, c->keysTmp.reserve(nn * 8)); CU(c, c->valsTmp.reserve(nn * 4));
-    CU(c, c->sortTemp.reserve(size_t(radixSortTempWords(n)) * 4));
+    CU(c, c->sortTemp.reserve(size_t(radixSortTempWords(uint32_t(cap))) * 4));
     CU(c, c->left.reserve(nn * 4)); CU(c, c->right.reserve(nn * 4)); CU(c, c->parentInner.reserve(nn * 4)); CU(c, c->parentLeaf.reserve(nn * 4));
     CU(c, c->nodeLo.reserve(nn * 16)); CU(c, c->nodeHi.reserve(nn * 16));
     CU(c, c->visit.reserve(nn * 4)); CU(c, c->wideCounters.reserve(16)); CU(c, c->sah.reserve(8));
     CU(c, c->wideItemsA.reserve((nn / 4 + 2) * sizeof(WideItem))); CU(c, c->wideItemsB.reserve((nn / 4 + 2) * sizeof(WideItem)));
-    CU(c, c->wnodes.reserve(nn * 16 * OHB_WNODE_VECS)); CU(c, c->tris.reserve(nn * 48));     // a wide node is a binary node with > 3 triangles: fewer than n
-    BuildArrays b{};
+    memset(&b, 0, sizeof(b));
     b.positions = c->positions.as<uint8_t>(); b.posStride = c->posStride; b.indices = c->indices.as<uint32_t>(); b.triInst = c->triInst.as<uint32_t>();
-    b.instXform = c->instXform.as<f4>(); b.activeTris = c->activeTris.as<uint32_t>(); b.n = n;
+    b.instXform = c->instXform.as<f4>(); b.activeTris = c->activeTris.as<uint32_t>(); b.n = uint32_t(cap);
     b.wtri = c->wtri.as<f4>(); b.primLo = c->primLo.as<f4>(); b.primHi = c->primHi.as<f4>(); b.boundsBits = c->boundsBits.as<uint32_t>();
     b.keys = c->keys.as<uint64_t>(); b.vals = c->vals.as<uint32_t>();
     b.left = c->left.as<int32_t>(); b.right = c->right.as<int32_t>(); b.parentInner = c->parentInner.as<int32_t>(); b.parentLeaf = c->parentLeaf.as<int32_t>();
     b.nodeLo = c->nodeLo.as<f4>(); b.nodeHi = c->nodeHi.as<f4>();
     b.visit = c->visit.as<uint32_t>(); b.wideCounters = c->wideCounters.as<uint32_t>(); b.sah = c->sah.as<float>();
     b.wnodes = c->wnodes.as<u4>(); b.tris = c->tris.as<f4>();
-    CU(c, cudaEventRecord(c->evA, c->stream));
-    static const uint32_t treeletPasses = []() { const char* e = getenv("OHB_TREELET_PASSES"); return e ? uint32_t(strtoul(e, nullptr, 10)) : 3u; }();
-    launchBuild(b, c->keysTmp.as<uint64_t>(), c->valsTmp.as<uint32_t>(), c->sortTemp.as<uint32_t>(), c->wideItemsA.as<WideItem>(), c->wideItemsB.as<WideItem>(),
-                treeletPasses, c->stream, &c->launches);
-    c->stats.treelet_passes = treeletPasses;
-    CU(c, cudaEventRecord(c->evB, c->stream));
-    uint32_t wc[4] = {1, 0, 0, 0}; float sah[2] = {0, 0}; f4 rootLo{}, rootHi{};
-    CU(c, cudaMemcpyAsync(wc, c->wideCounters.p, 16, cudaMemcpyDeviceToHost, c->stream));
-    if (n >= 2) {
-        CU(c, cudaMemcpyAsync(&rootLo, c->nodeLo.p, 16, cudaMemcpyDeviceToHost, c->stream));
-        CU(c, cudaMemcpyAsync(&rootHi, c->nodeHi.p, 16, cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+static int tlasBuildArrays(ohb_ctx* c, uint32_t np, BuildArrays& b) {
+    const size_t nn = np;
+    CU(c, c->tWtri.reserve(nn * 48)); CU(c, c->tPrimLo.reserve(nn * 16)); CU(c, c->tPrimHi.reserve(nn * 16)); CU(c, c->tBounds.reserve(32));
+    CU(c, c->tKeys.reserve(nn * 8)); CU(c, c->tVals.reserve(nn * 4)); CU(c, c->tKeysTmp.reserve(nn * 8)); CU(c, c->tValsTmp.reserve(nn * 4));
+    CU(c, c->tSortTemp.reserve(size_t(radixSortTempWords(np)) * 4));
+    CU(c, c->tLeft.reserve(nn * 4)); CU(c, c->tRight.reserve(nn * 4)); CU(c, c->tParentInner.reserve(nn * 4)); CU(c, c->tParentLeaf.reserve(nn * 4));
+    CU(c, c->tNodeLo.reserve(nn * 16)); CU(c, c->tNodeHi.reserve(nn * 16));
+    CU(c, c->tVisit.reserve(nn * 4)); CU(c, c->tWideCounters.reserve(16)); CU(c, c->tSah.reserve(8));
+    CU(c, c->tItemsA.reserve((nn / 4 + 2) * sizeof(WideItem))); CU(c, c->tItemsB.reserve((nn / 4 + 2) * sizeof(WideItem)));
+    CU(c, c->tlasNodes.reserve((nn + 1) * 16 * OHB_WNODE_VECS)); CU(c, c->tlasLeaves.reserve((nn + 1) * 48));
+    memset(&b, 0, sizeof(b));
+    b.instXform = c->instXform.as<f4>(); b.n = np;
+    b.wtri = c->tWtri.as<f4>(); b.primLo = c->tPrimLo.as<f4>(); b.primHi = c->tPrimHi.as<f4>(); b.boundsBits = c->tBounds.as<uint32_t>();
+    b.keys = c->tKeys.as<uint64_t>(); b.vals = c->tVals.as<uint32_t>();
+    b.left = c->tLeft.as<int32_t>(); b.right = c->tRight.as<int32_t>(); b.parentInner = c->tParentInner.as<int32_t>(); b.parentLeaf = c->tParentLeaf.as<int32_t>();
+    b.nodeLo = c->tNodeLo.as<f4>(); b.nodeHi = c->tNodeHi.as<f4>();
+    b.visit = c->tVisit.as<uint32_t>(); b.wideCounters = c->tWideCounters.as<uint32_t>(); b.sah = c->tSah.as<float>();
+    b.wnodes = c->tlasNodes.as<u4>(); b.tris = c->tlasLeaves.as<f4>();
+    return 0;
+}
+static uint32_t treeletPassesKnob() { static const uint32_t v = []() { const char* e = getenv("OHB_TREELET_PASSES"); return e ? uint32_t(strtoul(e, nullptr, 10)) : 3u; }(); return v; }
+
+int ohb_set_accel_mode(ohb_ctx* c, int mode) {
+    if (!c) return 1;
+    if (mode != OHB_ACCEL_FLATTEN && mode != OHB_ACCEL_TWO_LEVEL) OHB_FAIL(c, "ohb_set_accel_mode: unknown mode");
+    if (mode != c->accelMode) { c->accelMode = mode; c->accelValid = false; }
+    return 0;
+}
+
+int ohb_build_accel(ohb_ctx* c) {
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    if (!c->ntris) OHB_FAIL(c, "ohb_build_accel: no geometry");
+    const bool twoLevel = c->accelMode == OHB_ACCEL_TWO_LEVEL;
+    uint32_t ni = uint32_t(c->instances.size());
+    std::vector<uint32_t> triInst(c->ntris, 0xFFFFFFFFu), active;
+    struct Range { uint32_t inst, first, count; }; std::vector<Range> ranges;     // per visible, non-empty instance: its slice of `active`
+    for (uint32_t i = 0; i < ni; i++) {
+        const ohb_instance& in = c->instances[i];
+        if (uint64_t(in.first_tri) + in.tri_count > c->ntris) OHB_FAIL(c, "ohb_build_accel: instance triangle range out of bounds");
+        if ((in.mask & 0xFFu) == 0u) continue;   // invisible to cullMask 0xFF
+        const uint32_t first = uint32_t(active.size());
+        for (uint32_t t = in.first_tri; t < in.first_tri + in.tri_count; t++) {
+            if (triInst[t] == 0xFFFFFFFFu) active.push_back(t);
+            else if (twoLevel) OHB_FAIL(c, "ohb_build_accel: two-level mode needs disjoint triangle ranges per instance (one BLAS per actor, rt_build.cpp:851-897)");
+            triInst[t] = i;
+        }
+        if (active.size() > first) ranges.push_back({i, first, uint32_t(active.size()) - first});
     }
-    CU(c, cudaMemcpyAsync(sah, c->sah.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    uint32_t n = uint32_t(active.size());
+    c->numActive = n; c->numTlasPrims = 0;
+    if (uploadInstanceTables(c)) return 1;
+    CU(c, c->triInst.reserve(size_t(c->ntris) * 4));
+    CU(c, cudaMemcpyAsync(c->triInst.p, triInst.data(), size_t(c->ntris) * 4, cudaMemcpyHostToDevice, c->stream));
+    memset(&c->stats, 0, sizeof(c->stats));
+    c->stats.num_tris = n;
+    if (n == 0) { c->accelValid = true; CU(c, cudaStreamSynchronize(c->stream)); return 0; }
+    size_t nn = n;
+    CU(c, c->activeTris.reserve(nn * 4)); CU(c, cudaMemcpyAsync(c->activeTris.p, active.data(), nn * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, c->wnodes.reserve(nn * 16 * OHB_WNODE_VECS)); CU(c, c->tris.reserve(nn * 48));     // a wide node is a binary node with > 3 triangles: fewer than n
+    const uint32_t treeletPasses = treeletPassesKnob();
+    c->stats.treelet_passes = treeletPasses;
+    if (!twoLevel) {
+        BuildArrays b; if (mainBuildArrays(c, nn, b)) return 1;
+        CU(c, cudaEventRecord(c->evA, c->stream));
+        launchBuild(b, c->keysTmp.as<uint64_t>(), c->valsTmp.as<uint32_t>(), c->sortTemp.as<uint32_t>(), c->wideItemsA.as<WideItem>(), c->wideItemsB.as<WideItem>(),
+                    treeletPasses, c->stream, &c->launches);
+        CU(c, cudaEventRecord(c->evB, c->stream));
+        uint32_t wc[4] = {1, 0, 0, 0}; float sah[2] = {0, 0}; f4 rootLo{}, rootHi{};
+        CU(c, cudaMemcpyAsync(wc, c->wideCounters.p, 16, cudaMemcpyDeviceToHost, c->stream));
+        if (n >= 2) {
+            CU(c, cudaMemcpyAsync(&rootLo, c->nodeLo.p, 16, cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaMemcpyAsync(&rootHi, c->nodeHi.p, 16, cudaMemcpyDeviceToHost, c->stream));
+        }
+        CU(c, cudaMemcpyAsync(sah, c->sah.p, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        CU(c, cudaGetLastError());
+        if (wc[3] > OHB_MAX_LEVELS) OHB_FAIL(c, "ohb_build_accel: the 8-wide BVH is deeper than OHB_MAX_LEVELS (degenerate geometry: too many coincident triangles)");
+        c->accelValid = true;
+        cudaEventElapsedTime(&c->stats.build_ms, c->evA, c->evB);
+        c->stats.num_nodes = wc[0];
+        c->stats.max_leaf_tris = OHB_MAX_LEAF;
+        c->stats.levels = wc[3] + 1u;
+        float ra = boxArea(xyz(rootLo), xyz(rootHi));
+        c->stats.sah_cost = (n >= 2 && ra > 0.0f) ? (sah[0] + sah[1]) / ra : float(n);
+        return 0;
+    }
+    // ---- two-level: one object-space BLAS per instance (createBLAS, rt_acceleration_structure.cpp:205-405) + the TLAS (buildTLAS, :419-535) ----
+    uint32_t maxCount = 0; for (const Range& r : ranges) maxCount = std::max(maxCount, r.count);
+    const uint32_t np = uint32_t(ranges.size());
+    BuildArrays b; if (mainBuildArrays(c, maxCount, b)) return 1;
+    CU(c, c->blasLo.reserve(size_t(ni) * 16 + 16)); CU(c, c->blasHi.reserve(size_t(ni) * 16 + 16)); CU(c, c->blasInfo.reserve(size_t(ni) * 16 + 16));
+    CU(c, c->instOfPrim.reserve(size_t(np) * 4 + 4)); CU(c, c->maxLevels.reserve(4));
+    std::vector<uint32_t> info(size_t(ni) * 4, 0u), iop(np);
+    for (uint32_t k = 0; k < np; k++) { const Range& r = ranges[k]; info[size_t(r.inst) * 4 + 0] = r.first; info[size_t(r.inst) * 4 + 1] = r.first; info[size_t(r.inst) * 4 + 2] = r.count; iop[k] = r.inst; }
+    CU(c, cudaMemcpyAsync(c->blasInfo.p, info.data(), info.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->instOfPrim.p, iop.data(), iop.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemsetAsync(c->maxLevels.p, 0, 4, c->stream));
+    CU(c, cudaEventRecord(c->evA, c->stream));
+    for (const Range& r : ranges) {
+        BuildArrays bi = b;
+        bi.objectSpace = 1u; bi.activeTris = c->activeTris.as<uint32_t>() + r.first; bi.n = r.count;
+        bi.wnodes = c->wnodes.as<u4>() + size_t(r.first) * OHB_WNODE_VECS; bi.tris = c->tris.as<f4>() + size_t(r.first) * 3u;   // node / triangle capacity of a BLAS = its triangle count
+        launchBuildBlas(bi, c->keysTmp.as<uint64_t>(), c->valsTmp.as<uint32_t>(), c->sortTemp.as<uint32_t>(), c->wideItemsA.as<WideItem>(), c->wideItemsB.as<WideItem>(), treeletPasses,
+                        c->blasLo.as<f4>(), c->blasHi.as<f4>(), r.inst, c->maxLevels.as<uint32_t>(), c->stream, &c->launches);
+    }
+    BuildArrays tb; if (tlasBuildArrays(c, np, tb)) return 1;
+    launchBuildTlas(tb, c->blasLo.as<f4>(), c->blasHi.as<f4>(), c->instOfPrim.as<uint32_t>(), false, c->tKeysTmp.as<uint64_t>(), c->tValsTmp.as<uint32_t>(), c->tSortTemp.as<uint32_t>(),
+                    c->tItemsA.as<WideItem>(), c->tItemsB.as<WideItem>(), c->stream, &c->launches);
+    CU(c, cudaEventRecord(c->evB, c->stream));
+    uint32_t twc[4] = {1, 0, 0, 0}, blasLevels = 0;
+    CU(c, cudaMemcpyAsync(twc, c->tWideCounters.p, 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(&blasLevels, c->maxLevels.p, 4, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     CU(c, cudaGetLastError());
-    if (wc[3] > OHB_MAX_LEVELS) OHB_FAIL(c, "ohb_build_accel: the 8-wide BVH is deeper than OHB_MAX_LEVELS (degenerate geometry: too many coincident triangles)");
+    // one stack: TLAS groups + sentinel + BLAS groups + postponed triangle groups
+    if (blasLevels > OHB_MAX_LEVELS || twc[3] > OHB_MAX_LEVELS || blasLevels + twc[3] + 4u + OHB_POSTPONE_SLOTS > OHB_STACK_SIZE)
+        OHB_FAIL(c, "ohb_build_accel: TLAS + BLAS depth exceeds the traversal stack");
+    c->numTlasPrims = np;
     c->accelValid = true;
     cudaEventElapsedTime(&c->stats.build_ms, c->evA, c->evB);
-    c->stats.num_nodes = wc[0];
+    c->stats.num_nodes = twc[0];                 // TLAS nodes; the BLAS node counts stay on the device
     c->stats.max_leaf_tris = OHB_MAX_LEAF;
-    c->stats.levels = wc[3] + 1u;
-    float ra = boxArea(xyz(rootLo), xyz(rootHi));
-    c->stats.sah_cost = (n >= 2 && ra > 0.0f) ? (sah[0] + sah[1]) / ra : float(n);
+    c->stats.levels = twc[3] + 1u + blasLevels + 1u;
+    c->stats.sah_cost = 0.0f;
+    return 0;
+}
+
+// MODE_UPDATE (rt_acceleration_structure.cpp:503-512): same instances, new object->world transforms.  Flattened structure:
+// triangles re-transformed, boxes refit bottom-up, wide nodes re-emitted (no sort / hierarchy / treelets).  Two-level: only
+// the TLAS is refit — the object-space BLASes do not change.
+int ohb_update_instances(ohb_ctx* c, const ohb_instance* inst, uint32_t n) {
+    if (!c) return 1;
+    if (!c->accelValid) OHB_FAIL(c, "ohb_update_instances: no acceleration structure to update (call ohb_build_accel)");
+    if (!inst || n != c->instances.size()) OHB_FAIL(c, "ohb_update_instances: the instance count must not change (rebuild instead)");
+    for (uint32_t i = 0; i < n; i++)
+        if (inst[i].first_tri != c->instances[i].first_tri || inst[i].tri_count != c->instances[i].tri_count || (inst[i].mask & 0xFFu) != (c->instances[i].mask & 0xFFu))
+            OHB_FAIL(c, "ohb_update_instances: only transforms may change (rebuild instead)");
+    cudaSetDevice(c->device);
+    for (uint32_t i = 0; i < n; i++) memcpy(c->instances[i].xform, inst[i].xform, 48);
+    if (uploadInstanceTables(c)) return 1;
+    if (c->numActive == 0) return 0;
+    CU(c, cudaEventRecord(c->evA, c->stream));
+    if (c->accelMode == OHB_ACCEL_TWO_LEVEL) {
+        BuildArrays tb; if (tlasBuildArrays(c, c->numTlasPrims, tb)) return 1;
+        launchBuildTlas(tb, c->blasLo.as<f4>(), c->blasHi.as<f4>(), c->instOfPrim.as<uint32_t>(), true, c->tKeysTmp.as<uint64_t>(), c->tValsTmp.as<uint32_t>(), c->tSortTemp.as<uint32_t>(),
+                        c->tItemsA.as<WideItem>(), c->tItemsB.as<WideItem>(), c->stream, &c->launches);
+    } else {
+        BuildArrays b; if (mainBuildArrays(c, c->numActive, b)) return 1;
+        launchRefit(b, c->wideItemsA.as<WideItem>(), c->wideItemsB.as<WideItem>(), c->stream, &c->launches);
+    }
+    CU(c, cudaEventRecord(c->evB, c->stream));
+    uint32_t wc[4] = {1, 0, 0, 0};
+    CU(c, cudaMemcpyAsync(wc, c->accelMode == OHB_ACCEL_TWO_LEVEL ? c->tWideCounters.p : c->wideCounters.p, 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaGetLastError());
+    if (wc[3] > OHB_MAX_LEVELS) { c->accelValid = false; OHB_FAIL(c, "ohb_update_instances: refit tree too deep"); }
+    cudaEventElapsedTime(&c->stats.update_ms, c->evA, c->evB);
+    c->stats.num_nodes = wc[0];
     return 0;
 }
 

@@ -26,6 +26,7 @@ struct BuildArrays {
     const uint32_t* triInst;                          // per global tri
     const f4* instXform;                              // 3 rows per instance (object->world)
     const uint32_t* activeTris; uint32_t n;           // triangles to build over
+    uint32_t objectSpace;                             // 1: no instance transform (a BLAS of the two-level structure is built in object space)
     // intermediates (length n unless noted)
     f4* wtri;            // 3n : world-space triangles in INPUT order, v0.w = global id
     f4* primLo; f4* primHi;
@@ -99,7 +100,7 @@ OHB_HD void buildWorldTri(const BuildArrays& b, uint32_t a) {
     f3 v[3];
     for (int k = 0; k < 3; k++) {
         const float* pp = reinterpret_cast<const float*>(b.positions + size_t(b.indices[size_t(g) * 3 + k]) * b.posStride);
-        v[k] = xformPoint(rows, mk3(pp[0], pp[1], pp[2]));
+        v[k] = b.objectSpace ? mk3(pp[0], pp[1], pp[2]) : xformPoint(rows, mk3(pp[0], pp[1], pp[2]));
     }
     b.wtri[size_t(a) * 3 + 0] = mk4(v[0], u2f(g));
     b.wtri[size_t(a) * 3 + 1] = mk4(v[1], 0.0f);
@@ -108,6 +109,37 @@ OHB_HD void buildWorldTri(const BuildArrays& b, uint32_t a) {
     b.primLo[a] = mk4(lo, 0.0f); b.primHi[a] = mk4(hi, 0.0f);
     atomicMinU32(b.boundsBits + 0, floatOrdered(lo.x)); atomicMinU32(b.boundsBits + 1, floatOrdered(lo.y)); atomicMinU32(b.boundsBits + 2, floatOrdered(lo.z));
     atomicMaxU32(b.boundsBits + 3, floatOrdered(hi.x)); atomicMaxU32(b.boundsBits + 4, floatOrdered(hi.y)); atomicMaxU32(b.boundsBits + 5, floatOrdered(hi.z));
+}
+
+// Two-level structure (RTAccelerationStructure::buildTLAS, rt_acceleration_structure.cpp:419-535): the TLAS is the same
+// 8-wide tree built over ONE primitive per instance.  Primitive a = instance a: its box is the world-space bounding box of
+// the 8 transformed corners of the instance's object-space BLAS root box, padded by more than the rounding error of the
+// transform (a hit is found in object space; its world position agrees with the transformed box only to a few ulp).
+// The "triangle" record of the primitive carries the instance index where a triangle carries its global id.
+OHB_HD void buildTlasPrim(const BuildArrays& b, const f4* blasLo, const f4* blasHi, const uint32_t* instOfPrim, uint32_t a) {
+    const uint32_t inst = instOfPrim[a];
+    const f4* rows = b.instXform + size_t(inst) * 3u;
+    const f3 l = xyz(blasLo[inst]), h = xyz(blasHi[inst]);
+    f3 lo = mk3(3.0e38f), hi = mk3(-3.0e38f);
+    for (int c = 0; c < 8; c++) {
+        f3 p = xformPoint(rows, mk3((c & 1) ? h.x : l.x, (c & 2) ? h.y : l.y, (c & 4) ? h.z : l.z));
+        lo = vmin(lo, p); hi = vmax(hi, p);
+    }
+    const f3 e = hi - lo; const float ext = fmaxf(e.x, fmaxf(e.y, e.z));
+    const float k = 4.0e-6f;
+    lo = mk3(lo.x - (fabsf(lo.x) + ext) * k - 1e-30f, lo.y - (fabsf(lo.y) + ext) * k - 1e-30f, lo.z - (fabsf(lo.z) + ext) * k - 1e-30f);
+    hi = mk3(hi.x + (fabsf(hi.x) + ext) * k + 1e-30f, hi.y + (fabsf(hi.y) + ext) * k + 1e-30f, hi.z + (fabsf(hi.z) + ext) * k + 1e-30f);
+    b.wtri[size_t(a) * 3 + 0] = mk4(0.0f, 0.0f, 0.0f, u2f(inst));
+    b.wtri[size_t(a) * 3 + 1] = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+    b.wtri[size_t(a) * 3 + 2] = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+    b.primLo[a] = mk4(lo, 0.0f); b.primHi[a] = mk4(hi, 0.0f);
+    atomicMinU32(b.boundsBits + 0, floatOrdered(lo.x)); atomicMinU32(b.boundsBits + 1, floatOrdered(lo.y)); atomicMinU32(b.boundsBits + 2, floatOrdered(lo.z));
+    atomicMaxU32(b.boundsBits + 3, floatOrdered(hi.x)); atomicMaxU32(b.boundsBits + 4, floatOrdered(hi.y)); atomicMaxU32(b.boundsBits + 5, floatOrdered(hi.z));
+}
+// object-space root box of the BLAS just built (the binary root's box, or the single triangle's)
+OHB_HD void storeBlasRootBox(const BuildArrays& b, f4* blasLo, f4* blasHi, uint32_t inst, uint32_t* maxLevels) {
+    if (b.n >= 2u) { blasLo[inst] = b.nodeLo[0]; blasHi[inst] = b.nodeHi[0]; } else { blasLo[inst] = b.primLo[0]; blasHi[inst] = b.primHi[0]; }
+    if (b.wideCounters[3] > *maxLevels) *maxLevels = b.wideCounters[3];
 }
 
 // Stage 2: 63-bit Morton code of the AABB centre (21 bits per axis).

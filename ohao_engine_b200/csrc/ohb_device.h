@@ -35,6 +35,11 @@ cudaError_t uploadConstants();
 uint32_t radixSortTempWords(uint32_t n);
 void launchBuild(const BuildArrays& b, uint64_t* keysTmp, uint32_t* valsTmp, uint32_t* sortTemp, WideItem* itemsA, WideItem* itemsB,
                  uint32_t treeletPasses, cudaStream_t st, uint64_t* launches);
+void launchRefit(const BuildArrays& b, WideItem* itemsA, WideItem* itemsB, cudaStream_t st, uint64_t* launches);
+void launchBuildBlas(const BuildArrays& b, uint64_t* keysTmp, uint32_t* valsTmp, uint32_t* sortTemp, WideItem* itemsA, WideItem* itemsB, uint32_t treeletPasses,
+                     f4* blasLo, f4* blasHi, uint32_t inst, uint32_t* maxLevels, cudaStream_t st, uint64_t* launches);
+void launchBuildTlas(const BuildArrays& b, const f4* blasLo, const f4* blasHi, const uint32_t* instOfPrim, bool refit, uint64_t* keysTmp, uint32_t* valsTmp, uint32_t* sortTemp,
+                     WideItem* itemsA, WideItem* itemsB, cudaStream_t st, uint64_t* launches);
 void launchEnvCdf(const f4* env, uint32_t W, uint32_t H, float* cond, float* marg, float* rowTotal, float* integral, cudaStream_t st, uint64_t* launches);
 void launchEnvSample(const SceneDev& sc, const float* u12, uint32_t n, f4* dirPdf, float* pdfOfDir, cudaStream_t st, uint64_t* launches);
 void launchHybridShadow(const SceneDev& sc, const HybridShadowParams& pc, const f4* gPos, const f2* gNrm, uint8_t* mask, cudaStream_t st, uint64_t* launches);

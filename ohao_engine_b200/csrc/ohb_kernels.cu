@@ -167,27 +167,17 @@ void radixSort64(uint64_t* keys, uint32_t* vals, uint64_t* keysTmp, uint32_t* va
     }
 }
 
-void launchBuild(const BuildArrays& b, uint64_t* keysTmp, uint32_t* valsTmp, uint32_t* sortTemp, WideItem* itemsA, WideItem* itemsB,
-                 uint32_t treeletPasses, cudaStream_t st, uint64_t* launches) {
-    const unsigned T = 256; unsigned g = gridFor(b.n, T);
-    k_init_build<<<g, T, 0, st>>>(b);
-    k_world_tris<<<g, T, 0, st>>>(b);
-    k_morton<<<g, T, 0, st>>>(b);
-    *launches += 3;
-    radixSort64(b.keys, b.vals, keysTmp, valsTmp, b.n, sortTemp, st, launches);
-    if (b.n >= 2) {
-        k_hierarchy<<<g, T, 0, st>>>(b);
-        k_sweep<<<g, T, 0, st>>>(b, 0u);                        // refit + counts + SAH cost
-        *launches += 2;
-        for (uint32_t pass = 0, gamma = OHB_TREELET_LEAVES; pass < treeletPasses; pass++, gamma *= 2u) {
-            k_clear_visit<<<g, T, 0, st>>>(b);
-            k_sweep<<<gridFor(b.n, 64), 64, 0, st>>>(b, gamma);  // treelet restructuring (1.2 KB of DP tables per thread)
-            *launches += 2;
-        }
-    }
-    // 8-wide collapse, level by level.  Level l holds at most min(8^l, n / 4) nodes (every inner child owns > 3
-    // triangles); the loop runs OHB_MAX_LEVELS + 1 times so that wideCounters[3] (levels that produced
-    // children) exceeds OHB_MAX_LEVELS exactly when the tree is too deep for the traversal stack.
+__global__ void k_tlas_prims(BuildArrays b, const f4* blasLo, const f4* blasHi, const uint32_t* instOfPrim) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < b.n) buildTlasPrim(b, blasLo, blasHi, instOfPrim, i);
+}
+__global__ void k_store_root_box(BuildArrays b, f4* blasLo, f4* blasHi, uint32_t inst, uint32_t* maxLevels) {
+    if (blockIdx.x || threadIdx.x) return;
+    storeBlasRootBox(b, blasLo, blasHi, inst, maxLevels);
+}
+// the 8-wide collapse, level by level.  Level l holds at most min(8^l, n / 4) nodes (every inner child owns > 3
+// triangles); the loop runs OHB_MAX_LEVELS + 1 times so that wideCounters[3] (levels that produced
+// children) exceeds OHB_MAX_LEVELS exactly when the tree is too deep for the traversal stack.
+static void launchCollapse(const BuildArrays& b, WideItem* itemsA, WideItem* itemsB, cudaStream_t st, uint64_t* launches) {
     k_wide_begin<<<1, 32, 0, st>>>(b, itemsA); (*launches)++;
     WideItem* in = itemsA; WideItem* out = itemsB; uint32_t* cin = b.wideCounters + 1; uint32_t* cout = b.wideCounters + 2;
     uint64_t cap = 1;
@@ -199,6 +189,60 @@ void launchBuild(const BuildArrays& b, uint64_t* keysTmp, uint32_t* valsTmp, uin
         WideItem* ti = in; in = out; out = ti; uint32_t* tc = cin; cin = cout; cout = tc;
         if (cap < (uint64_t(1) << 40)) cap *= 8;
     }
+}
+// primitives (wtri / primLo / primHi / boundsBits) -> sorted Morton codes -> Karras hierarchy -> refit -> treelets -> 8-wide collapse
+static void launchBuildFromPrims(const BuildArrays& b, uint64_t* keysTmp, uint32_t* valsTmp, uint32_t* sortTemp, WideItem* itemsA, WideItem* itemsB,
+                                 uint32_t treeletPasses, cudaStream_t st, uint64_t* launches) {
+    const unsigned T = 256; unsigned g = gridFor(b.n, T);
+    k_morton<<<g, T, 0, st>>>(b); (*launches)++;
+    radixSort64(b.keys, b.vals, keysTmp, valsTmp, b.n, sortTemp, st, launches);
+    if (b.n >= 2) {
+        k_hierarchy<<<g, T, 0, st>>>(b);
+        k_sweep<<<g, T, 0, st>>>(b, 0u);                        // refit + counts + SAH cost
+        *launches += 2;
+        for (uint32_t pass = 0, gamma = OHB_TREELET_LEAVES; pass < treeletPasses; pass++, gamma *= 2u) {
+            k_clear_visit<<<g, T, 0, st>>>(b);
+            k_sweep<<<gridFor(b.n, 64), 64, 0, st>>>(b, gamma);  // treelet restructuring (1.2 KB of DP tables per thread)
+            *launches += 2;
+        }
+    }
+    launchCollapse(b, itemsA, itemsB, st, launches);
+}
+void launchBuild(const BuildArrays& b, uint64_t* keysTmp, uint32_t* valsTmp, uint32_t* sortTemp, WideItem* itemsA, WideItem* itemsB,
+                 uint32_t treeletPasses, cudaStream_t st, uint64_t* launches) {
+    const unsigned T = 256; unsigned g = gridFor(b.n, T);
+    k_init_build<<<g, T, 0, st>>>(b);
+    k_world_tris<<<g, T, 0, st>>>(b);
+    *launches += 2;
+    launchBuildFromPrims(b, keysTmp, valsTmp, sortTemp, itemsA, itemsB, treeletPasses, st, launches);
+}
+// MODE_UPDATE of rt_acceleration_structure.cpp:508 for the flattened structure: the instance transforms changed, the topology
+// of the binary tree is kept — re-transform the triangles, refit the boxes bottom-up, re-emit the wide nodes.  No Morton codes,
+// no sort, no hierarchy, no treelets (the sorted order b.vals and the links b.left / b.right / parents stay as built).
+void launchRefit(const BuildArrays& b, WideItem* itemsA, WideItem* itemsB, cudaStream_t st, uint64_t* launches) {
+    const unsigned T = 256; unsigned g = gridFor(b.n, T);
+    k_init_build<<<g, T, 0, st>>>(b);
+    k_world_tris<<<g, T, 0, st>>>(b);
+    *launches += 2;
+    if (b.n >= 2) { k_sweep<<<g, T, 0, st>>>(b, 0u); (*launches)++; }
+    launchCollapse(b, itemsA, itemsB, st, launches);
+}
+// one BLAS of the two-level structure: launchBuild in object space, then its root box -> blasLo/Hi[inst]
+void launchBuildBlas(const BuildArrays& b, uint64_t* keysTmp, uint32_t* valsTmp, uint32_t* sortTemp, WideItem* itemsA, WideItem* itemsB, uint32_t treeletPasses,
+                     f4* blasLo, f4* blasHi, uint32_t inst, uint32_t* maxLevels, cudaStream_t st, uint64_t* launches) {
+    launchBuild(b, keysTmp, valsTmp, sortTemp, itemsA, itemsB, treeletPasses, st, launches);
+    k_store_root_box<<<1, 32, 0, st>>>(b, blasLo, blasHi, inst, maxLevels); (*launches)++;
+}
+// TLAS build (refit == false) or MODE_UPDATE (refit == true: same instances, new transforms -> boxes refit, topology kept)
+void launchBuildTlas(const BuildArrays& b, const f4* blasLo, const f4* blasHi, const uint32_t* instOfPrim, bool refit, uint64_t* keysTmp, uint32_t* valsTmp, uint32_t* sortTemp,
+                     WideItem* itemsA, WideItem* itemsB, cudaStream_t st, uint64_t* launches) {
+    const unsigned T = 256; unsigned g = gridFor(b.n, T);
+    k_init_build<<<g, T, 0, st>>>(b);
+    k_tlas_prims<<<g, T, 0, st>>>(b, blasLo, blasHi, instOfPrim);
+    *launches += 2;
+    if (!refit) { launchBuildFromPrims(b, keysTmp, valsTmp, sortTemp, itemsA, itemsB, 3u, st, launches); return; }
+    if (b.n >= 2) { k_sweep<<<g, T, 0, st>>>(b, 0u); (*launches)++; }
+    launchCollapse(b, itemsA, itemsB, st, launches);
 }
 
 // =============================================================================================
@@ -313,7 +357,7 @@ static TraceKnobs traceKnobs() {
 // in shared memory, bit 1 = the top OHB_SMEM_TOP wide nodes (levels 0-2 of the tree) staged in shared memory per CTA.
 #define OHB_SMEM_STACK 8
 #define OHB_SMEM_TOP 73u
-template <bool ANY, int VAR, class IO>
+template <bool ANY, int VAR, class IO, bool TL = false>
 __device__ __forceinline__ void persistentTrace(const SceneDev& sc, uint32_t n, uint32_t* work, IO& io, int minActive, int postponeDen) {
     const uint32_t lane = threadIdx.x & 31u;
     __shared__ TravStackEntry sStack[(VAR & 1) ? OHB_SMEM_STACK * TRACE_THREADS : 1];
@@ -343,7 +387,7 @@ __device__ __forceinline__ void persistentTrace(const SceneDev& sc, uint32_t n, 
         }
         if (!__any_sync(0xffffffffu, have)) break;
         bool done = false;
-        if (have) done = travRun<ANY>(t, stack, sc, top, minActive, postponeDen);
+        if (have) done = travRun<ANY, decltype(stack), TL>(t, stack, sc, top, minActive, postponeDen);
         __syncwarp();
         if (done) { io.store(idx, t); have = false; }
     }
@@ -387,6 +431,17 @@ __global__ void __launch_bounds__(TRACE_THREADS, MINB) k_trace_shadow(SceneDev s
     PathShadowIO io{P};
     persistentTrace<true, VAR>(sc, *P.shCount, work, io, minActive, postponeDen);
 }
+// two-level variants (ohb_set_accel_mode(OHB_ACCEL_TWO_LEVEL)): the same persistent loop, travRun with the instance descent
+__global__ void __launch_bounds__(TRACE_THREADS, 6) k_trace_closest_tl(SceneDev sc, PathArrays P, uint32_t* work, int minActive, int postponeDen) {
+    PathClosestIO io{P, 0u};
+    persistentTrace<false, 0, PathClosestIO, true>(sc, *P.countIn, work, io, minActive, postponeDen);
+    uint32_t hits = __reduce_add_sync(0xffffffffu, io.hits);
+    if ((threadIdx.x & 31u) == 0 && hits) atomicAdd(P.counters + 3, (unsigned long long)hits);
+}
+__global__ void __launch_bounds__(TRACE_THREADS, 6) k_trace_shadow_tl(SceneDev sc, PathArrays P, uint32_t* work, int minActive, int postponeDen) {
+    PathShadowIO io{P};
+    persistentTrace<true, 0, PathShadowIO, true>(sc, *P.shCount, work, io, minActive, postponeDen);
+}
 // resident CTAs per SM the traversal kernels are compiled for: 5 -> 96 registers, 6 -> 80, 7 -> 72, 8 -> 64, 9 -> 56, 10 -> 48.
 #ifndef OHB_TRACE_OCC_DEFAULT
 #define OHB_TRACE_OCC_DEFAULT 8
@@ -416,10 +471,12 @@ static int traceVar() {
     } } while (0)
 static void launchTraceClosest(unsigned smGrid8, const SceneDev& sc, const PathArrays& P, uint32_t* work, cudaStream_t st) {
     const TraceKnobs k = traceKnobs();
+    if (sc.twoLevel) { k_trace_closest_tl<<<smGrid8 / 8u * 6u, TRACE_THREADS, 0, st>>>(sc, P, work, k.minActive, k.postponeDen & 0xFF); return; }
     OHB_TRACE_DISPATCH(k_trace_closest, sc, P, work, k.minActive, k.postponeDen);
 }
 static void launchTraceShadow(unsigned smGrid8, const SceneDev& sc, const PathArrays& P, uint32_t* work, cudaStream_t st) {
     const TraceKnobs k = traceKnobs();
+    if (sc.twoLevel) { k_trace_shadow_tl<<<smGrid8 / 8u * 6u, TRACE_THREADS, 0, st>>>(sc, P, work, k.minActive, k.postponeDen & 0xFF); return; }
     OHB_TRACE_DISPATCH(k_trace_shadow, sc, P, work, k.minActive, k.postponeDen);
 }
 #define SHADE_THREADS 128
@@ -726,19 +783,26 @@ struct HookIO {
         else occ[i] = t.anyHit ? 1 : 0;
     }
 };
+template <bool TL>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_batch(SceneDev sc, const ohb_ray* rays, uint32_t n, ohb_hit* hits, uint32_t* work, int minActive, int postponeDen) {
     HookIO io{rays, hits, nullptr};
-    persistentTrace<false, 0>(sc, n, work, io, minActive, postponeDen);
+    persistentTrace<false, 0, HookIO, TL>(sc, n, work, io, minActive, postponeDen);
 }
+template <bool TL>
 __global__ void __launch_bounds__(TRACE_THREADS) k_occluded_batch(SceneDev sc, const ohb_ray* rays, uint32_t n, uint8_t* occ, uint32_t* work, int minActive, int postponeDen) {
     HookIO io{rays, nullptr, occ};
-    persistentTrace<true, 0>(sc, n, work, io, minActive, postponeDen);
+    persistentTrace<true, 0, HookIO, TL>(sc, n, work, io, minActive, postponeDen);
 }
 void launchTraceBatch(const SceneDev& sc, const ohb_ray* rays, uint32_t n, ohb_hit* hits, uint8_t* occ, uint32_t* work, int numSMs, cudaStream_t st, uint64_t* launches) {
     k_zero_u32<<<1, 32, 0, st>>>(work, 2);
     const TraceKnobs k = traceKnobs();
-    if (hits) k_trace_batch<<<numSMs * 8, TRACE_THREADS, 0, st>>>(sc, rays, n, hits, work, k.minActive, k.postponeDen);
-    else      k_occluded_batch<<<numSMs * 8, TRACE_THREADS, 0, st>>>(sc, rays, n, occ, work, k.minActive, k.postponeDen);
+    if (sc.twoLevel) {
+        if (hits) k_trace_batch<true><<<numSMs * 6, TRACE_THREADS, 0, st>>>(sc, rays, n, hits, work, k.minActive, k.postponeDen & 0xFF);
+        else      k_occluded_batch<true><<<numSMs * 6, TRACE_THREADS, 0, st>>>(sc, rays, n, occ, work, k.minActive, k.postponeDen & 0xFF);
+    } else {
+        if (hits) k_trace_batch<false><<<numSMs * 8, TRACE_THREADS, 0, st>>>(sc, rays, n, hits, work, k.minActive, k.postponeDen);
+        else      k_occluded_batch<false><<<numSMs * 8, TRACE_THREADS, 0, st>>>(sc, rays, n, occ, work, k.minActive, k.postponeDen);
+    }
     *launches += 2;
 }
 

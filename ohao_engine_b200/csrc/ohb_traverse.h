@@ -192,6 +192,8 @@ OHB_HD bool intersectTri(const RayPrep& r, const TriRows& q, float tlim, TriHit&
 struct Trav {
     RayPrep r; float tlim; BestHit best; uint32_t prim;
     u2 G, Gt; int sp; uint32_t octinv; bool anyHit;
+    // two-level traversal only: the world-space ray while inside an instance, and the tree the current groups refer to
+    f3 wo, wd; const u4* curNodes; const f4* curTris; bool inBlas;
 };
 typedef u2 TravStackEntry;
 // Traversal stack.  ArrayStack: a per-thread array (local memory on the device).  SharedStack<SH, STRIDE>: the first SH
@@ -213,14 +215,46 @@ struct SharedStack {
 // allocates wide nodes level by level, so nodes [0, count) are the top levels.  top == nullptr: everything from global.
 struct TopNodes { const u4* top; uint32_t count; };
 
+OHB_HD uint32_t octantOf(const RayPrep& r) { return (r.idir.x < 0.0f ? 0u : 4u) | (r.idir.y < 0.0f ? 0u : 2u) | (r.idir.z < 0.0f ? 0u : 1u); }
 OHB_HD void travInit(Trav& t, const SceneDev& s, f3 o, f3 d, float tmin, float tmax) {
     t.r = prepRay(o, d, tmin); t.tlim = tmax;
     t.best.V = 0.0f; t.best.W = 0.0f; t.best.det = 1.0f; t.prim = OHB_MISS;
     t.sp = 0; t.anyHit = false;
     // bit 2/1/0 set = the ray travels toward +x/+y/+z: slot ^ octinv is then the visit priority (7 first)
-    t.octinv = (t.r.idir.x < 0.0f ? 0u : 4u) | (t.r.idir.y < 0.0f ? 0u : 2u) | (t.r.idir.z < 0.0f ? 0u : 1u);
+    t.octinv = octantOf(t.r);
     t.G.x = 0u; t.G.y = s.numTris ? 0x80000000u : 0u;      // the root is "slot 7 ^ octinv" of a virtual group
     t.Gt.x = 0u; t.Gt.y = 0u;
+    t.wo = o; t.wd = d; t.inBlas = false;
+    t.curNodes = s.twoLevel ? s.tlasNodes : s.wnodes; t.curTris = s.twoLevel ? s.tlasLeaves : s.tris;
+}
+// ---- two-level traversal (RTAccelerationStructure's BLAS/TLAS, rt_acceleration_structure.cpp:205-535) ----------------------
+// A TLAS leaf entry is an instance.  Entering it parks what is left of the TLAS-level groups on the stack under a sentinel,
+// maps the ray into the instance's object space — o' = M^-1 o, d' = M^-1 d, NOT renormalised, so t is the same parameter in
+// both spaces and the closest-hit bound carries over — and continues in the instance's BLAS; popping the sentinel restores
+// the world-space ray.  The transform arithmetic is part of the spec shared with the oracle: ((m0 x + m1 y) + m2 z) + m3,
+// one rounding per operation (xformPoint of the builder).
+#define OHB_TL_SENTINEL 0xFFFFFFFFu
+OHB_HD void travEnterInstance(Trav& t, const SceneDev& s, uint32_t inst) {
+    const f4* iv = s.instInv + size_t(inst) * 3u;
+    const f4 r0 = iv[0], r1 = iv[1], r2 = iv[2];
+    const f3 o = t.wo, d = t.wd;
+    const f3 oo = mk3(xadd(xadd(xadd(xmul(r0.x, o.x), xmul(r0.y, o.y)), xmul(r0.z, o.z)), r0.w),
+                      xadd(xadd(xadd(xmul(r1.x, o.x), xmul(r1.y, o.y)), xmul(r1.z, o.z)), r1.w),
+                      xadd(xadd(xadd(xmul(r2.x, o.x), xmul(r2.y, o.y)), xmul(r2.z, o.z)), r2.w));
+    const f3 od = mk3(xadd(xadd(xmul(r0.x, d.x), xmul(r0.y, d.y)), xmul(r0.z, d.z)),
+                      xadd(xadd(xmul(r1.x, d.x), xmul(r1.y, d.y)), xmul(r1.z, d.z)),
+                      xadd(xadd(xmul(r2.x, d.x), xmul(r2.y, d.y)), xmul(r2.z, d.z)));
+    const float tmin = t.r.tmin;
+    t.r = prepRay(oo, od, tmin); t.octinv = octantOf(t.r);
+    const u4 bi = s.blasInfo[inst];
+    t.curNodes = s.wnodes + size_t(bi.x) * OHB_WNODE_VECS; t.curTris = s.tris + size_t(bi.y) * 3u;
+    t.inBlas = true;
+    t.G.x = 0u; t.G.y = bi.z ? 0x80000000u : 0u; t.Gt.x = 0u; t.Gt.y = 0u;
+}
+OHB_HD void travLeaveInstance(Trav& t, const SceneDev& s) {
+    const float tmin = t.r.tmin;
+    t.r = prepRay(t.wo, t.wd, tmin); t.octinv = octantOf(t.r);
+    t.curNodes = s.tlasNodes; t.curTris = s.tlasLeaves; t.inBlas = false;
 }
 // the result of a finished closest-hit query in ABI form (prim == OHB_MISS and t = -1 on miss)
 OHB_HD ohb_hit travResult(const Trav& t) {
@@ -338,7 +372,7 @@ OHB_HD uint32_t nextChildOf(const u2& G, uint32_t octinv) {
 // postponeDen carries the prefetch mode in bits 8.. : bits 8-9 = prefetch the NEXT SIBLING when a group with children left
 // is pushed (the node a later stack pop will want; 1 = L2, 2 = L1), bits 10-11 = prefetch the FIRST HIT CHILD right after
 // the box tests, before the leaf triangles of this node are tested, bit 12 = four prefetches per node
-template <bool ANY, class Stack>
+template <bool ANY, class Stack, bool TL = false>
 OHB_HD bool travRun(Trav& t, Stack& stack, const SceneDev& s, const TopNodes& top, int minActive, int postponeDenAndPf) {
     const int postponeDen = postponeDenAndPf & 0xFF, pfSib = (postponeDenAndPf >> 8) & 3, pfKid = (postponeDenAndPf >> 10) & 3, pf4 = (postponeDenAndPf >> 8) & 16;
     for (;;) {
@@ -353,7 +387,7 @@ OHB_HD bool travRun(Trav& t, Stack& stack, const SceneDev& s, const TopNodes& to
                 if (pfSib) prefetchNode(s.wnodes + size_t(nextChildOf(t.G, t.octinv)) * OHB_WNODE_VECS, pfSib | pf4);
             }
             uint32_t childBase, triBase, imask;
-            const uint32_t hits = intersectWideNode(t, s.wnodes, top, idx, t.tlim, childBase, triBase, imask);
+            const uint32_t hits = intersectWideNode(t, TL ? t.curNodes : s.wnodes, top, idx, t.tlim, childBase, triBase, imask);
             t.G.x = childBase; t.G.y = (hits & 0xFF000000u) | imask;
             t.Gt.x = triBase; t.Gt.y = hits & 0x00FFFFFFu;
             if (pfKid && (t.G.y & 0xFF000000u) && t.Gt.y) prefetchNode(s.wnodes + size_t(nextChildOf(t.G, t.octinv)) * OHB_WNODE_VECS, pfKid | pf4);
@@ -361,6 +395,17 @@ OHB_HD bool travRun(Trav& t, Stack& stack, const SceneDev& s, const TopNodes& to
             t.Gt = t.G; t.G.x = 0u; t.G.y = 0u;            // a postponed triangle group came off the stack
         }
         // leaf triangles; when most lanes of the warp have none left, the rest postpone theirs (Ylitie et al. §4.3)
+        if (TL && !t.inBlas && t.Gt.y) {
+            // TLAS level: the group's entries are instances.  Take the first one, park the rest, descend into its BLAS.
+            const uint32_t k = bfind32(t.Gt.y);
+            t.Gt.y &= ~(1u << k);
+            const uint32_t inst = f2u(ld4(t.curTris + size_t(t.Gt.x + k) * 3u).w);
+            if (t.G.y & 0xFF000000u) stack.push(t.sp++, t.G);
+            if (t.Gt.y) stack.push(t.sp++, t.Gt);
+            TravStackEntry sentinel; sentinel.x = OHB_TL_SENTINEL; sentinel.y = 0u; stack.push(t.sp++, sentinel);
+            travEnterInstance(t, s, inst);
+            continue;
+        }
         const int entered = postponeDen ? OHB_WARP_ACTIVE() : 0;
         while (t.Gt.y) {
             if (postponeDen && OHB_WARP_ACTIVE() * postponeDen < entered && t.sp < OHB_POSTPONE_SLOTS) { stack.push(t.sp++, t.Gt); t.Gt.y = 0u; break; }
@@ -372,8 +417,9 @@ OHB_HD bool travRun(Trav& t, Stack& stack, const SceneDev& s, const TopNodes& to
             const bool two = t.Gt.y != 0u;
             const uint32_t k1 = two ? bfind32(t.Gt.y) : k0;
             t.Gt.y &= ~(1u << k1);
-            const TriRows q0 = loadTri(t.r, s.tris + size_t(t.Gt.x + k0) * 3u);
-            const TriRows q1 = loadTri(t.r, s.tris + size_t(t.Gt.x + k1) * 3u);
+            const f4* triBasePtr = TL ? t.curTris : s.tris;
+            const TriRows q0 = loadTri(t.r, triBasePtr + size_t(t.Gt.x + k0) * 3u);
+            const TriRows q1 = loadTri(t.r, triBasePtr + size_t(t.Gt.x + k1) * 3u);
 #ifdef __CUDA_ARCH__
 #pragma unroll 1
 #endif
@@ -392,6 +438,13 @@ OHB_HD bool travRun(Trav& t, Stack& stack, const SceneDev& s, const TopNodes& to
         if (!(t.G.y & 0xFF000000u)) {
             if (t.sp == 0) return true;
             t.G = stack.pop(--t.sp);
+            if (TL) {
+                while (t.G.x == OHB_TL_SENTINEL && t.G.y == 0u) {        // the instance's BLAS is exhausted: back to the TLAS level
+                    travLeaveInstance(t, s);
+                    if (t.sp == 0) return true;
+                    t.G = stack.pop(--t.sp);
+                }
+            }
         }
         if (OHB_WARP_ACTIVE() < minActive) return false;
     }
@@ -400,13 +453,19 @@ OHB_HD bool travRun(Trav& t, Stack& stack, const SceneDev& s, const TopNodes& to
 // Closest hit.  Returns prim == OHB_MISS and t = -1 on miss.
 OHB_HD ohb_hit traceClosest(const SceneDev& s, f3 o, f3 d, float tmin, float tmax) {
     Trav t; TravStackEntry mem[OHB_STACK_SIZE]; ArrayStack stack{mem}; const TopNodes top{nullptr, 0u}; travInit(t, s, o, d, tmin, tmax);
-    if (t.G.y) while (!travRun<false>(t, stack, s, top, 0, OHB_POSTPONE_DEN_DEFAULT)) {}
+    if (t.G.y) {
+        if (s.twoLevel) { while (!travRun<false, ArrayStack, true>(t, stack, s, top, 0, OHB_POSTPONE_DEN_DEFAULT)) {} }
+        else { while (!travRun<false>(t, stack, s, top, 0, OHB_POSTPONE_DEN_DEFAULT)) {} }
+    }
     return travResult(t);
 }
 // Any hit in (tmin, tmax): TerminateOnFirstHit | SkipClosestHit.
 OHB_HD bool traceAny(const SceneDev& s, f3 o, f3 d, float tmin, float tmax) {
     Trav t; TravStackEntry mem[OHB_STACK_SIZE]; ArrayStack stack{mem}; const TopNodes top{nullptr, 0u}; travInit(t, s, o, d, tmin, tmax);
-    if (t.G.y) while (!travRun<true>(t, stack, s, top, 0, OHB_POSTPONE_DEN_DEFAULT)) {}
+    if (t.G.y) {
+        if (s.twoLevel) { while (!travRun<true, ArrayStack, true>(t, stack, s, top, 0, OHB_POSTPONE_DEN_DEFAULT)) {} }
+        else { while (!travRun<true>(t, stack, s, top, 0, OHB_POSTPONE_DEN_DEFAULT)) {} }
+    }
     return t.anyHit;
 }
 

@@ -622,6 +622,32 @@ void* orc_scene_create(const orc_scene_desc* d) {
     return s;
 }
 void orc_scene_destroy(void* h) { delete (Scene*)h; }
+// ohb_set_accel_mode: 0 flatten (world-space triangles), 1 two-level (object-space BLAS per instance, ray mapped on descent)
+void orc_scene_set_accel_mode(void* h, int mode) {
+    Scene* s = (Scene*)h; s->twoLevel = mode != 0;
+    if (s->twoLevel && s->blas.empty()) buildTwoLevel(*s);
+}
+// ohb_update_instances: new transforms for the same instances
+void orc_scene_update_instances(void* h, const ohb_instance* insts, uint32_t n) {
+    Scene* s = (Scene*)h;
+    for (uint32_t i = 0; i < n && i < s->inst.size(); i++) {
+        Instance& in = s->inst[i];
+        std::memcpy(in.x, insts[i].xform, 48);
+        M3 a; for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) a.r[r][c] = in.x[r * 4 + c];
+        in.normalMat = inverse_transpose(a);
+        for (int r = 0; r < 3; r++) {
+            for (int c = 0; c < 3; c++) in.inv[r * 4 + c] = in.normalMat.r[c][r];
+            in.inv[r * 4 + 3] = -(in.inv[r * 4 + 0] * in.x[3] + in.inv[r * 4 + 1] * in.x[7] + in.inv[r * 4 + 2] * in.x[11]);
+        }
+        for (uint32_t t = in.firstTri; t < in.firstTri + in.triCount && size_t(t) * 3 + 2 < s->wtri.size(); t++)
+            for (int k = 0; k < 3; k++) {
+                V3 p = s->pos[s->idx[size_t(t) * 3 + k]];
+                const float* m = in.x;
+                s->wtri[size_t(t) * 3 + k] = {((m[0] * p.x + m[1] * p.y) + m[2] * p.z) + m[3], ((m[4] * p.x + m[5] * p.y) + m[6] * p.z) + m[7], ((m[8] * p.x + m[9] * p.y) + m[10] * p.z) + m[11]};
+            }
+    }
+    buildBvh(*s);
+}
 
 // Cheap edits mirroring updateRTMaterialParams / updateRTLightParams (no BVH rebuild).
 void orc_scene_set_materials(void* h, const float* mat_colors, uint32_t nmat) {

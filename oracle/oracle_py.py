@@ -154,6 +154,8 @@ def lib() -> C.CDLL:
         _LIB.orc_scene_env_cdf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
         _LIB.orc_env_sample_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         _LIB.orc_env_pdf_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        _LIB.orc_scene_set_accel_mode.argtypes = [C.c_void_p, C.c_int]
+        _LIB.orc_scene_update_instances.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         _LIB.orc_hybrid_shadow.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _LIB.orc_hybrid_gi.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _LIB.orc_nrd_pack_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -234,6 +236,13 @@ class OracleScene:
     def __del__(self):
         if getattr(self, "h", None):
             lib().orc_scene_destroy(self.h); self.h = None
+
+    def set_accel_mode(self, two_level: bool):
+        lib().orc_scene_set_accel_mode(self.h, int(two_level))
+
+    def update_instances(self, instances):
+        inst = np.ascontiguousarray(instances)
+        lib().orc_scene_update_instances(self.h, _p(inst), len(inst))
 
     def set_materials(self, mat_colors):
         mc = np.ascontiguousarray(mat_colors, np.float32)

@@ -190,9 +190,56 @@ static inline bool slab(const BvhNode& n, const RayPrep& r, float tmax, float& t
     return tfar >= std::max(tnear, r.tmin - 1e-6f) && tnear <= tmax;
 }
 
+// Two-level spec (shared with ohb_traverse.h travEnterInstance): the ray is mapped into each instance's object space with
+// o' = ((m0 x + m1 y) + m2 z) + m3, d' = (m0 x + m1 y) + m2 z over the rows of world->object (one rounding per operation, no
+// renormalisation: t is the same parameter in both spaces), the watertight test runs on the OBJECT-space triangles, and the
+// closest candidate over all instances wins, equal t resolved toward the lower global id.
+static void toObject(const Instance& in, V3 o, V3 d, V3& oo, V3& od) {
+    const float* m = in.inv;
+    oo = {((m[0] * o.x + m[1] * o.y) + m[2] * o.z) + m[3], ((m[4] * o.x + m[5] * o.y) + m[6] * o.z) + m[7], ((m[8] * o.x + m[9] * o.y) + m[10] * o.z) + m[11]};
+    od = {(m[0] * d.x + m[1] * d.y) + m[2] * d.z, (m[4] * d.x + m[5] * d.y) + m[6] * d.z, (m[8] * d.x + m[9] * d.y) + m[10] * d.z};
+}
+void buildTwoLevel(Scene& s) {
+    s.blas.clear();
+    for (uint32_t i = 0; i < s.inst.size(); i++) {
+        const Instance& in = s.inst[i];
+        if ((in.mask & 0xFFu) == 0u || in.triCount == 0u) continue;
+        Scene::Blas bl; bl.inst = i; bl.firstTri = in.firstTri; bl.sub = std::make_unique<Scene>();
+        Scene& sub = *bl.sub;
+        sub.idx.resize(size_t(in.triCount) * 3); sub.wtri.resize(size_t(in.triCount) * 3);
+        for (uint32_t t = 0; t < in.triCount; t++) {
+            for (int k = 0; k < 3; k++) sub.wtri[size_t(t) * 3 + k] = s.pos[s.idx[size_t(in.firstTri + t) * 3 + k]];      // object space, untransformed
+            sub.activeTris.push_back(t);
+        }
+        buildBvh(sub);
+        s.blas.push_back(std::move(bl));
+    }
+}
+static ohb_hit traceClosestFlat(const Scene& s, V3 o, V3 d, float tmin, float tmax);
+static bool traceAnyFlat(const Scene& s, V3 o, V3 d, float tmin, float tmax);
 ohb_hit traceClosest(const Scene& s, V3 o, V3 d, float tmin, float tmax) {
+    if (!s.twoLevel) return traceClosestFlat(s, o, d, tmin, tmax);
+    ohb_hit best{-1.0f, 0.0f, 0.0f, OHB_MISS};
+    for (const Scene::Blas& bl : s.blas) {
+        V3 oo, od; toObject(s.inst[bl.inst], o, d, oo, od);
+        ohb_hit h = traceClosestFlat(*bl.sub, oo, od, tmin, tmax);
+        if (h.prim == OHB_MISS) continue;
+        uint32_t gid = bl.firstTri + h.prim;
+        if (best.prim == OHB_MISS || h.t < best.t || (h.t == best.t && gid < best.prim)) best = {h.t, h.u, h.v, gid};
+    }
+    return best;
+}
+bool traceAny(const Scene& s, V3 o, V3 d, float tmin, float tmax) {
+    if (!s.twoLevel) return traceAnyFlat(s, o, d, tmin, tmax);
+    for (const Scene::Blas& bl : s.blas) {
+        V3 oo, od; toObject(s.inst[bl.inst], o, d, oo, od);
+        if (traceAnyFlat(*bl.sub, oo, od, tmin, tmax)) return true;
+    }
+    return false;
+}
+static ohb_hit traceClosestFlat(const Scene& s, V3 o, V3 d, float tmin, float tmax) {
     ohb_hit best{tmax, 0.0f, 0.0f, OHB_MISS};
-    if (s.nodes.empty()) return best;
+    if (s.nodes.empty()) { best.t = -1.0f; return best; }
     RayPrep r = prepRay(o, d, tmin);
     int stack[128]; int sp = 0; stack[sp++] = 0;
     float dummy;
@@ -229,7 +276,7 @@ ohb_hit traceClosestBrute(const Scene& s, V3 o, V3 d, float tmin, float tmax) {
     if (best.prim == OHB_MISS) best.t = -1.0f;
     return best;
 }
-bool traceAny(const Scene& s, V3 o, V3 d, float tmin, float tmax) {
+static bool traceAnyFlat(const Scene& s, V3 o, V3 d, float tmin, float tmax) {
     if (s.nodes.empty()) return false;
     RayPrep r = prepRay(o, d, tmin);
     int stack[128]; int sp = 0; stack[sp++] = 0;

@@ -5,6 +5,7 @@
 #include "../include/ohao_b200.h"
 #include "oracle_math.h"
 #include <vector>
+#include <memory>
 #include <cstdio>
 
 namespace orc {
@@ -125,7 +126,13 @@ struct Scene {
     std::vector<BvhNode> nodes;
     std::vector<uint32_t> bvhTris;   // leaf order -> global triangle id
     bool hasEnv() const { return envMapTexIdx != 0xFFFFFFFFu && !env.empty(); }
+    // two-level mode (mirrors ohb_set_accel_mode(OHB_ACCEL_TWO_LEVEL)): one object-space sub-scene per visible instance;
+    // sub-scene triangle ids are local (0 .. count-1), global id = firstTri + local
+    bool twoLevel = false;
+    struct Blas { uint32_t inst, firstTri; std::unique_ptr<Scene> sub; };
+    std::vector<Blas> blas;
 };
+void buildTwoLevel(Scene& s);
 
 void buildEnvCDF(const float* rgba, int W, int H, std::vector<float>& marg, std::vector<float>& cond, float& integral);
 void buildBvh(Scene& s);

@@ -42,9 +42,15 @@ struct EmulScene {
     std::vector<GPULight> lights; uint32_t lightCount = 0, envMapTexIdx = 0xFFFFFFFFu; float envIntensity = 1.0f;
     uint32_t envW = 0, envH = 0; std::vector<float> marg, cond; float envIntegral = 0;
     std::vector<u4> wnodes; std::vector<f4> tris; uint32_t numActive = 0, numNodes = 0, levels = 0; float sah = 0;
+    // two-level structure + what MODE_UPDATE needs
+    std::vector<ohb_instance> instances; int accelMode = 0;
+    struct Range { uint32_t inst, first, count; }; std::vector<Range> ranges;
+    std::vector<u4> tlasNodes, blasInfo; std::vector<f4> tlasLeaves, blasLo, blasHi; std::vector<uint32_t> instOfPrim;
+    struct HostBuilder* mainB = nullptr; struct HostBuilder* tlasB = nullptr;
     SceneDev dev() const {
         SceneDev s; memset(&s, 0, sizeof(s));
-        s.wnodes = wnodes.data(); s.tris = tris.data(); s.numTris = numActive; s.numWideNodes = numNodes;
+        s.wnodes = wnodes.data(); s.tris = tris.data(); s.numTris = numActive; s.numWideNodes = accelMode ? 0u : numNodes;
+        s.twoLevel = accelMode ? 1u : 0u; s.tlasNodes = tlasNodes.data(); s.tlasLeaves = tlasLeaves.data(); s.blasInfo = blasInfo.data();
         s.indices = indices.data(); s.normals = normals.data(); s.uvs = uvs.data(); s.matIds = matIds.data(); s.triInst = triInst.data();
         s.instNormalMat = instNormalMat.data(); s.instInv = instInv.data(); s.matColors = matColors.data();
         s.tex = tex.data(); s.texW = texW; s.texH = texH; s.texLayers = texLayers;
@@ -53,6 +59,148 @@ struct EmulScene {
         return s;
     }
 };
+
+
+// ---- host stand-in for the builder's launch sequences (ohb_kernels.cu launchBuild / launchRefit / launchBuildBlas / launchBuildTlas) ----
+struct HostBuilder {
+    std::vector<f4> wtri, primLo, primHi, nodeLo, nodeHi; std::vector<uint32_t> bounds, vals, visit, wideCounters; std::vector<uint64_t> keys;
+    std::vector<int32_t> left, right, pin, pleaf; std::vector<float> sah; std::vector<WideItem> qa, qb;
+    BuildArrays arrays(uint32_t n) {
+        wtri.resize(size_t(n) * 3); primLo.resize(n); primHi.resize(n); nodeLo.resize(n); nodeHi.resize(n); bounds.assign(6, 0); vals.resize(n); visit.assign(n, 0); wideCounters.assign(4, 0);
+        keys.resize(n); left.resize(n); right.resize(n); pin.assign(n, -1); pleaf.assign(n, -1); sah.assign(2, 0.0f); qa.resize(n / 4 + 2); qb.resize(n / 4 + 2);
+        return view(n);
+    }
+    BuildArrays view(uint32_t n) {
+        BuildArrays b{}; b.n = n; b.wtri = wtri.data(); b.primLo = primLo.data(); b.primHi = primHi.data(); b.boundsBits = bounds.data();
+        b.keys = keys.data(); b.vals = vals.data(); b.left = left.data(); b.right = right.data(); b.parentInner = pin.data(); b.parentLeaf = pleaf.data();
+        b.nodeLo = nodeLo.data(); b.nodeHi = nodeHi.data(); b.visit = visit.data(); b.wideCounters = wideCounters.data(); b.sah = sah.data();
+        return b;
+    }
+    void initBuild(BuildArrays& b) { std::fill(visit.begin(), visit.end(), 0u); bounds[0] = bounds[1] = bounds[2] = 0xFFFFFFFFu; bounds[3] = bounds[4] = bounds[5] = 0u; sah[0] = sah[1] = 0.0f; (void)b; }
+    void collapse(BuildArrays& b) {                                   // launchCollapse
+        qa[0] = WideItem{0, 0u, 0u, 0u}; wideCounters[0] = 1; wideCounters[1] = 1; wideCounters[2] = 0; wideCounters[3] = 0;
+        WideItem* in = qa.data(); WideItem* out = qb.data(); uint32_t* cin = &wideCounters[1]; uint32_t* cout = &wideCounters[2];
+        for (int level = 0; level <= OHB_MAX_LEVELS; level++) {
+            for (uint32_t i = 0; i < *cin; i++) emitWideNode(b, in[i], out, cout);
+            *cin = 0; if (*cout) wideCounters[3]++;
+            std::swap(in, out); std::swap(cin, cout);
+        }
+    }
+    void fromPrims(BuildArrays& b) {                                  // launchBuildFromPrims
+        const uint32_t n = b.n;
+        for (uint32_t i = 0; i < n; i++) buildMorton(b, i);
+        {   // stand-in for radixSort64 (device-only): stable sort by key
+            std::vector<uint32_t> order(n); std::iota(order.begin(), order.end(), 0u);
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return keys[x] < keys[y]; });
+            std::vector<uint64_t> k2(n); std::vector<uint32_t> v2(n);
+            for (uint32_t i = 0; i < n; i++) { k2[i] = keys[order[i]]; v2[i] = vals[order[i]]; }
+            std::copy(k2.begin(), k2.end(), keys.begin()); std::copy(v2.begin(), v2.end(), vals.begin());
+        }
+        if (n >= 2) {
+            for (uint32_t i = 0; i + 1 < n; i++) buildHierarchyNode(b, int(i));
+            for (uint32_t i = 0; i < n; i++) sweepFromLeaf(b, i, 0u);
+            const char* tp = getenv("OHB_TREELET_PASSES"); uint32_t passes = tp ? uint32_t(atoi(tp)) : 3u;
+            for (uint32_t pass = 0, gamma = OHB_TREELET_LEAVES; pass < passes; pass++, gamma *= 2u) {
+                std::fill(visit.begin(), visit.end(), 0u);
+                for (uint32_t i = 0; i < n; i++) sweepFromLeaf(b, i, gamma);
+            }
+        }
+        collapse(b);
+    }
+    void build(BuildArrays& b) { initBuild(b); for (uint32_t i = 0; i < b.n; i++) buildWorldTri(b, i); fromPrims(b); }                 // launchBuild
+    void refit(BuildArrays& b) {                                                                                                       // launchRefit
+        initBuild(b); for (uint32_t i = 0; i < b.n; i++) buildWorldTri(b, i);
+        if (b.n >= 2) for (uint32_t i = 0; i < b.n; i++) sweepFromLeaf(b, i, 0u);
+        collapse(b);
+    }
+    void tlas(BuildArrays& b, const f4* lo, const f4* hi, const uint32_t* iop, bool refitOnly) {                                       // launchBuildTlas
+        initBuild(b); for (uint32_t i = 0; i < b.n; i++) buildTlasPrim(b, lo, hi, iop, i);
+        if (!refitOnly) { fromPrims(b); return; }
+        if (b.n >= 2) for (uint32_t i = 0; i < b.n; i++) sweepFromLeaf(b, i, 0u);
+        collapse(b);
+    }
+};
+static void emulInstanceTables(EmulScene* s) {           // instanceTables of ohb_api.cu
+    uint32_t ni = uint32_t(s->instances.size());
+    s->instXform.assign(size_t(ni) * 3 + 3, f4{}); s->instNormalMat.assign(size_t(ni) * 3 + 3, f4{}); s->instInv.assign(size_t(ni) * 3 + 3, f4{});
+    for (uint32_t i = 0; i < ni; i++) {
+        const float* a = s->instances[i].xform;
+        memcpy(&s->instXform[size_t(i) * 3], a, 48);
+        float co[3][3];
+        co[0][0] = a[5] * a[10] - a[6] * a[9];  co[0][1] = a[6] * a[8] - a[4] * a[10]; co[0][2] = a[4] * a[9] - a[5] * a[8];
+        co[1][0] = a[2] * a[9] - a[1] * a[10];  co[1][1] = a[0] * a[10] - a[2] * a[8]; co[1][2] = a[1] * a[8] - a[0] * a[9];
+        co[2][0] = a[1] * a[6] - a[2] * a[5];   co[2][1] = a[2] * a[4] - a[0] * a[6];  co[2][2] = a[0] * a[5] - a[1] * a[4];
+        float det = a[0] * co[0][0] + a[1] * co[0][1] + a[2] * co[0][2], id = 1.0f / det;
+        float nm[12], iv[12];
+        for (int r = 0; r < 3; r++) { for (int k = 0; k < 3; k++) nm[r * 4 + k] = co[r][k] * id; nm[r * 4 + 3] = 0; }
+        for (int r = 0; r < 3; r++) { for (int k = 0; k < 3; k++) iv[r * 4 + k] = nm[k * 4 + r]; iv[r * 4 + 3] = -(iv[r * 4] * a[3] + iv[r * 4 + 1] * a[7] + iv[r * 4 + 2] * a[11]); }
+        memcpy(&s->instNormalMat[size_t(i) * 3], nm, 48); memcpy(&s->instInv[size_t(i) * 3], iv, 48);
+    }
+}
+static BuildArrays emulMainArrays(EmulScene* s, uint32_t n) {
+    BuildArrays b = s->mainB->arrays(n);
+    b.positions = s->positions.data(); b.posStride = s->stride; b.indices = s->indices.data(); b.triInst = s->triInst.data(); b.instXform = s->instXform.data();
+    b.activeTris = s->active.data(); b.wnodes = s->wnodes.data(); b.tris = s->tris.data();
+    return b;
+}
+// ohb_build_accel, both modes
+static void emulBuildAccel(EmulScene* s) {
+    if (!s->mainB) s->mainB = new HostBuilder();
+    if (!s->tlasB) s->tlasB = new HostBuilder();
+    uint32_t ni = uint32_t(s->instances.size());
+    s->triInst.assign(s->ntris, 0xFFFFFFFFu); s->active.clear(); s->ranges.clear();
+    emulInstanceTables(s);
+    for (uint32_t i = 0; i < ni; i++) {
+        const ohb_instance& in = s->instances[i];
+        if ((in.mask & 0xFFu) == 0u) continue;
+        uint32_t first = uint32_t(s->active.size());
+        for (uint32_t t = in.first_tri; t < in.first_tri + in.tri_count && t < s->ntris; t++) { if (s->triInst[t] == 0xFFFFFFFFu) s->active.push_back(t); s->triInst[t] = i; }
+        if (s->active.size() > first) s->ranges.push_back({i, first, uint32_t(s->active.size()) - first});
+    }
+    uint32_t n = uint32_t(s->active.size()); s->numActive = n; s->numNodes = 0; s->levels = 0; s->sah = 0;
+    if (n == 0) return;
+    s->wnodes.assign(size_t(n) * OHB_WNODE_VECS, u4{0, 0, 0, 0}); s->tris.assign(size_t(n) * 3, f4{});
+    if (!s->accelMode) {
+        BuildArrays b = emulMainArrays(s, n);
+        s->mainB->build(b);
+        s->numNodes = s->mainB->wideCounters[0]; s->levels = s->mainB->wideCounters[3] + 1;
+        float ra = n >= 2 ? boxArea(xyz(s->mainB->nodeLo[0]), xyz(s->mainB->nodeHi[0])) : 0.0f;
+        s->sah = ra > 0 ? (s->mainB->sah[0] + s->mainB->sah[1]) / ra : float(n);
+        return;
+    }
+    s->blasLo.assign(ni + 1, f4{}); s->blasHi.assign(ni + 1, f4{}); s->blasInfo.assign(ni + 1, u4{0, 0, 0, 0}); s->instOfPrim.clear();
+    uint32_t blasLevels = 0;
+    for (const EmulScene::Range& r : s->ranges) {
+        BuildArrays b = emulMainArrays(s, r.count);
+        b.objectSpace = 1u; b.activeTris = s->active.data() + r.first; b.wnodes = s->wnodes.data() + size_t(r.first) * OHB_WNODE_VECS; b.tris = s->tris.data() + size_t(r.first) * 3u;
+        s->mainB->build(b);
+        storeBlasRootBox(b, s->blasLo.data(), s->blasHi.data(), r.inst, &blasLevels);
+        s->blasInfo[r.inst] = u4{r.first, r.first, r.count, 0u}; s->instOfPrim.push_back(r.inst);
+    }
+    uint32_t np = uint32_t(s->ranges.size());
+    s->tlasNodes.assign(size_t(np + 1) * OHB_WNODE_VECS, u4{0, 0, 0, 0}); s->tlasLeaves.assign(size_t(np + 1) * 3, f4{});
+    BuildArrays tb = s->tlasB->arrays(np); tb.instXform = s->instXform.data(); tb.wnodes = s->tlasNodes.data(); tb.tris = s->tlasLeaves.data();
+    s->tlasB->tlas(tb, s->blasLo.data(), s->blasHi.data(), s->instOfPrim.data(), false);
+    s->numNodes = s->tlasB->wideCounters[0]; s->levels = s->tlasB->wideCounters[3] + 1 + blasLevels + 1;
+}
+// ohb_update_instances
+static void emulUpdateInstances(EmulScene* s, const ohb_instance* inst, uint32_t n) {
+    for (uint32_t i = 0; i < n && i < s->instances.size(); i++) memcpy(s->instances[i].xform, inst[i].xform, 48);
+    emulInstanceTables(s);
+    if (!s->numActive) return;
+    if (s->accelMode) {
+        uint32_t np = uint32_t(s->ranges.size());
+        BuildArrays tb = s->tlasB->view(np); tb.instXform = s->instXform.data(); tb.wnodes = s->tlasNodes.data(); tb.tris = s->tlasLeaves.data();
+        s->tlasB->tlas(tb, s->blasLo.data(), s->blasHi.data(), s->instOfPrim.data(), true);
+        s->numNodes = s->tlasB->wideCounters[0];
+    } else {
+        BuildArrays b = s->mainB->view(s->numActive);
+        b.positions = s->positions.data(); b.posStride = s->stride; b.indices = s->indices.data(); b.triInst = s->triInst.data(); b.instXform = s->instXform.data();
+        b.activeTris = s->active.data(); b.wnodes = s->wnodes.data(); b.tris = s->tris.data();
+        s->mainB->refit(b);
+        s->numNodes = s->mainB->wideCounters[0];
+    }
+}
 
 extern "C" {
 
@@ -87,124 +235,13 @@ void* emul_scene_create(const emul_scene_desc* d) {
         s->envW = d->env_w; s->envH = d->env_h; s->env.resize(size_t(d->env_w) * d->env_h); memcpy(s->env.data(), d->env, s->env.size() * 16);
         s->marg.assign(d->marg, d->marg + d->env_h); s->cond.assign(d->cond, d->cond + size_t(d->env_w) * d->env_h); s->envIntegral = d->env_integral;
     } else { s->marg.assign(1, 1.0f); s->cond.assign(1, 1.0f); }
-    // ---- same host prologue as ohb_build_accel -------------------------------------------------
-    uint32_t ni = d->ninstances;
-    s->triInst.assign(d->ntris, 0xFFFFFFFFu);
-    s->instXform.resize(size_t(ni) * 3 + 3); s->instNormalMat.resize(size_t(ni) * 3 + 3); s->instInv.resize(size_t(ni) * 3 + 3);
-    for (uint32_t i = 0; i < ni; i++) {
-        const ohb_instance& in = d->instances[i];
-        const float* a = in.xform;
-        memcpy(&s->instXform[size_t(i) * 3], a, 48);
-        float co[3][3];
-        co[0][0] = a[5] * a[10] - a[6] * a[9];  co[0][1] = a[6] * a[8] - a[4] * a[10]; co[0][2] = a[4] * a[9] - a[5] * a[8];
-        co[1][0] = a[2] * a[9] - a[1] * a[10];  co[1][1] = a[0] * a[10] - a[2] * a[8]; co[1][2] = a[1] * a[8] - a[0] * a[9];
-        co[2][0] = a[1] * a[6] - a[2] * a[5];   co[2][1] = a[2] * a[4] - a[0] * a[6];  co[2][2] = a[0] * a[5] - a[1] * a[4];
-        float det = a[0] * co[0][0] + a[1] * co[0][1] + a[2] * co[0][2], id = 1.0f / det;
-        float nm[12], iv[12];
-        for (int r = 0; r < 3; r++) { for (int k = 0; k < 3; k++) nm[r * 4 + k] = co[r][k] * id; nm[r * 4 + 3] = 0; }
-        for (int r = 0; r < 3; r++) { for (int k = 0; k < 3; k++) iv[r * 4 + k] = nm[k * 4 + r]; iv[r * 4 + 3] = -(iv[r * 4] * a[3] + iv[r * 4 + 1] * a[7] + iv[r * 4 + 2] * a[11]); }
-        memcpy(&s->instNormalMat[size_t(i) * 3], nm, 48); memcpy(&s->instInv[size_t(i) * 3], iv, 48);
-        if ((in.mask & 0xFFu) == 0u) continue;
-        for (uint32_t t = in.first_tri; t < in.first_tri + in.tri_count && t < d->ntris; t++) { if (s->triInst[t] == 0xFFFFFFFFu) s->active.push_back(t); s->triInst[t] = i; }
-    }
-    // ---- emulate launchBuild ---------------------------------------------------------------------
-    uint32_t n = uint32_t(s->active.size()); s->numActive = n;
-    if (n == 0) return s;
-    std::vector<f4> wtri(size_t(n) * 3), primLo(n), primHi(n), nodeLo(n), nodeHi(n);
-    std::vector<uint32_t> bounds(6), vals(n), visit(n, 0), wideCounters(4, 0);
-    std::vector<uint64_t> keys(n);
-    std::vector<int32_t> left(n), right(n), pin(n, -1), pleaf(n, -1);
-    std::vector<float> sah(2, 0.0f);
-    s->wnodes.assign(size_t(n) * OHB_WNODE_VECS, u4{0, 0, 0, 0}); s->tris.resize(size_t(n) * 3);
-    BuildArrays b{};
-    b.positions = s->positions.data(); b.posStride = s->stride; b.indices = s->indices.data(); b.triInst = s->triInst.data(); b.instXform = s->instXform.data();
-    b.activeTris = s->active.data(); b.n = n; b.wtri = wtri.data(); b.primLo = primLo.data(); b.primHi = primHi.data(); b.boundsBits = bounds.data();
-    b.keys = keys.data(); b.vals = vals.data(); b.left = left.data(); b.right = right.data(); b.parentInner = pin.data(); b.parentLeaf = pleaf.data();
-    b.nodeLo = nodeLo.data(); b.nodeHi = nodeHi.data(); b.visit = visit.data();
-    b.wideCounters = wideCounters.data(); b.sah = sah.data(); b.wnodes = s->wnodes.data(); b.tris = s->tris.data();
-    bounds[0] = bounds[1] = bounds[2] = 0xFFFFFFFFu; bounds[3] = bounds[4] = bounds[5] = 0u;
-    for (uint32_t i = 0; i < n; i++) buildWorldTri(b, i);
-    for (uint32_t i = 0; i < n; i++) buildMorton(b, i);
-    {   // stand-in for radixSort64 (device-only): stable sort by key
-        std::vector<uint32_t> order(n); std::iota(order.begin(), order.end(), 0u);
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return keys[x] < keys[y]; });
-        std::vector<uint64_t> k2(n); std::vector<uint32_t> v2(n);
-        for (uint32_t i = 0; i < n; i++) { k2[i] = keys[order[i]]; v2[i] = vals[order[i]]; }
-        keys.swap(k2); vals.swap(v2); b.keys = keys.data(); b.vals = vals.data();
-    }
-    if (n >= 2 && getenv("EMUL_SAH_BUILD")) {
-        // EXPERIMENT (tree-quality ceiling): top-down binned SAH over all three axes instead of the Karras hierarchy; the
-        // product's refit sweep, treelet passes and 8-wide collapse then run on this topology unchanged.
-        struct Bx { f3 lo, hi; };
-        auto grow = [](Bx& a, f3 lo, f3 hi) { a.lo = vmin(a.lo, lo); a.hi = vmax(a.hi, hi); };
-        auto area = [](const Bx& a) { f3 e = a.hi - a.lo; return e.x < 0 ? 0.0f : 2.0f * (e.x * e.y + e.y * e.z + e.z * e.x); };
-        std::vector<uint32_t> ord(n); std::iota(ord.begin(), ord.end(), 0u);       // positions -> prim index (becomes vals)
-        std::vector<f3> cen(n); for (uint32_t i = 0; i < n; i++) cen[i] = (xyz(primLo[i]) + xyz(primHi[i])) * 0.5f;
-        int nextNode = 0;
-        struct Job { uint32_t first, count; int node; };
-        std::vector<Job> jobs; jobs.push_back({0, n, nextNode++}); pin[0] = -1;
-        const int NB = 32;
-        while (!jobs.empty()) {
-            Job j = jobs.back(); jobs.pop_back();
-            Bx cb{mk3(3e38f), mk3(-3e38f)};
-            for (uint32_t i = j.first; i < j.first + j.count; i++) grow(cb, cen[ord[i]], cen[ord[i]]);
-            float best = 3e38f; int bAxis = -1, bk = -1;
-            for (int ax = 0; ax < 3; ax++) {
-                float cmin = comp(cb.lo, ax), cext = comp(cb.hi, ax) - cmin; if (!(cext > 0)) continue;
-                Bx bb[NB]; int bc[NB]; for (int k = 0; k < NB; k++) { bb[k] = Bx{mk3(3e38f), mk3(-3e38f)}; bc[k] = 0; }
-                for (uint32_t i = j.first; i < j.first + j.count; i++) { uint32_t t = ord[i]; int k = std::min(NB - 1, int(NB * ((comp(cen[t], ax) - cmin) / cext))); grow(bb[k], xyz(primLo[t]), xyz(primHi[t])); bc[k]++; }
-                float lA[NB], rA[NB]; int lC[NB], rC[NB]; Bx acc{mk3(3e38f), mk3(-3e38f)}; int c = 0;
-                for (int k = 0; k < NB; k++) { grow(acc, bb[k].lo, bb[k].hi); c += bc[k]; lA[k] = area(acc); lC[k] = c; }
-                acc = Bx{mk3(3e38f), mk3(-3e38f)}; c = 0;
-                for (int k = NB - 1; k >= 0; k--) { grow(acc, bb[k].lo, bb[k].hi); c += bc[k]; rA[k] = area(acc); rC[k] = c; }
-                for (int k = 0; k < NB - 1; k++) { if (!lC[k] || !rC[k + 1]) continue; float cost = lA[k] * lC[k] + rA[k + 1] * rC[k + 1]; if (cost < best) { best = cost; bAxis = ax; bk = k; } }
-            }
-            uint32_t mid = j.first + j.count / 2;
-            if (bAxis >= 0) {
-                float cmin = comp(cb.lo, bAxis), cext = comp(cb.hi, bAxis) - cmin;
-                auto it = std::partition(ord.begin() + j.first, ord.begin() + j.first + j.count, [&](uint32_t t) { return std::min(NB - 1, int(NB * ((comp(cen[t], bAxis) - cmin) / cext))) <= bk; });
-                mid = uint32_t(it - ord.begin());
-            }
-            if (mid == j.first || mid == j.first + j.count) mid = j.first + j.count / 2;
-            uint32_t cnts[2] = {mid - j.first, j.first + j.count - mid}, firsts[2] = {j.first, mid}; int ch[2];
-            for (int h = 0; h < 2; h++) {
-                if (cnts[h] == 1) { ch[h] = ~int(firsts[h]); pleaf[firsts[h]] = j.node; }
-                else { ch[h] = nextNode++; pin[ch[h]] = j.node; jobs.push_back({firsts[h], cnts[h], ch[h]}); }
-            }
-            left[j.node] = ch[0]; right[j.node] = ch[1];
-        }
-        for (uint32_t i = 0; i < n; i++) vals[i] = ord[i];
-        for (uint32_t i = 0; i < n; i++) sweepFromLeaf(b, i, 0u);
-        const char* tp = getenv("OHB_TREELET_PASSES"); uint32_t passes = tp ? uint32_t(atoi(tp)) : 3u;
-        for (uint32_t pass = 0, gamma = OHB_TREELET_LEAVES; pass < passes; pass++, gamma *= 2u) {
-            std::fill(visit.begin(), visit.end(), 0u);
-            for (uint32_t i = 0; i < n; i++) sweepFromLeaf(b, i, gamma);
-        }
-    } else if (n >= 2) {
-        for (uint32_t i = 0; i + 1 < n; i++) buildHierarchyNode(b, int(i));
-        for (uint32_t i = 0; i < n; i++) sweepFromLeaf(b, i, 0u);
-        const char* tp = getenv("OHB_TREELET_PASSES"); uint32_t passes = tp ? uint32_t(atoi(tp)) : 3u;
-        for (uint32_t pass = 0, gamma = OHB_TREELET_LEAVES; pass < passes; pass++, gamma *= 2u) {
-            std::fill(visit.begin(), visit.end(), 0u);
-            for (uint32_t i = 0; i < n; i++) sweepFromLeaf(b, i, gamma);
-        }
-    }
-    {   // emulate the level loop of launchBuild
-        std::vector<WideItem> qa(n / 4 + 2), qb(n / 4 + 2);
-        qa[0] = WideItem{0, 0u, 0u, 0u}; wideCounters[0] = 1; wideCounters[1] = 1; wideCounters[2] = 0; wideCounters[3] = 0;
-        WideItem* in = qa.data(); WideItem* out = qb.data(); uint32_t* cin = &wideCounters[1]; uint32_t* cout = &wideCounters[2];
-        for (int level = 0; level <= OHB_MAX_LEVELS; level++) {
-            for (uint32_t i = 0; i < *cin; i++) emitWideNode(b, in[i], out, cout);
-            *cin = 0; if (*cout) wideCounters[3]++;
-            std::swap(in, out); std::swap(cin, cout);
-        }
-    }
-    s->numNodes = wideCounters[0]; s->levels = wideCounters[3] + 1;
-    float ra = n >= 2 ? boxArea(xyz(nodeLo[0]), xyz(nodeHi[0])) : 0.0f;
-    s->sah = ra > 0 ? (sah[0] + sah[1]) / ra : float(n);
+    s->instances.assign(d->instances, d->instances + d->ninstances);
+    emulBuildAccel(s);
     return s;
 }
-void emul_scene_destroy(void* h) { delete (EmulScene*)h; }
+void emul_scene_destroy(void* h) { EmulScene* s = (EmulScene*)h; delete s->mainB; delete s->tlasB; delete s; }
+void emul_scene_set_accel_mode(void* h, int mode) { EmulScene* s = (EmulScene*)h; if ((mode != 0) != (s->accelMode != 0)) { s->accelMode = mode ? 1 : 0; emulBuildAccel(s); } }
+void emul_scene_update_instances(void* h, const ohb_instance* inst, uint32_t n) { emulUpdateInstances((EmulScene*)h, inst, n); }
 void emul_accel_stats(void* h, uint32_t* numNodes, float* sah) { EmulScene* s = (EmulScene*)h; *numNodes = s->numNodes; *sah = s->sah; }
 uint32_t emul_accel_levels(void* h) { return ((EmulScene*)h)->levels; }
 // ---- SVGF denoiser (ohb_svgf.h) driven like launchSvgf (ohb_kernels.cu) ---------------------------------------

@@ -48,6 +48,8 @@ def lib():
         _LIB.emul_f2h.restype = C.c_uint16; _LIB.emul_f2h.argtypes = [C.c_float]
         _LIB.emul_h2f.restype = C.c_float; _LIB.emul_h2f.argtypes = [C.c_uint16]
         _LIB.emul_trav_stats.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.c_int]
+        _LIB.emul_scene_set_accel_mode.argtypes = [C.c_void_p, C.c_int]
+        _LIB.emul_scene_update_instances.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         _LIB.emul_hybrid_shadow.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _LIB.emul_hybrid_gi.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _LIB.emul_nrd_pack_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -92,6 +94,12 @@ class EmulScene:
     def occluded(self, rays):
         rays = np.ascontiguousarray(rays, O.RAY_DTYPE); occ = np.zeros(len(rays), np.uint8)
         lib().emul_occluded_batch(self.h, _p(rays), len(rays), _p(occ)); return occ
+
+    def set_accel_mode(self, two_level: bool):
+        lib().emul_scene_set_accel_mode(self.h, int(two_level))
+
+    def update_instances(self, instances):
+        inst = np.ascontiguousarray(instances); lib().emul_scene_update_instances(self.h, _p(inst), len(inst))
 
     def hybrid_shadow(self, W, H, gpos, gnrm, params):
         gpos = np.ascontiguousarray(gpos, np.float32); gnrm = np.ascontiguousarray(gnrm, np.float32); mask = np.zeros((H, W), np.uint8)
