@@ -16,12 +16,14 @@ namespace ohb {
 struct HybridShadowParams { f3 lightDir; float lightRadius; f3 lightPos; float lightRange; uint32_t W, H, lightType, sampleCount; };
 struct HybridGiParams { f3 lightPos; float lightIntensity; uint32_t W, H, sampleCount, frameIndex; };
 
-OHB_HD float fractf(float x) { return x - floorf(x); }
+OHB_HD float fractf(float x) { return xsub(x, floorf(x)); }
+// The hash multiplies its rounding errors by ~10^3 (fract of a product of magnitude ~2000), so its operation order is part of
+// the spec shared with the oracle: one rounding per operation, never contracted into an FMA.
 OHB_HD float hybridHash(float px, float py) {                       // rt_shadow.rgen:25-29 == rt_gi.rgen:30-34
-    f3 p3 = mk3(fractf(px * 0.1031f), fractf(py * 0.1031f), fractf(px * 0.1031f));
-    float d = dot(p3, mk3(p3.y + 33.33f, p3.z + 33.33f, p3.x + 33.33f));
-    p3 = mk3(p3.x + d, p3.y + d, p3.z + d);
-    return fractf((p3.x + p3.y) * p3.z);
+    f3 p3 = mk3(fractf(xmul(px, 0.1031f)), fractf(xmul(py, 0.1031f)), fractf(xmul(px, 0.1031f)));
+    float d = xadd(xadd(xmul(p3.x, xadd(p3.y, 33.33f)), xmul(p3.y, xadd(p3.z, 33.33f))), xmul(p3.z, xadd(p3.x, 33.33f)));
+    p3 = mk3(xadd(p3.x, d), xadd(p3.y, d), xadd(p3.z, d));
+    return fractf(xmul(xadd(p3.x, p3.y), p3.z));
 }
 OHB_HD f3 decodeNormalOctahedron(float ex, float ey) {              // encoding.glsl:15-22
     float fx = ex * 2.0f - 1.0f, fy = ey * 2.0f - 1.0f;
@@ -46,7 +48,7 @@ OHB_HD uint8_t hybridShadowPixel(const SceneDev& sc, const HybridShadowParams& p
     float visibility = 0.0f;
     for (uint32_t s = 0; s < sampleCount; s++) {
         const float fs = float(s);
-        const float r1 = hybridHash(float(x) + fs * 7.13f, float(y) + fs * 13.37f), r2 = hybridHash(float(x) + fs * 31.17f, float(y) + fs * 47.53f);
+        const float r1 = hybridHash(xadd(float(x), xmul(fs, 7.13f)), xadd(float(y), xmul(fs, 13.37f))), r2 = hybridHash(xadd(float(x), xmul(fs, 31.17f)), xadd(float(y), xmul(fs, 47.53f)));
         f3 L; float tMax;
         if (pc.lightType == 0u) {
             f3 lightDir = normalize(-pc.lightDir), T, B; hybridBasis(lightDir, T, B);
@@ -84,8 +86,8 @@ OHB_HD h4 hybridGiPixel(const SceneDev& sc, const HybridGiParams& pc, const f4* 
     const uint32_t sampleCount = pc.sampleCount > 1u ? pc.sampleCount : 1u;
     f3 indirect = mk3(0.0f);
     for (uint32_t s = 0; s < sampleCount; s++) {
-        const float fs = float(s), hx = float(x) + (fs * 7.13f + float(pc.frameIndex) * 1.618f), hy = float(y) + fs * 13.37f;
-        const f3 dir = hybridCosineHemisphere(hybridHash(hx, hy), hybridHash(hx + 127.1f, hy + 311.7f), N);
+        const float fs = float(s), hx = xadd(float(x), xadd(xmul(fs, 7.13f), xmul(float(pc.frameIndex), 1.618f))), hy = xadd(float(y), xmul(fs, 13.37f));
+        const f3 dir = hybridCosineHemisphere(hybridHash(hx, hy), hybridHash(xadd(hx, 127.1f), xadd(hy, 311.7f)), N);
         const ohb_hit h = traceClosest(sc, origin, dir, 0.01f, 100.0f);
         if (h.prim == OHB_MISS) continue;
         const f4 m = instMaterials[sc.triInst[h.prim]];                 // materials[gl_InstanceID]

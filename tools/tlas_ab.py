@@ -27,9 +27,9 @@ for name, two in (("flatten", False), ("two_level", True)):
     t0 = time.perf_counter(); r.trace(rays[:4096]); r.synchronize()
     t0 = time.perf_counter(); h = r.trace(rays); e["trace_batch_mrays_s_incl_copies"] = len(rays) / (time.perf_counter() - t0) / 1e6
     v, p = cam.view(), cam.proj(W, H)
-    r.render(v, p, 4); r.synchronize(); r.reset_accumulation(); r.reset_counters()
-    r.timer_start(); r.render(v, p, 16); ms = r.timer_stop(); c = r.counters()
-    e["render_msamples_s"] = W * H * 16 / ms / 1e3; e["render_grays_s"] = (c["closest_rays"] + c["shadow_rays"]) / ms / 1e6
+    r.render(v, p, 16); r.render(v, p, 16); r.synchronize(); r.reset_accumulation(); r.reset_counters()      # warm-up with the same batch size (path-state allocation)
+    r.timer_start(); r.render(v, p, 16); r.render(v, p, 16); ms = r.timer_stop(); c = r.counters()
+    e["render_msamples_s"] = W * H * 32 / ms / 1e3; e["render_grays_s"] = (c["closest_rays"] + c["shadow_rays"]) / ms / 1e6
     ups = []
     for k in range(3):
         st = r.update_instances(moved if k % 2 == 0 else inst); ups.append(float(st.update_ms))
