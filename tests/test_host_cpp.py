@@ -58,7 +58,7 @@ def test_turntable_and_inverse_fit_binaries(tmp_path):
         assert len(frames) == 3
         im = np.asarray(Image.open(os.path.join(out, frames[1])).convert("RGB"))
         assert im.shape == (90, 160, 3) and im.mean() > 2
-    r = subprocess.run([os.path.join(HOST, "inverse_fit"), "--backend", "pt", "--preset", "lantern", "--quality", "draft", "--iters", "6", "--tris", "3000"], capture_output=True, text=True)
+    r = subprocess.run([os.path.join(HOST, "inverse_fit"), "--backend", "pt", "--preset", "lantern", "--quality", "draft", "--iters", "6", "--tris", "3000", "--schedule", "flat"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr                         # exit 0 <=> the fit reduced the loss
     assert "probes/s" in r.stdout
 
@@ -86,3 +86,15 @@ def test_cpp_host_ingests_the_real_assets_like_the_python_packer(tmp_path):
     assert np.frombuffer(rec[7], ps.instances.dtype).tobytes() == ps.instances.tobytes()                                            # T * R_y(180) * S
     assert rec[8] == ps.light_ssbo.tobytes()                                                                                        # key light + emissive-mesh auto light + env index
     assert tuple(np.frombuffer(rec[9], np.uint32)) == (2048, 2048, 4) and np.array_equal(np.frombuffer(rec[10], np.uint8).reshape(ps.textures.shape), ps.textures)
+
+
+@pytest.mark.gpu
+def test_inverse_fit_staged_schedule_reduces_the_loss():
+    """StagedFitter restated (staged_fit.hpp): multi-start probe, the env -> lights -> albedo -> brdf -> ... -> refine stage list with
+    per-stage Adam, hybridSpecularRGB + regularisers; the probes of every stage fan out over the GPUs."""
+    _build()
+    r = subprocess.run([os.path.join(HOST, "inverse_fit"), "--backend", "pt", "--preset", "lantern", "--quality", "draft", "--iters", "20", "--tris", "3000"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr                  # exit 0 <=> final loss < initial loss
+    out = r.stdout
+    assert "candidate 5/5" in out and all(f"-- stage {s} " in out for s in ("env", "lights", "albedo", "brdf", "brdf2", "pedestal", "lights2", "refine"))
+    assert "probes/s" in out and "final loss" in out

@@ -4,7 +4,7 @@ timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
 tail -c 700 $O/${TAG}_config4_n$N.json; tail -3 $O/${TAG}_config4_n$N.err
 timeout 300 python tools/converged_4k.py --spp 256 > $O/${TAG}_config4_n1.json 2> $O/${TAG}_config4_n1.err; tail -c 400 $O/${TAG}_config4_n1.json
 make -C host all > /dev/null 2>&1
-( time timeout 600 host/inverse_fit --backend pt --preset lantern --quality draft --iters 6 --gpus $N ) > $O/${TAG}_config5_n$N.log 2>&1; tail -8 $O/${TAG}_config5_n$N.log
+( time timeout 600 host/inverse_fit --backend pt --preset lantern --quality draft --iters 6 --gpus $N --schedule flat ) > $O/${TAG}_config5_n$N.log 2>&1; tail -8 $O/${TAG}_config5_n$N.log
 ( time timeout 600 host/inverse_fit --backend pt --preset lantern --quality draft --iters 6 --gpus 1 ) > $O/${TAG}_config5_n1.log 2>&1; tail -8 $O/${TAG}_config5_n1.log
 # realtime config with the reworked a-trous weights, with and without the SVGF denoiser; realtime + SVGF GPU tests
 timeout 300 python bench.py --workload synthetic2m --integrator realtime --steps 60 --no-cpu-baseline > $O/${TAG}_bench_s2m_rt.json 2> $O/${TAG}_bench_s2m_rt.err

@@ -31,7 +31,7 @@ timeout 300 python tools/converged_4k.py --spp 256 > $O/${TAG}_config4_n1.json 2
 make -C host all > /dev/null 2>&1
 for N in 1 4 8; do
   [ $N -gt $NG ] && continue
-  ( time timeout 600 host/inverse_fit --backend pt --preset lantern --quality draft --iters 6 --gpus $N ) > $O/${TAG}_config5_n$N.log 2>&1; grep -E "probes/s|real" $O/${TAG}_config5_n$N.log | tail -3
+  ( time timeout 600 host/inverse_fit --backend pt --preset lantern --quality draft --iters 6 --gpus $N --schedule flat ) > $O/${TAG}_config5_n$N.log 2>&1; grep -E "probes/s|real" $O/${TAG}_config5_n$N.log | tail -3
 done
 for N in 1 2 4 8; do
   [ $N -gt $NG ] && continue
