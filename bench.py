@@ -423,6 +423,10 @@ def main():
                                          "kernels": {k: {kk: v[kk] for kk in ("ms", "launches", "share_of_step", "bound", "frac") if kk in v} for k, v in k2.items()},
                                          "e2e": m2["e2e"], "gpu_launches": int(m2["cnt"]["kernel_launches"]), "clocks": m2["clk"]})
                 del r2
+                if integ == "offline" and not args.no_cpu_baseline:      # a short sample of the CPU restatement on this box's host cores, same scene and resolution
+                    cores = os.cpu_count() or 1
+                    cv, nfr, dt = cpu_oracle_rate(ps2, cam2, min(args.cpu_seconds, 4.0), cores, w2, h2)
+                    out["workloads"][-1]["cpu_baseline"] = {"value": cv, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": f"{nfr} x 1 spp x {w2}x{h2} frames in {dt:.1f} s"}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             cv, nfr, dt = cpu_oracle_rate(ps, cam, args.cpu_seconds, cores, Wd, Hd)

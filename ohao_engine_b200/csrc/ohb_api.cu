@@ -34,6 +34,18 @@ struct DevBuf {
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// scratch of one builder instance (launchBuild): the two-level build runs several BLAS builds concurrently, one set per stream
+struct BuilderSet {
+    DevBuf wtri, primLo, primHi, boundsBits, keys, vals, keysTmp, valsTmp, sortTemp, left, right, parentInner, parentLeaf, nodeLo, nodeHi, visit, wideCounters, itemsA, itemsB, sah;
+    cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
+    void release() {
+        DevBuf* all[] = {&wtri, &primLo, &primHi, &boundsBits, &keys, &vals, &keysTmp, &valsTmp, &sortTemp, &left, &right, &parentInner, &parentLeaf, &nodeLo, &nodeHi, &visit, &wideCounters, &itemsA, &itemsB, &sah};
+        for (DevBuf* b : all) b->release();
+        if (stream) cudaStreamDestroy(stream);
+        if (done) cudaEventDestroy(done);
+        stream = nullptr; done = nullptr;
+    }
+};
 struct M4h { float m[16]; };
 static M4h inverse4(const float* m) {   // cofactor inverse, fp32 (what glm::inverse computes)
     float inv[16];
@@ -79,6 +91,7 @@ struct ohb_ctx {
     uint32_t texW = 0, texH = 0, texLayers = 0, envW = 0, envH = 0; float envIntegral = 0.0f;
     bool accelValid = false; uint32_t numActive = 0;
     int accelMode = OHB_ACCEL_FLATTEN; uint32_t numTlasPrims = 0;
+    std::vector<BuilderSet> blasSets;        // extra builder scratch + streams for concurrent BLAS builds (set 0 = the context's own buffers and stream)
     ohb_accel_stats stats{};
     // scene (device)
     DevBuf positions, indices, normals, uvs, matIds, triInst, instXform, instNormalMat, instInv, matColors, tex, lights, env, marg, cond, rowTotal, integral;
@@ -195,6 +208,7 @@ void ohb_destroy(ohb_ctx* c) {
                      &c->motionAOV, &c->depthAOV, &c->svgfHistColor[0], &c->svgfHistColor[1], &c->svgfHistMoments[0], &c->svgfHistMoments[1],
                      &c->svgfHistGeom[0], &c->svgfHistGeom[1], &c->svgfColor[0], &c->svgfColor[1], &c->svgfVar[0], &c->svgfVar[1]};
     for (DevBuf* b : all) b->release();
+    for (BuilderSet& bs : c->blasSets) bs.release();
     if (c->evA) cudaEventDestroy(c->evA);
     if (c->evB) cudaEventDestroy(c->evB);
     if (c->evT0) cudaEventDestroy(c->evT0);
@@ -496,6 +510,27 @@ static int tlasBuildArrays(ohb_ctx* c, uint32_t np, BuildArrays& b) {
     b.wnodes = c->tlasNodes.as<u4>(); b.tris = c->tlasLeaves.as<f4>();
     return 0;
 }
+static int setBuildArrays(ohb_ctx* c, BuilderSet& q, size_t cap, BuildArrays& b) {
+    const size_t nn = cap;
+    CU(c, q.wtri.reserve(nn * 48)); CU(c, q.primLo.reserve(nn * 16)); CU(c, q.primHi.reserve(nn * 16)); CU(c, q.boundsBits.reserve(32));
+    CU(c, q.keys.reserve(nn * 8)); CU(c, q.vals.reserve(nn * 4)); CU(c, q.keysTmp.reserve(nn * 8)); CU(c, q.valsTmp.reserve(nn * 4));
+    CU(c, q.sortTemp.reserve(size_t(radixSortTempWords(uint32_t(cap))) * 4));
+    CU(c, q.left.reserve(nn * 4)); CU(c, q.right.reserve(nn * 4)); CU(c, q.parentInner.reserve(nn * 4)); CU(c, q.parentLeaf.reserve(nn * 4));
+    CU(c, q.nodeLo.reserve(nn * 16)); CU(c, q.nodeHi.reserve(nn * 16));
+    CU(c, q.visit.reserve(nn * 4)); CU(c, q.wideCounters.reserve(16)); CU(c, q.sah.reserve(8));
+    CU(c, q.itemsA.reserve((nn / 4 + 2) * sizeof(WideItem))); CU(c, q.itemsB.reserve((nn / 4 + 2) * sizeof(WideItem)));
+    if (!q.stream) { CU(c, cudaStreamCreateWithFlags(&q.stream, cudaStreamNonBlocking)); CU(c, cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming)); }
+    memset(&b, 0, sizeof(b));
+    b.positions = c->positions.as<uint8_t>(); b.posStride = c->posStride; b.indices = c->indices.as<uint32_t>(); b.triInst = c->triInst.as<uint32_t>();
+    b.instXform = c->instXform.as<f4>(); b.activeTris = c->activeTris.as<uint32_t>(); b.n = uint32_t(cap);
+    b.wtri = q.wtri.as<f4>(); b.primLo = q.primLo.as<f4>(); b.primHi = q.primHi.as<f4>(); b.boundsBits = q.boundsBits.as<uint32_t>();
+    b.keys = q.keys.as<uint64_t>(); b.vals = q.vals.as<uint32_t>();
+    b.left = q.left.as<int32_t>(); b.right = q.right.as<int32_t>(); b.parentInner = q.parentInner.as<int32_t>(); b.parentLeaf = q.parentLeaf.as<int32_t>();
+    b.nodeLo = q.nodeLo.as<f4>(); b.nodeHi = q.nodeHi.as<f4>();
+    b.visit = q.visit.as<uint32_t>(); b.wideCounters = q.wideCounters.as<uint32_t>(); b.sah = q.sah.as<float>();
+    b.wnodes = c->wnodes.as<u4>(); b.tris = c->tris.as<f4>();
+    return 0;
+}
 static uint32_t treeletPassesKnob() { static const uint32_t v = []() { const char* e = getenv("OHB_TREELET_PASSES"); return e ? uint32_t(strtoul(e, nullptr, 10)) : 3u; }(); return v; }
 
 int ohb_set_accel_mode(ohb_ctx* c, int mode) {
@@ -566,7 +601,6 @@ int ohb_build_accel(ohb_ctx* c) {
     // ---- two-level: one object-space BLAS per instance (createBLAS, rt_acceleration_structure.cpp:205-405) + the TLAS (buildTLAS, :419-535) ----
     uint32_t maxCount = 0; for (const Range& r : ranges) maxCount = std::max(maxCount, r.count);
     const uint32_t np = uint32_t(ranges.size());
-    BuildArrays b; if (mainBuildArrays(c, maxCount, b)) return 1;
     CU(c, c->blasLo.reserve(size_t(ni) * 16 + 16)); CU(c, c->blasHi.reserve(size_t(ni) * 16 + 16)); CU(c, c->blasInfo.reserve(size_t(ni) * 16 + 16));
     CU(c, c->instOfPrim.reserve(size_t(np) * 4 + 4)); CU(c, c->maxLevels.reserve(4));
     std::vector<uint32_t> info(size_t(ni) * 4, 0u), iop(np);
@@ -574,14 +608,24 @@ int ohb_build_accel(ohb_ctx* c) {
     CU(c, cudaMemcpyAsync(c->blasInfo.p, info.data(), info.size() * 4, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(c->instOfPrim.p, iop.data(), iop.size() * 4, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemsetAsync(c->maxLevels.p, 0, 4, c->stream));
+    // BLAS builds are chains of small, latency-bound kernels: run them on OHB_BLAS_STREAMS streams (default 8), each with its own
+    // builder scratch, so that several are in flight; everything joins the context's stream before the TLAS is built
+    static const uint32_t kStreams = []() { const char* e = getenv("OHB_BLAS_STREAMS"); uint32_t v = e ? uint32_t(strtoul(e, nullptr, 10)) : 8u; return std::min(std::max(v, 1u), 32u); }();
+    const uint32_t ns = std::min<uint32_t>(kStreams, np);
+    if (c->blasSets.size() < ns) c->blasSets.resize(ns);
+    std::vector<BuildArrays> sets(ns);
+    for (uint32_t k = 0; k < ns; k++) if (setBuildArrays(c, c->blasSets[k], maxCount, sets[k])) return 1;
     CU(c, cudaEventRecord(c->evA, c->stream));
-    for (const Range& r : ranges) {
-        BuildArrays bi = b;
+    for (uint32_t k = 0; k < ns; k++) CU(c, cudaStreamWaitEvent(c->blasSets[k].stream, c->evA, 0));       // the uploads above are on the context's stream
+    for (uint32_t j = 0; j < np; j++) {
+        const Range& r = ranges[j]; BuilderSet& q = c->blasSets[j % ns];
+        BuildArrays bi = sets[j % ns];
         bi.objectSpace = 1u; bi.activeTris = c->activeTris.as<uint32_t>() + r.first; bi.n = r.count;
         bi.wnodes = c->wnodes.as<u4>() + size_t(r.first) * OHB_WNODE_VECS; bi.tris = c->tris.as<f4>() + size_t(r.first) * 3u;   // node / triangle capacity of a BLAS = its triangle count
-        launchBuildBlas(bi, c->keysTmp.as<uint64_t>(), c->valsTmp.as<uint32_t>(), c->sortTemp.as<uint32_t>(), c->wideItemsA.as<WideItem>(), c->wideItemsB.as<WideItem>(), treeletPasses,
-                        c->blasLo.as<f4>(), c->blasHi.as<f4>(), r.inst, c->maxLevels.as<uint32_t>(), c->stream, &c->launches);
+        launchBuildBlas(bi, q.keysTmp.as<uint64_t>(), q.valsTmp.as<uint32_t>(), q.sortTemp.as<uint32_t>(), q.itemsA.as<WideItem>(), q.itemsB.as<WideItem>(), treeletPasses,
+                        c->blasLo.as<f4>(), c->blasHi.as<f4>(), r.inst, c->maxLevels.as<uint32_t>(), q.stream, &c->launches);
     }
+    for (uint32_t k = 0; k < ns; k++) { CU(c, cudaEventRecord(c->blasSets[k].done, c->blasSets[k].stream)); CU(c, cudaStreamWaitEvent(c->stream, c->blasSets[k].done, 0)); }
     BuildArrays tb; if (tlasBuildArrays(c, np, tb)) return 1;
     launchBuildTlas(tb, c->blasLo.as<f4>(), c->blasHi.as<f4>(), c->instOfPrim.as<uint32_t>(), false, c->tKeysTmp.as<uint64_t>(), c->tValsTmp.as<uint32_t>(), c->tSortTemp.as<uint32_t>(),
                     c->tItemsA.as<WideItem>(), c->tItemsB.as<WideItem>(), c->stream, &c->launches);

@@ -139,7 +139,7 @@ OHB_HD void buildTlasPrim(const BuildArrays& b, const f4* blasLo, const f4* blas
 // object-space root box of the BLAS just built (the binary root's box, or the single triangle's)
 OHB_HD void storeBlasRootBox(const BuildArrays& b, f4* blasLo, f4* blasHi, uint32_t inst, uint32_t* maxLevels) {
     if (b.n >= 2u) { blasLo[inst] = b.nodeLo[0]; blasHi[inst] = b.nodeHi[0]; } else { blasLo[inst] = b.primLo[0]; blasHi[inst] = b.primHi[0]; }
-    if (b.wideCounters[3] > *maxLevels) *maxLevels = b.wideCounters[3];
+    atomicMaxU32(maxLevels, b.wideCounters[3]);          // BLAS builds run concurrently on several streams
 }
 
 // Stage 2: 63-bit Morton code of the AABB centre (21 bits per axis).
