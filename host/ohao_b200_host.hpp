@@ -321,6 +321,9 @@ public:
     }
     [[nodiscard]] bool setMaterialData(const std::vector<float>& mc) { return check(ohb_set_materials(m_ctx, mc.data(), uint32_t(mc.size() / 12)), "setMaterialData"); }
     [[nodiscard]] bool setLightBuffer(const std::vector<uint8_t>& ssbo) { return check(ohb_set_lights(m_ctx, ssbo.data(), ssbo.size()), "setLightBuffer"); }
+    // RTAccelerationStructure: how BLAS / TLAS are realised, and buildTLAS in MODE_UPDATE (rt_acceleration_structure.cpp:467,503-512)
+    [[nodiscard]] bool setAccelMode(bool twoLevel) { return check(ohb_set_accel_mode(m_ctx, twoLevel ? OHB_ACCEL_TWO_LEVEL : OHB_ACCEL_FLATTEN), "setAccelMode"); }
+    [[nodiscard]] bool updateTLAS(const std::vector<ohb_instance>& inst) { return check(ohb_update_instances(m_ctx, inst.data(), uint32_t(inst.size())), "buildTLAS(update)"); }
     [[nodiscard]] bool readLDR(uint8_t* rgba8) { return check(ohb_read_ldr(m_ctx, rgba8), "getPixels"); }
     [[nodiscard]] bool readHDR(float* beauty, float* albedo, float* normal) { return check(ohb_read_hdr(m_ctx, beauty, albedo, normal), "readbackHDRBuffers"); }
     ohb_ctx* ctx() const { return m_ctx; }
@@ -351,6 +354,7 @@ public:
         if (!m_scene || !ensureRTRenderer()) return false;
         m_packed = packScene(*m_scene, !m_env.empty(), m_envIntensity);
         m_sceneDirty = false; m_lightsDirty = false;
+        if (!m_rt->setAccelMode(m_twoLevel)) return false;
         return m_rt->uploadScene(m_packed.arrays, m_env.empty() ? nullptr : m_env.data(), m_envW, m_envH);
     }
     [[nodiscard]] bool updateRTMaterialParams() {                             // no BVH rebuild (render_session.hpp:49-56)
@@ -358,6 +362,21 @@ public:
         packMaterials(m_packed.arrays, m_packed.layerIdx);
         return m_rt->setMaterialData(m_packed.arrays.matColors);
     }
+    // Actors moved (position / scale / yaw180 only): refit instead of rebuilding — the reference's per-frame buildTLAS(MODE_UPDATE).
+    // The mesh actors, their order and their triangle ranges must be those of the last updateSceneBuffers().
+    [[nodiscard]] bool updateInstanceTransforms() {
+        if (!m_rt || m_sceneDirty) return updateSceneBuffers();
+        SceneArrays& a = m_packed.arrays;
+        for (size_t i = 0; i < a.meshActors.size() && i < a.instances.size(); i++) {
+            const Actor* act = a.meshActors[i]; const float ry = act->yaw180 ? -1.0f : 1.0f;
+            float x[12] = {ry * act->scale.x, 0, 0, act->position.x, 0, act->scale.y, 0, act->position.y, 0, 0, ry * act->scale.z, act->position.z};
+            std::memcpy(a.instances[i].xform, x, 48);
+        }
+        m_rt->resetAccumulation();
+        packLights(a, !m_env.empty(), m_envIntensity);                       // emissive-mesh auto lights follow their actors
+        return m_rt->updateTLAS(a.instances) && m_rt->setLightBuffer(a.lightSSBO);
+    }
+    void setTwoLevelAccel(bool on) { m_twoLevel = on; m_sceneDirty = true; }
     [[nodiscard]] bool updateRTLightParams() {
         if (!m_rt || m_sceneDirty) return updateSceneBuffers();
         packLights(m_packed.arrays, !m_env.empty(), m_envIntensity); m_lightsDirty = false;
@@ -396,7 +415,7 @@ private:
     }
     uint32_t m_w, m_h; int m_device; Scene* m_scene = nullptr; Camera m_camera; RenderMode m_mode = RenderMode::RTOffline; DenoiseMode m_denoise = DenoiseMode::None;
     std::unique_ptr<CudaRTRenderer> m_rt; PackedScene m_packed; std::vector<float> m_env; uint32_t m_envW = 0, m_envH = 0; float m_envIntensity = 1.0f;
-    uint32_t m_seed = 0, m_spf = 1; bool m_sceneDirty = true, m_lightsDirty = false, m_settingsDirty = true; std::vector<uint8_t> m_pixels;
+    uint32_t m_seed = 0, m_spf = 1; bool m_sceneDirty = true, m_lightsDirty = false, m_settingsDirty = true, m_twoLevel = false; std::vector<uint8_t> m_pixels;
 };
 
 // ---- image output: PNG with stored (uncompressed) deflate blocks, no dependencies -----------------------------------------

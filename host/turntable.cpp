@@ -88,6 +88,10 @@ int main(int argc, char** argv) {
     if (!renderer.updateSceneBuffers()) { std::cerr << "FATAL: scene upload failed\n"; return 1; }
     const float orbitRadius = mode == "env" ? 8.0f : (mode == "mirror" ? 4.5f : 4.2f), orbitHeight = mode == "env" ? 1.0f : -3.5f;
     const bool write = !hasFlag(argc, argv, "no-write");
+    // --two-level: BLAS per actor + TLAS instead of the flattened tree; --bob: the hero also bobs up and down every frame and the
+    // structure is refit (buildTLAS in MODE_UPDATE) instead of rebuilt
+    const bool bob = hasFlag(argc, argv, "bob"); const float heroY0 = hero->position.y;
+    if (hasFlag(argc, argv, "two-level")) { renderer.setTwoLevelAccel(true); if (!renderer.updateSceneBuffers()) { std::cerr << "FATAL: scene upload failed\n"; return 1; } }
     if (write) std::filesystem::create_directories(outdir);
     auto t0 = std::chrono::high_resolution_clock::now();
     for (int frame = 0; frame < totalFrames; frame++) {
@@ -97,6 +101,7 @@ int main(int argc, char** argv) {
         camera.setPosition({cx, orbitHeight, cz});
         camera.setRotation(15.0f, std::atan2(-cz, -cx) * 57.29577951308232f);
         camera.setFov(70.0f);
+        if (bob) { hero->position.y = heroY0 + 0.3f * std::sin(angle * 4.0f); if (!renderer.updateInstanceTransforms()) { std::cerr << "FATAL: TLAS update failed\n"; return 1; } }
         if (realtime) { renderer.notifyCameraChanged(); renderer.render(); }            // realtime: one frame per orbit step, history carried over
         else { renderer.resetAccumulation(); renderer.render(uint32_t(spp)); }            // offline: spp render() calls, batched into one submission
         const auto pixels = renderer.getPixelSpan();

@@ -51,7 +51,7 @@ def test_cornell_box_binary_matches_python_binding(tmp_path):
 def test_turntable_and_inverse_fit_binaries(tmp_path):
     _build()
     out = str(tmp_path / "tt")
-    for mode, extra in (("env", []), ("cornell", ["--realtime"])):
+    for mode, extra in (("env", []), ("cornell", ["--realtime"]), ("dark", ["--two-level", "--bob"])):
         r = subprocess.run([os.path.join(HOST, "turntable"), "blob:5000", mode, "4", "3", "--width", "160", "--height", "90", "--outdir", out] + extra, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         frames = sorted(f for f in os.listdir(out) if f.startswith(mode))
