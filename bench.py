@@ -284,12 +284,18 @@ def kernel_table(m, st, workload, integrator, W, H, spp, steps, num_sms=148):
         e = {"ms": round(x["ms"], 3), "launches": x["launches"], "share_of_step": round(x["ms"] / ms, 4), "units_per_launch": upl, "avg_launch_ms": avg,
              "measured_dram_bytes_per_unit": prof["dram_bytes_per_unit"] if prof else None, "profile_source": prof["source"] if prof else None}
         if k.startswith("trace_"):
+            # Issue roofline.  frac = the fraction of issue slots the schedulers used (smsp__issue_active, hardware counter, weighted by
+            # instructions over the launches of the committed capture); achieved = frac x peak.  Instruction counts cannot be measured
+            # outside a profiler, and the capture runs 4 spp per step (its short launches carry relatively more tail), so its
+            # warp-instructions per ray are reported as profiled and the live figure is the one implied by the live ray rate.
             wi = prof["warp_inst_per_unit"] if prof else None
-            ach = (wi * upl / (avg * 1e-3) / 1e9) if (wi and avg > 0) else None
-            e.update({"bound": "issue", "warp_inst_per_ray": wi, "thr_per_inst": prof["thr_per_inst"] if prof else None, "l2_hit_pct": prof["l2_hit_pct"] if prof else None,
-                      "grays_per_s": upl / (avg * 1e-3) / 1e9 if avg > 0 else 0.0,
-                      "achieved": ach, "peak": issue_peak, "unit": "G warp-inst/s", "frac": (ach / issue_peak) if ach else None,
-                      "dram_gbs": (prof["dram_bytes_per_unit"] * upl / (avg * 1e-3) / 1e9) if (prof and avg > 0) else None})
+            ia = (prof["issue_active_pct"] / 100.0) if (prof and prof.get("issue_active_pct")) else None
+            rate = upl / (avg * 1e-3) / 1e9 if avg > 0 else 0.0                     # Grays/s, measured live (CUDA events)
+            e.update({"bound": "issue", "frac": ia, "achieved": (ia * issue_peak) if ia else None, "peak": issue_peak, "unit": "G warp-inst/s",
+                      "frac_source": "smsp__issue_active.avg.pct_of_peak_sustained_active of the committed ncu capture",
+                      "grays_per_s": rate, "warp_inst_per_ray_profiled": wi, "warp_inst_per_ray_implied_live": (ia * issue_peak / rate) if (ia and rate > 0) else None,
+                      "thr_per_inst": prof["thr_per_inst"] if prof else None, "l2_hit_pct": prof["l2_hit_pct"] if prof else None,
+                      "dram_gbs": (prof["dram_bytes_per_unit"] * rate) if prof else None})
         else:
             ach = upl * bpu / (avg * 1e-3) / 1e9 if avg > 0 else 0.0
             e.update({"bound": "hbm", "bytes_per_unit": bpu, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
@@ -303,7 +309,8 @@ def kernel_table(m, st, workload, integrator, W, H, spp, steps, num_sms=148):
         roof.update({"peak_source": peak_src, "bytes_per_unit": dk["bytes_per_unit"], "frac_measured_bytes": dk["frac_measured_bytes"]})
     else:
         roof.update({"peak_source": f"{num_sms} SMs x {SM_ISSUE_SLOTS} schedulers x {clk_mhz:.0f} MHz (SM clock sampled during the timed region)",
-                     "warp_inst_per_ray": dk["warp_inst_per_ray"], "thr_per_inst": dk["thr_per_inst"], "l2_hit_pct": dk["l2_hit_pct"], "dram_gbs": dk["dram_gbs"],
+                     "frac_source": dk["frac_source"], "grays_per_s": dk["grays_per_s"], "warp_inst_per_ray_profiled": dk["warp_inst_per_ray_profiled"],
+                     "warp_inst_per_ray_implied_live": dk["warp_inst_per_ray_implied_live"], "thr_per_inst": dk["thr_per_inst"], "l2_hit_pct": dk["l2_hit_pct"], "dram_gbs": dk["dram_gbs"],
                      "hbm_peak": peak})
     return kern, roof
 

@@ -10,7 +10,7 @@ python - <<'PY'
 import json
 d = json.loads([l for l in open("gpurun_out/r2x_bench.json") if l.startswith("{")][0])
 print("headline", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), d["roofline"]["kernel"], d["roofline"]["frac"], d["roofline"].get("frac_measured_bytes"))
-for k, v in d["kernels"].items(): print("  ", k, v["bound"], "share", v["share_of_step"], "frac", v["frac"], "winst/ray", v.get("warp_inst_per_ray"), "B/unit", v.get("measured_dram_bytes_per_unit"))
+for k, v in d["kernels"].items(): print("  ", k, v["bound"], "share", v["share_of_step"], "frac", v["frac"], "winst/ray profiled", v.get("warp_inst_per_ray_profiled"), "implied live", v.get("warp_inst_per_ray_implied_live"), "B/unit", v.get("measured_dram_bytes_per_unit"))
 for w in d.get("workloads", []):
     print(w["name"], w["integrator"], w["resolution"], round(w["value"], 1), "SBE", round(w["rays"]["gsamples_sbe_per_s"], 3), "roofline", w["roofline"]["kernel"], w["roofline"]["bound"], w["roofline"]["frac"], "cpu", (w.get("cpu_baseline") or {}).get("value"))
     for k, v in w["kernels"].items(): print("     ", k, v)
