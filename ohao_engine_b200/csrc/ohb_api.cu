@@ -102,7 +102,7 @@ struct ohb_ctx {
     DevBuf blasLo, blasHi, blasInfo, instOfPrim, maxLevels, tlasNodes, tlasLeaves;
     DevBuf tWtri, tPrimLo, tPrimHi, tBounds, tKeys, tVals, tKeysTmp, tValsTmp, tSortTemp, tLeft, tRight, tParentInner, tParentLeaf, tNodeLo, tNodeHi, tVisit, tWideCounters, tItemsA, tItemsB, tSah;
     // paths (device)
-    DevBuf rayO, rayD, hit, thr, rad, pendA, pendB, meta, fh0, fh1, fh2, pay0, pay1, pay2, pay3, shO, shD, queueA, queueB, queueS, hitFlag, sobolTab, smallCounters, devCounters;
+    DevBuf rayO, rayD, hit, thr, rad, pendA, pendB, meta, fh0, fh1, fh2, pay0, pay1, pay2, pay3, shO, shD, queueA, queueB, queueS, hitFlag, sobolTab, smallCounters, devCounters, octPerm, octHist, octScanTmp;
     uint32_t pathCapacity = 0;
     // film
     DevBuf accum, ldr, albedoAOV, normalAOV, sampleDump;
@@ -198,7 +198,7 @@ void ohb_destroy(ohb_ctx* c) {
                      &c->tex, &c->lights, &c->env, &c->marg, &c->cond, &c->rowTotal, &c->integral, &c->activeTris, &c->wtri, &c->primLo, &c->primHi, &c->boundsBits,
                      &c->keys, &c->vals, &c->keysTmp, &c->valsTmp, &c->sortTemp, &c->left, &c->right, &c->parentInner, &c->parentLeaf,
                      &c->nodeLo, &c->nodeHi, &c->visit, &c->wideCounters, &c->wideItemsA, &c->wideItemsB, &c->sah, &c->wnodes, &c->tris, &c->rayO, &c->rayD, &c->hit, &c->thr, &c->rad,
-                     &c->pendA, &c->pendB, &c->meta, &c->fh0, &c->fh1, &c->fh2, &c->pay0, &c->pay1, &c->pay2, &c->pay3, &c->shO, &c->shD, &c->queueA, &c->queueB, &c->queueS, &c->hitFlag, &c->sobolTab, &c->smallCounters, &c->devCounters,
+                     &c->pendA, &c->pendB, &c->meta, &c->fh0, &c->fh1, &c->fh2, &c->pay0, &c->pay1, &c->pay2, &c->pay3, &c->shO, &c->shD, &c->queueA, &c->queueB, &c->queueS, &c->hitFlag, &c->sobolTab, &c->smallCounters, &c->devCounters, &c->octPerm, &c->octHist, &c->octScanTmp,
                      &c->accum, &c->ldr, &c->albedoAOV, &c->normalAOV, &c->sampleDump, &c->hookRays, &c->hookOut, &c->hookAux,
                      &c->accumPrev, &c->surf[0], &c->surf[1], &c->shad[0], &c->shad[1], &c->res[0][0], &c->res[0][1], &c->res[0][2],
                      &c->res[1][0], &c->res[1][1], &c->res[1][2], &c->rtDump[0], &c->rtDump[1], &c->rtDump[2],
@@ -725,6 +725,10 @@ int ensurePaths(ohb_ctx* c, uint32_t cap) {
         CU(c, c->pay0.reserve(n * 16)); CU(c, c->pay1.reserve(n * 16)); CU(c, c->pay2.reserve(n * 16)); CU(c, c->pay3.reserve(n * 16));
     }
     CU(c, c->shO.reserve(n * 32)); CU(c, c->shD.reserve(n * 32)); CU(c, c->queueA.reserve(n * 4)); CU(c, c->queueB.reserve(n * 4)); CU(c, c->queueS.reserve(n * 4)); CU(c, c->hitFlag.reserve(n));
+    {   // octant binning (the visibility-ray queue holds up to 2 rays per path): 4096-entry blocks, 8 bins per block
+        const size_t blocks = (2 * n + 4095) / 4096;
+        CU(c, c->octPerm.reserve(2 * n * 4)); CU(c, c->octHist.reserve(blocks * 8 * 4 + 64)); CU(c, c->octScanTmp.reserve((blocks * 8 / 1024 + 4096) * 4));
+    }
     c->pathCapacity = cap;
     return 0;
 }
@@ -755,6 +759,7 @@ static void fillPaths(ohb_ctx* c, PathArrays& P) {
     P.counters = c->devCounters.as<unsigned long long>();
     P.albedoAOV = c->albedoAOV.as<f4>(); P.normalAOV = c->normalAOV.as<f4>();
     P.sobolTab = c->sobolTab.as<u4>(); P.queueSorted = c->queueS.as<uint32_t>(); P.sortCount = small + 12; P.hitFlag = c->hitFlag.as<uint8_t>();
+    P.octPerm = c->octPerm.as<uint32_t>(); P.octHist = c->octHist.as<uint32_t>(); P.octScanTmp = c->octScanTmp.as<uint32_t>(); P.octBlocks = uint32_t((2 * size_t(c->pathCapacity) + 4095) / 4096);
 }
 int ensurePaths(ohb_ctx* c, uint32_t cap);
 static int ensureSvgf(ohb_ctx* c);

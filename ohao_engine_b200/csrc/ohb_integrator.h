@@ -57,6 +57,10 @@ struct PathArrays {
     uint32_t samplesInBatch;
     uint32_t firstSampleIndex;     // sample index of s = 0
     const u4* sobolTab;            // samplesInBatch entries: sobolQuad(firstSampleIndex + s)
+    // STABLE octant binning of a ray queue before it is traced (k_oct_hist / scan / k_oct_scatter, OHB_OCT_BIN=1): octPerm lists
+    // the queue slots grouped by ray octant, queue order kept inside each group — a warp then holds rays of one octant from
+    // neighbouring paths, which descend the children of a node in the same order.  null = trace in queue order.
+    uint32_t* octPerm; uint32_t* octHist; uint32_t* octScanTmp; uint32_t octBlocks;
 };
 
 struct Payload { f3 color, attenuation, hitPos, hitNormal, hitAlbedo; float hitDist, envPdf; };

@@ -358,7 +358,7 @@ static TraceKnobs traceKnobs() {
 #define OHB_SMEM_STACK 8
 #define OHB_SMEM_TOP 73u
 template <bool ANY, int VAR, class IO, bool TL = false>
-__device__ __forceinline__ void persistentTrace(const SceneDev& sc, uint32_t n, uint32_t* work, IO& io, int minActive, int postponeDen) {
+__device__ __forceinline__ void persistentTrace(const SceneDev& sc, uint32_t n, uint32_t* work, IO& io, int minActive, int postponeDen, const uint32_t* perm = nullptr) {
     const uint32_t lane = threadIdx.x & 31u;
     __shared__ TravStackEntry sStack[(VAR & 1) ? OHB_SMEM_STACK * TRACE_THREADS : 1];
     __shared__ u4 sTop[(VAR & 2) ? OHB_SMEM_TOP * OHB_WNODE_VECS : 1];
@@ -381,7 +381,10 @@ __device__ __forceinline__ void persistentTrace(const SceneDev& sc, uint32_t n, 
             base = __shfl_sync(0xffffffffu, base, __ffs(int(need)) - 1);
             if (!have && !exhausted) {
                 idx = base + uint32_t(__popc(need & ((1u << lane) - 1u)));
-                if (idx < n) { f3 o, d; float tmin, tmax; io.load(idx, o, d, tmin, tmax); travInit(t, sc, o, d, tmin, tmax); have = true; }
+                if (idx < n) {
+                    if (perm) idx = perm[idx];                   // queue slot of the idx-th ray in (octant, queue) order
+                    f3 o, d; float tmin, tmax; io.load(idx, o, d, tmin, tmax); travInit(t, sc, o, d, tmin, tmax); have = true;
+                }
                 else exhausted = true;
             }
         }
@@ -410,7 +413,7 @@ struct PathClosestIO {
 template <int MINB, int VAR>
 __global__ void __launch_bounds__(TRACE_THREADS, MINB) k_trace_closest(SceneDev sc, PathArrays P, uint32_t* work, int minActive, int postponeDen) {
     PathClosestIO io{P, 0u};
-    persistentTrace<false, VAR>(sc, *P.countIn, work, io, minActive, postponeDen);
+    persistentTrace<false, VAR>(sc, *P.countIn, work, io, minActive, postponeDen, P.octPerm);
     uint32_t hits = __reduce_add_sync(0xffffffffu, io.hits);
     if ((threadIdx.x & 31u) == 0 && hits) atomicAdd(P.counters + 3, (unsigned long long)hits);
 }
@@ -429,7 +432,78 @@ struct PathShadowIO {
 template <int MINB, int VAR>
 __global__ void __launch_bounds__(TRACE_THREADS, MINB) k_trace_shadow(SceneDev sc, PathArrays P, uint32_t* work, int minActive, int postponeDen) {
     PathShadowIO io{P};
-    persistentTrace<true, VAR>(sc, *P.shCount, work, io, minActive, postponeDen);
+    persistentTrace<true, VAR>(sc, *P.shCount, work, io, minActive, postponeDen, P.octPerm);
+}
+// ---- stable octant binning of a ray queue (PathArrays::octPerm): one pass of the LSD radix sort above with the ray octant as the
+// digit (8 bins) and the queue slot as the value; the queue length is read on the device, the grid covers the capacity -------------
+#ifndef OHB_OCT_BIN_DEFAULT
+#define OHB_OCT_BIN_DEFAULT 0
+#endif
+__device__ __forceinline__ uint32_t dirOctant(f4 d) {   // == octantOf(prepRay(...)): bit set = the ray travels toward + on that axis
+    return ((__float_as_uint(d.x) >> 31) ? 0u : 4u) | ((__float_as_uint(d.y) >> 31) ? 0u : 2u) | ((__float_as_uint(d.z) >> 31) ? 0u : 1u);
+}
+template <bool SHADOW>
+__device__ __forceinline__ uint32_t queueOctant(const PathArrays& P, uint32_t i) { return dirOctant(SHADOW ? P.shD[i] : P.rayD[OHB_Q_PATH(P.queueIn[i])]); }
+template <bool SHADOW>
+__global__ void __launch_bounds__(RS_THREADS) k_oct_hist(PathArrays P) {
+    __shared__ uint32_t h[8];
+    const uint32_t n = SHADOW ? *P.shCount : *P.countIn;
+    if (threadIdx.x < 8u) h[threadIdx.x] = 0u;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * RS_TILE;
+    if (base < n) {
+        for (uint32_t i = threadIdx.x; i < RS_TILE; i += RS_THREADS) {
+            const uint32_t idx = base + i;
+            const uint32_t oct = idx < n ? queueOctant<SHADOW>(P, idx) : 8u;
+            const unsigned peers = __match_any_sync(0xffffffffu, oct);
+            if (oct < 8u && (threadIdx.x & 31u) == uint32_t(__ffs(int(peers)) - 1)) atomicAdd(&h[oct], uint32_t(__popc(peers)));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 8u) P.octHist[threadIdx.x * P.octBlocks + blockIdx.x] = h[threadIdx.x];
+}
+template <bool SHADOW>
+__global__ void __launch_bounds__(RS_THREADS) k_oct_scatter(PathArrays P) {
+    __shared__ uint32_t wh[RS_WARPS][8];
+    const uint32_t n = SHADOW ? *P.shCount : *P.countIn;
+    if (blockIdx.x * RS_TILE >= n) return;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    if (threadIdx.x < RS_WARPS * 8) (&wh[0][0])[threadIdx.x] = 0u;
+    __syncthreads();
+    const uint32_t chunk = blockIdx.x * RS_TILE + warp * (32u * RS_ROUNDS);
+    uint32_t octs = 0u;                                           // this lane's 16 octants, 4 bits each (8 = past the end)... two words
+    uint32_t octs2 = 0u;
+    for (int r = 0; r < RS_ROUNDS; r++) {
+        const uint32_t idx = chunk + uint32_t(r) * 32u + lane;
+        const uint32_t oct = idx < n ? queueOctant<SHADOW>(P, idx) : 8u;
+        if (r < 8) octs |= oct << (4 * r); else octs2 |= oct << (4 * (r - 8));
+        const unsigned peers = __match_any_sync(0xffffffffu, oct);
+        if (oct < 8u && lane == uint32_t(__ffs(int(peers)) - 1)) wh[warp][oct] += uint32_t(__popc(peers));
+        __syncwarp();
+    }
+    __syncthreads();
+    if (threadIdx.x < 8u) {
+        const uint32_t d = threadIdx.x;
+        uint32_t run = P.octHist[d * P.octBlocks + blockIdx.x];    // exclusive scan of the (octant-major, block-minor) histogram
+        for (int w = 0; w < RS_WARPS; w++) { uint32_t t = wh[w][d]; wh[w][d] = run; run += t; }
+    }
+    __syncthreads();
+    for (int r = 0; r < RS_ROUNDS; r++) {
+        const uint32_t idx = chunk + uint32_t(r) * 32u + lane;
+        const uint32_t oct = r < 8 ? (octs >> (4 * r)) & 15u : (octs2 >> (4 * (r - 8))) & 15u;
+        const unsigned peers = __match_any_sync(0xffffffffu, oct);
+        if (oct < 8u) P.octPerm[wh[warp][oct] + uint32_t(__popc(peers & ((1u << lane) - 1u)))] = idx;
+        __syncwarp();
+        if (oct < 8u && lane == uint32_t(__ffs(int(peers)) - 1)) wh[warp][oct] += uint32_t(__popc(peers));
+        __syncwarp();
+    }
+}
+static bool octBinOn() { static const bool v = []() { const char* e = getenv("OHB_OCT_BIN"); return e ? atoi(e) != 0 : OHB_OCT_BIN_DEFAULT != 0; }(); return v; }
+template <bool SHADOW>
+static void launchOctBin(const PathArrays& P, cudaStream_t st, uint64_t* launches) {
+    k_oct_hist<SHADOW><<<P.octBlocks, RS_THREADS, 0, st>>>(P); (*launches)++;
+    exclusiveScanU32(P.octHist, 8u * P.octBlocks, P.octScanTmp, st, launches);
+    k_oct_scatter<SHADOW><<<P.octBlocks, RS_THREADS, 0, st>>>(P); (*launches)++;
 }
 // two-level variants (ohb_set_accel_mode(OHB_ACCEL_TWO_LEVEL)): the same persistent loop, travRun with the instance descent
 __global__ void __launch_bounds__(TRACE_THREADS, 6) k_trace_closest_tl(SceneDev sc, PathArrays P, uint32_t* work, int minActive, int postponeDen) {
@@ -645,9 +719,12 @@ void launchOfflineBatch(const SceneDev& sc, const FrameParams& fr, PathArrays P,
     unsigned shadeGrid = unsigned(numSMs) * 8u;
     uint32_t iters = 1u + 2u * fr.maxBounces;
     static const int bounceOcc = []() { const char* e = getenv("OHB_BOUNCE_OCC"); return e ? atoi(e) : 8; }();
+    const bool bin = octBinOn() && !sc.twoLevel && P.octPerm != nullptr;
+    if (!bin) P.octPerm = nullptr;
     static const int shadePf = []() { const char* e = getenv("OHB_SHADE_PREFETCH"); int v = e ? atoi(e) : OHB_SHADE_PREFETCH_DEFAULT; return v < 0 ? 0 : (v > 2 ? 2 : v); }();
     for (uint32_t it = 0; it < iters; it++) {
         if (th) th->begin(0, st);
+        if (bin) launchOctBin<false>(P, st, launches);
         launchTraceClosest(traceGrid, sc, P, work, st);
         if (th) th->end(0, st);
         if (th) th->begin(7, st);
@@ -656,6 +733,7 @@ void launchOfflineBatch(const SceneDev& sc, const FrameParams& fr, PathArrays P,
         if (bounceOcc >= 8) k_shade<8><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P, shadePf); else k_shade<6><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P, shadePf);
         if (th) th->end(1, st);
         if (th) th->begin(2, st);
+        if (bin) launchOctBin<true>(P, st, launches);
         launchTraceShadow(traceGrid, sc, P, work + 1, st);
         if (th) th->end(2, st);
         k_advance<<<1, 32, 0, st>>>(P, work, 0);
@@ -702,9 +780,12 @@ void launchRealtimeFrame(const SceneDev& sc, const FrameParams& fr, PathArrays P
     k_advance<<<1, 32, 0, st>>>(P, work, 1);
     *launches += 5;
     unsigned grid = unsigned(numSMs) * 8u;
+    const bool bin = octBinOn() && !sc.twoLevel && P.octPerm != nullptr;
+    if (!bin) P.octPerm = nullptr;
     uint32_t iters = 2u + fr.maxBounces;          // primary + chain B + the ReSTIR GI bounce
     for (uint32_t it = 0; it < iters; it++) {
         if (th) th->begin(0, st);
+        if (bin) launchOctBin<false>(P, st, launches);
         launchTraceClosest(grid, sc, P, work, st);
         if (th) th->end(0, st);
         if (th) th->begin(7, st);
@@ -716,6 +797,7 @@ void launchRealtimeFrame(const SceneDev& sc, const FrameParams& fr, PathArrays P
         k_bounce_rt<<<grid, SHADE_THREADS, 0, st>>>(sc, fr, P);
         if (th) th->end(1, st);
         if (th) th->begin(2, st);
+        if (bin) launchOctBin<true>(P, st, launches);
         launchTraceShadow(grid, sc, P, work + 1, st);
         if (th) th->end(2, st);
         k_advance<<<1, 32, 0, st>>>(P, work, 0);
