@@ -94,7 +94,8 @@ struct ohb_ctx {
     std::vector<BuilderSet> blasSets;        // extra builder scratch + streams for concurrent BLAS builds (set 0 = the context's own buffers and stream)
     ohb_accel_stats stats{};
     // scene (device)
-    DevBuf positions, indices, normals, uvs, matIds, triInst, instXform, instNormalMat, instInv, matColors, tex, lights, env, marg, cond, rowTotal, integral;
+    DevBuf positions, indices, normals, uvs, matIds, triInst, instXform, instNormalMat, instInv, matColors, tex, lights, env, marg, cond, rowTotal, integral, margTop, condTop;
+    bool envTops = false;
     // accel (device)
     DevBuf activeTris, wtri, primLo, primHi, boundsBits, keys, vals, keysTmp, valsTmp, sortTemp, left, right, parentInner, parentLeaf,
            nodeLo, nodeHi, visit, wideCounters, wideItemsA, wideItemsB, sah, wnodes, tris;
@@ -195,7 +196,7 @@ void ohb_destroy(ohb_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf* all[] = {&c->positions, &c->indices, &c->normals, &c->uvs, &c->matIds, &c->triInst, &c->instXform, &c->instNormalMat, &c->instInv, &c->matColors,
-                     &c->tex, &c->lights, &c->env, &c->marg, &c->cond, &c->rowTotal, &c->integral, &c->activeTris, &c->wtri, &c->primLo, &c->primHi, &c->boundsBits,
+                     &c->tex, &c->lights, &c->env, &c->marg, &c->cond, &c->rowTotal, &c->integral, &c->margTop, &c->condTop, &c->activeTris, &c->wtri, &c->primLo, &c->primHi, &c->boundsBits,
                      &c->keys, &c->vals, &c->keysTmp, &c->valsTmp, &c->sortTemp, &c->left, &c->right, &c->parentInner, &c->parentLeaf,
                      &c->nodeLo, &c->nodeHi, &c->visit, &c->wideCounters, &c->wideItemsA, &c->wideItemsB, &c->sah, &c->wnodes, &c->tris, &c->rayO, &c->rayD, &c->hit, &c->thr, &c->rad,
                      &c->pendA, &c->pendB, &c->meta, &c->fh0, &c->fh1, &c->fh2, &c->pay0, &c->pay1, &c->pay2, &c->pay3, &c->shO, &c->shD, &c->queueA, &c->queueB, &c->queueS, &c->hitFlag, &c->sobolTab, &c->smallCounters, &c->devCounters, &c->octPerm, &c->octHist, &c->octScanTmp,
@@ -305,7 +306,11 @@ int ohb_set_env(ohb_ctx* c, const float* rgba, uint32_t w, uint32_t h) {
     size_t n = size_t(w) * h;
     CU(c, c->env.reserve(n * 16)); CU(c, c->cond.reserve(n * 4)); CU(c, c->marg.reserve(size_t(h) * 4)); CU(c, c->rowTotal.reserve(size_t(h) * 4)); CU(c, c->integral.reserve(4));
     CU(c, cudaMemcpyAsync(c->env.p, rgba, n * 16, cudaMemcpyHostToDevice, c->stream));
-    launchEnvCdf(c->env.as<f4>(), w, h, c->cond.as<float>(), c->marg.as<float>(), c->rowTotal.as<float>(), c->integral.as<float>(), c->stream, &c->launches);
+    static const bool blockedOn = []() { const char* e = getenv("OHB_ENV_BLOCKED"); return e ? atoi(e) != 0 : true; }();
+    c->envTops = blockedOn && (w % 32u) == 0u && (h % 32u) == 0u;      // the blocked CDF search needs whole 32-entry blocks
+    if (c->envTops) { CU(c, c->condTop.reserve(size_t(h) * (w / 32) * 4)); CU(c, c->margTop.reserve(size_t(h / 32) * 4)); }
+    launchEnvCdf(c->env.as<f4>(), w, h, c->cond.as<float>(), c->marg.as<float>(), c->rowTotal.as<float>(), c->integral.as<float>(),
+                 c->envTops ? c->condTop.as<float>() : nullptr, c->envTops ? c->margTop.as<float>() : nullptr, c->stream, &c->launches);
     CU(c, cudaMemcpyAsync(&c->envIntegral, c->integral.p, 4, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     c->envW = w; c->envH = h;
@@ -336,6 +341,7 @@ static void fillScene(ohb_ctx* c, SceneDev& s) {
     s.lights = c->lights.as<GPULight>(); s.lightCount = c->lightCount; s.envMapTexIdx = c->envMapTexIdx; s.envIntensity = c->envIntensity;
     s.env = c->envW ? c->env.as<f4>() : nullptr; s.envW = c->envW; s.envH = c->envH;
     s.marg = c->marg.as<float>(); s.cond = c->cond.as<float>(); s.envIntegral = c->envIntegral;
+    s.margTop = (c->envW && c->envTops) ? c->margTop.as<float>() : nullptr; s.condTop = (c->envW && c->envTops) ? c->condTop.as<float>() : nullptr;
     if (!c->envW) s.envMapTexIdx = 0xFFFFFFFFu;
 }
 

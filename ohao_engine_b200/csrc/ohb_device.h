@@ -40,7 +40,7 @@ void launchBuildBlas(const BuildArrays& b, uint64_t* keysTmp, uint32_t* valsTmp,
                      f4* blasLo, f4* blasHi, uint32_t inst, uint32_t* maxLevels, cudaStream_t st, uint64_t* launches);
 void launchBuildTlas(const BuildArrays& b, const f4* blasLo, const f4* blasHi, const uint32_t* instOfPrim, bool refit, uint64_t* keysTmp, uint32_t* valsTmp, uint32_t* sortTemp,
                      WideItem* itemsA, WideItem* itemsB, cudaStream_t st, uint64_t* launches);
-void launchEnvCdf(const f4* env, uint32_t W, uint32_t H, float* cond, float* marg, float* rowTotal, float* integral, cudaStream_t st, uint64_t* launches);
+void launchEnvCdf(const f4* env, uint32_t W, uint32_t H, float* cond, float* marg, float* rowTotal, float* integral, float* condTop, float* margTop, cudaStream_t st, uint64_t* launches);
 void launchEnvSample(const SceneDev& sc, const float* u12, uint32_t n, f4* dirPdf, float* pdfOfDir, cudaStream_t st, uint64_t* launches);
 void launchHybridShadow(const SceneDev& sc, const HybridShadowParams& pc, const f4* gPos, const f2* gNrm, uint8_t* mask, cudaStream_t st, uint64_t* launches);
 void launchHybridGi(const SceneDev& sc, const HybridGiParams& pc, const f4* gPos, const f2* gNrm, const f4* gAlbedo, const f4* history, const f4* instMat, h4* out, cudaStream_t st, uint64_t* launches);

@@ -436,9 +436,13 @@ OHB_HD f3 sampleSpecDir(ShadeCtx& cx, f3 d, f3 N, float rough) {
 
 // The raygen's per-bounce body for the path of queue entry e, given the payload (q0..q3) of its last query.
 // Returns the path's next queue entry, or OHB_Q_NONE if it traces no further closest-hit ray.
+// PRIM: 1 = every entry of this launch is a camera ray (iteration 0 of a wavefront), 0 = none is (later iterations), 2 = read
+// the queue flag.  The stage-specialised bodies drop the other stage's code (AOV writes, first-hit record, anisotropic GGX
+// vs Russian roulette, lobe selection, chain bookkeeping) from kernels whose size is a first-class cost.
+template <int PRIM = 2>
 OHB_HD uint32_t bounceBody(const SceneDev& sc, const FrameParams& fr, const PathArrays& P, uint32_t e, f4 q0, f4 q1, f4 q2, f4 q3) {
     const uint32_t p = OHB_Q_PATH(e);
-    const bool isMiss = (e & OHB_Q_MISS) != 0u, primary = (e & OHB_Q_PRIMARY) != 0u;
+    const bool isMiss = (e & OHB_Q_MISS) != 0u, primary = PRIM == 2 ? (e & OHB_Q_PRIMARY) != 0u : PRIM == 1;
     // every load of the path record is issued here, before the first use
     const u4 m = P.meta[p];
     const f4 rad4 = P.rad[p], d4 = P.rayD[p];
@@ -567,10 +571,11 @@ OHB_HD uint32_t bounceBody(const SceneDev& sc, const FrameParams& fr, const Path
     return p | ((keep & OHB_ST_PEND_A) ? OHB_Q_PEND_A : 0u) | ((keep & OHB_ST_PEND_B) ? OHB_Q_PEND_B : 0u);
 }
 // k_shade: both shading stages in one kernel, the payload stays in registers (no 64-B payload round trip through HBM).
+template <int PRIM = 2>
 OHB_HD uint32_t shadePath(const SceneDev& sc, const FrameParams& fr, const PathArrays& P, uint32_t e) {
     f4 q0, q1, q2, q3;
     const bool hit = surfaceShade(sc, fr, P, OHB_Q_PATH(e), q0, q1, q2, q3);
-    return bounceBody(sc, fr, P, hit ? e : (e | OHB_Q_MISS), q0, q1, q2, q3);
+    return bounceBody<PRIM>(sc, fr, P, hit ? e : (e | OHB_Q_MISS), q0, q1, q2, q3);
 }
 
 // ---------------------------------------------------------------------------------------------

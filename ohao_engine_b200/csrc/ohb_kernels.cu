@@ -276,10 +276,17 @@ __global__ void k_env_marginal(const float* rowTotal, uint32_t H, float* marg, f
     if (total > 0.0f) for (uint32_t y = 0; y < H; y++) marg[y] = __fdiv_rn(marg[y], total);
     else              for (uint32_t y = 0; y < H; y++) marg[y] = float(y + 1) / float(H);
 }
-void launchEnvCdf(const f4* env, uint32_t W, uint32_t H, float* cond, float* marg, float* rowTotal, float* integral, cudaStream_t st, uint64_t* launches) {
+// compact tables for cdfLowerBoundBlocked: every 32nd entry of the marginal and of each conditional row
+__global__ void k_env_tops(const float* cond, const float* marg, uint32_t W, uint32_t H, float* condTop, float* margTop) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, wb = W >> 5, hb = H >> 5;
+    if (i < H * wb) { const uint32_t y = i / wb, b = i % wb; condTop[i] = cond[size_t(y) * W + (b << 5) + 31u]; }
+    if (i < hb) margTop[i] = marg[(i << 5) + 31u];
+}
+void launchEnvCdf(const f4* env, uint32_t W, uint32_t H, float* cond, float* marg, float* rowTotal, float* integral, float* condTop, float* margTop, cudaStream_t st, uint64_t* launches) {
     k_env_rows<<<gridFor(H, 64), 64, 0, st>>>(env, W, H, cond, rowTotal);
     k_env_marginal<<<1, 32, 0, st>>>(rowTotal, H, marg, integral);
     *launches += 2;
+    if (condTop) { k_env_tops<<<gridFor(uint64_t(H) * (W >> 5), 128), 128, 0, st>>>(cond, marg, W, H, condTop, margTop); (*launches)++; }
 }
 __global__ void k_env_sample(SceneDev sc, const float* u12, uint32_t n, f4* dirPdf, float* pdfOfDir) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -646,8 +653,11 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_surface(SceneDev sc, FramePar
 __device__ __forceinline__ void shadePrefetch(const void* p, int pf) {
     if (pf == 2) asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); else asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
 }
-template <int MINB>
+// LEAN: the frame uses the Sobol sampler, no anisotropy, no subsurface term (every reference preset) — known at launch, folded at
+// compile time so the PCG / anisotropic-GGX / SSS code leaves the kernel
+template <int MINB, int PRIM, bool LEAN = false>
 __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(SceneDev sc, FrameParams fr, PathArrays P, int pf) {
+    if (LEAN) { fr.samplerType = OHB_SAMPLER_SOBOL; fr.aniso = 0.0f; fr.anisoRot = 0.0f; fr.sss = 0.0f; }
     OHB_TILE_EMIT(q);
     const uint32_t n = *P.countIn;
     for (uint32_t tile = blockIdx.x * QTILE; tile < n; tile += gridDim.x * QTILE) {
@@ -674,7 +684,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, MINB) k_shade(SceneDev sc, Fram
                 }
             }
             uint32_t e = OHB_Q_NONE;
-            if (eCur != OHB_Q_NONE) e = shadePath(sc, fr, P, eCur);
+            if (eCur != OHB_Q_NONE) e = shadePath<PRIM>(sc, fr, P, eCur);
             if (pf && primN != OHB_MISS) { shadePrefetch(sc.indices + size_t(primN) * 3u, pf); shadePrefetch(sc.triInst + primN, pf); shadePrefetch(sc.matIds + primN, pf); }
             q.round(e != OHB_Q_NONE, e);
         }
@@ -721,6 +731,9 @@ void launchOfflineBatch(const SceneDev& sc, const FrameParams& fr, PathArrays P,
     static const int bounceOcc = []() { const char* e = getenv("OHB_BOUNCE_OCC"); return e ? atoi(e) : 8; }();
     const bool bin = octBinOn() && !sc.twoLevel && P.octPerm != nullptr;
     if (!bin) P.octPerm = nullptr;
+    static const bool leanOn = []() { const char* e = getenv("OHB_SHADE_LEAN"); return e ? atoi(e) != 0 : true; }();
+    const bool lean = leanOn && fr.samplerType == OHB_SAMPLER_SOBOL && fr.aniso == 0.0f && fr.sss == 0.0f;
+    static const bool shadeStages = []() { const char* e = getenv("OHB_SHADE_STAGES"); return e ? atoi(e) != 0 : true; }();
     static const int shadePf = []() { const char* e = getenv("OHB_SHADE_PREFETCH"); int v = e ? atoi(e) : OHB_SHADE_PREFETCH_DEFAULT; return v < 0 ? 0 : (v > 2 ? 2 : v); }();
     for (uint32_t it = 0; it < iters; it++) {
         if (th) th->begin(0, st);
@@ -730,7 +743,11 @@ void launchOfflineBatch(const SceneDev& sc, const FrameParams& fr, PathArrays P,
         if (th) th->begin(7, st);
         k_sort_hits<<<shadeGrid, SHADE_THREADS, 0, st>>>(P);
         if (th) { th->end(7, st); th->begin(1, st); }
-        if (bounceOcc >= 8) k_shade<8><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P, shadePf); else k_shade<6><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P, shadePf);
+        // stage-specialised bodies: iteration 0 shades camera rays only, every later iteration none (OHB_SHADE_STAGES=0: one generic body)
+        if (!shadeStages) { if (bounceOcc >= 8) k_shade<8, 2><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P, shadePf); else k_shade<6, 2><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P, shadePf); }
+        else if (lean && bounceOcc >= 8) { if (it == 0) k_shade<8, 1, true><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P, shadePf); else k_shade<8, 0, true><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P, shadePf); }
+        else if (it == 0) { if (bounceOcc >= 8) k_shade<8, 1><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P, shadePf); else k_shade<6, 1><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P, shadePf); }
+        else { if (bounceOcc >= 8) k_shade<8, 0><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P, shadePf); else k_shade<6, 0><<<shadeGrid, SHADE_THREADS, 0, st>>>(sc, fr, P, shadePf); }
         if (th) th->end(1, st);
         if (th) th->begin(2, st);
         if (bin) launchOctBin<true>(P, st, launches);

@@ -40,7 +40,7 @@ struct EmulScene {
     std::vector<f2> uvs;
     std::vector<uint8_t> tex; uint32_t texW = 0, texH = 0, texLayers = 0;
     std::vector<GPULight> lights; uint32_t lightCount = 0, envMapTexIdx = 0xFFFFFFFFu; float envIntensity = 1.0f;
-    uint32_t envW = 0, envH = 0; std::vector<float> marg, cond; float envIntegral = 0;
+    uint32_t envW = 0, envH = 0; std::vector<float> marg, cond, margTop, condTop; float envIntegral = 0;
     std::vector<u4> wnodes; std::vector<f4> tris; uint32_t numActive = 0, numNodes = 0, levels = 0; float sah = 0;
     // two-level structure + what MODE_UPDATE needs
     std::vector<ohb_instance> instances; int accelMode = 0;
@@ -56,6 +56,7 @@ struct EmulScene {
         s.tex = tex.data(); s.texW = texW; s.texH = texH; s.texLayers = texLayers;
         s.lights = lights.data(); s.lightCount = lightCount; s.envMapTexIdx = envW ? envMapTexIdx : 0xFFFFFFFFu; s.envIntensity = envIntensity;
         s.env = envW ? env.data() : nullptr; s.envW = envW; s.envH = envH; s.marg = marg.data(); s.cond = cond.data(); s.envIntegral = envIntegral;
+        s.margTop = condTop.empty() ? nullptr : margTop.data(); s.condTop = condTop.empty() ? nullptr : condTop.data();
         return s;
     }
 };
@@ -234,6 +235,12 @@ void* emul_scene_create(const emul_scene_desc* d) {
     if (d->env && d->env_w) {
         s->envW = d->env_w; s->envH = d->env_h; s->env.resize(size_t(d->env_w) * d->env_h); memcpy(s->env.data(), d->env, s->env.size() * 16);
         s->marg.assign(d->marg, d->marg + d->env_h); s->cond.assign(d->cond, d->cond + size_t(d->env_w) * d->env_h); s->envIntegral = d->env_integral;
+        if (d->env_w % 32u == 0u && d->env_h % 32u == 0u && !getenv("OHB_ENV_BLOCKED_OFF")) {      // k_env_tops
+            const uint32_t wb = d->env_w >> 5, hb = d->env_h >> 5;
+            s->condTop.resize(size_t(d->env_h) * wb); s->margTop.resize(hb);
+            for (uint32_t y = 0; y < d->env_h; y++) for (uint32_t b = 0; b < wb; b++) s->condTop[size_t(y) * wb + b] = s->cond[size_t(y) * d->env_w + (b << 5) + 31u];
+            for (uint32_t b = 0; b < hb; b++) s->margTop[b] = s->marg[(b << 5) + 31u];
+        }
     } else { s->marg.assign(1, 1.0f); s->cond.assign(1, 1.0f); }
     s->instances.assign(d->instances, d->instances + d->ninstances);
     emulBuildAccel(s);
