@@ -766,6 +766,7 @@ void launchOfflineBatch(const SceneDev& sc, const FrameParams& fr, PathArrays P,
 // =============================================================================================
 // Realtime profile: one frame = N-spp wavefront + per-pixel ReSTIR GI / EMA + a-trous (ohb_realtime.h)
 // =============================================================================================
+template <bool FUSED>
 __global__ void __launch_bounds__(SHADE_THREADS, 8) k_bounce_rt(SceneDev sc, FrameParams fr, PathArrays P) {
     OHB_TILE_EMIT(q);
     const uint32_t n = *P.countIn;
@@ -774,7 +775,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, 8) k_bounce_rt(SceneDev sc, Fra
         for (int r = 0; r < QTILE_ROUNDS; r++) {
             const uint32_t i = tile + uint32_t(r) * SHADE_THREADS + threadIdx.x;
             uint32_t p = 0u; bool keep = false;
-            if (i < n) { p = OHB_Q_PATH(P.queueSorted[i]); keep = bouncePathRT(sc, fr, P, p); }
+            if (i < n) { p = OHB_Q_PATH(P.queueSorted[i]); keep = bouncePathRT<FUSED>(sc, fr, P, p); }
             q.round(keep, p);
         }
         q.flush(P.countOut, P.queueOut, true, 0u);
@@ -799,6 +800,7 @@ void launchRealtimeFrame(const SceneDev& sc, const FrameParams& fr, PathArrays P
     unsigned grid = unsigned(numSMs) * 8u;
     const bool bin = octBinOn() && !sc.twoLevel && P.octPerm != nullptr;
     if (!bin) P.octPerm = nullptr;
+    static const bool rtFused = []() { const char* e = getenv("OHB_RT_FUSED"); return e ? atoi(e) != 0 : true; }();
     uint32_t iters = 2u + fr.maxBounces;          // primary + chain B + the ReSTIR GI bounce
     for (uint32_t it = 0; it < iters; it++) {
         if (th) th->begin(0, st);
@@ -807,12 +809,19 @@ void launchRealtimeFrame(const SceneDev& sc, const FrameParams& fr, PathArrays P
         if (th) th->end(0, st);
         if (th) th->begin(7, st);
         k_sort_hits<<<grid, SHADE_THREADS, 0, st>>>(P); (*launches)++;
-        if (th) { th->end(7, st); th->begin(4, st); }
-        k_surface<<<grid, SHADE_THREADS, 0, st>>>(sc, fr, P);
-        if (th) th->end(4, st);
-        if (th) th->begin(1, st);
-        k_bounce_rt<<<grid, SHADE_THREADS, 0, st>>>(sc, fr, P);
-        if (th) th->end(1, st);
+        if (th) th->end(7, st);
+        if (rtFused) {          // closest-hit / miss shaders + the realtime raygen body in one kernel, the payload in registers
+            if (th) th->begin(1, st);
+            k_bounce_rt<true><<<grid, SHADE_THREADS, 0, st>>>(sc, fr, P); (*launches)--;
+            if (th) th->end(1, st);
+        } else {
+            if (th) th->begin(4, st);
+            k_surface<<<grid, SHADE_THREADS, 0, st>>>(sc, fr, P);
+            if (th) th->end(4, st);
+            if (th) th->begin(1, st);
+            k_bounce_rt<false><<<grid, SHADE_THREADS, 0, st>>>(sc, fr, P);
+            if (th) th->end(1, st);
+        }
         if (th) th->begin(2, st);
         if (bin) launchOctBin<true>(P, st, launches);
         launchTraceShadow(grid, sc, P, work + 1, st);

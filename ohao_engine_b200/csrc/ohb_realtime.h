@@ -142,6 +142,10 @@ OHB_HD void raygenPathRT(const FrameParams& fr, const PathArrays& P, uint32_t p)
 }
 
 // k_bounce_rt: per-bounce body of the realtime raygen for path p (after k_surface).  Returns true if the path traces again.
+// FUSED: the closest-hit / miss shader runs here and its 64-B payload stays in registers (k_shade_rt), like the offline k_shade;
+// only the payload pixelRT reads later — the ReSTIR GI sample's (x_s, n_s, Lo) — still goes to memory.  FUSED = false: the payload
+// was written by k_surface (host emulator, A/B).
+template <bool FUSED = false>
 OHB_HD bool bouncePathRT(const SceneDev& sc, const FrameParams& fr, const PathArrays& P, uint32_t p) {
     ShadeCtx cx(sc, fr, P);
     u4 m = P.meta[p];
@@ -156,7 +160,9 @@ OHB_HD bool bouncePathRT(const SceneDev& sc, const FrameParams& fr, const PathAr
     uint32_t stage = OHB_ST_STAGE(cx.state), bounce = OHB_ST_BOUNCE(cx.state);
     const bool primary = (stage == ST_PRIMARY);
     f3 d = xyz(P.rayD[p]);
-    f4 q0 = P.pay0[p], q1 = P.pay1[p];
+    f4 q0, q1, q2, q3;
+    if (FUSED) surfaceShade(sc, fr, P, p, q0, q1, q2, q3);
+    else { q0 = P.pay0[p]; q1 = P.pay1[p]; }
     const bool isMiss = q0.w < 0.0f;
     const bool legacy = (fr.flags & OHB_FLAG_RESTIRGI_LEGACY) != 0u;
 
@@ -166,9 +172,10 @@ OHB_HD bool bouncePathRT(const SceneDev& sc, const FrameParams& fr, const PathAr
 
     if (stage == ST_GI) {
         // ---- ReSTIR GI initial sample at x_s (:1377-1531); the RIS update itself happens in pixelRT, in sample order ----
+        if (FUSED) { P.pay0[p] = q0; P.pay1[p] = q1; if (!isMiss) P.pay3[p] = q3; }      // what pixelRT reads of the GI sample
         if (isMiss) doneFlags = OHB_ST_GI_MISS;
         else {
-            f4 q2 = P.pay2[p];
+            if (!FUSED) q2 = P.pay2[p];
             f3 xs = xyz(q0), ns = xyz(q1), sAlbedo = xyz(q2);
             float sPacked = q1.w;
             bool sIsMetal = sPacked < 0.0f;                                   // legacy encoding, always false today (quirk Q6)
@@ -196,7 +203,7 @@ OHB_HD bool bouncePathRT(const SceneDev& sc, const FrameParams& fr, const PathAr
             chainEnds = true;
         }
     } else {
-        f4 q2 = P.pay2[p], q3 = P.pay3[p];
+        if (!FUSED) { q2 = P.pay2[p]; q3 = P.pay3[p]; }
         f3 hp = xyz(q0), N = xyz(q1), albedo = xyz(q2), em = xyz(q3);
         float rough, metal; unpackHitPbr(mk3(q1.w, q2.w, q3.w), rough, metal);
         f3 F0 = mix(mk3(0.04f), albedo, metal);
