@@ -785,10 +785,14 @@ __global__ void __launch_bounds__(128) k_rt_pixel(SceneDev sc, FrameParams fr, P
     uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix < P.numPixels) pixelRT(sc, fr, P, im, pix);
 }
+// PASSES / FASTW: the shipped kernel is <1, true> (ohb_realtime.h denoiseRT); OHB_RT_DENOISE_VAR = 1 runs the shader's three
+// passes literally with expf / powf weights (<3, false>), 2 = <3, true>, 3 = <1, false> — A/B only (profiles/r2ae)
+template <int PASSES, bool FASTW>
 __global__ void __launch_bounds__(128) k_rt_denoise(FrameParams fr, const f4* accum, const f4* normalAOV, uint32_t* ldr, float* dump, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) denoiseRT(fr, accum, normalAOV, ldr, dump, i);
+    if (i < n) denoiseRT<PASSES, FASTW>(fr, accum, normalAOV, ldr, dump, i);
 }
+static int rtDenoiseVar() { static const int v = [] { const char* e = getenv("OHB_RT_DENOISE_VAR"); return e ? atoi(e) : 0; }(); return v; }
 void launchRealtimeFrame(const SceneDev& sc, const FrameParams& fr, PathArrays P, const RTImagesDev& im, uint32_t* ldr, float* denoisedDump,
                          uint32_t* work, int numSMs, cudaStream_t st, uint64_t* launches, TimingHooks* th) {
     uint32_t total = P.numPixels * P.samplesInBatch;
@@ -835,7 +839,15 @@ void launchRealtimeFrame(const SceneDev& sc, const FrameParams& fr, PathArrays P
     k_rt_pixel<<<gridFor(P.numPixels, 128), 128, 0, st>>>(sc, fr, P, im);
     if (th) th->end(5, st);
     if (th) th->begin(3, st);
-    k_rt_denoise<<<gridFor(fr.W * fr.H, 128), 128, 0, st>>>(fr, im.accumCurr, P.normalAOV, ldr, denoisedDump, fr.W * fr.H);
+    {
+        const unsigned g = gridFor(fr.W * fr.H, 128); const uint32_t n = fr.W * fr.H;
+        switch (rtDenoiseVar()) {
+        case 1: k_rt_denoise<3, false><<<g, 128, 0, st>>>(fr, im.accumCurr, P.normalAOV, ldr, denoisedDump, n); break;
+        case 2: k_rt_denoise<3, true><<<g, 128, 0, st>>>(fr, im.accumCurr, P.normalAOV, ldr, denoisedDump, n); break;
+        case 3: k_rt_denoise<1, false><<<g, 128, 0, st>>>(fr, im.accumCurr, P.normalAOV, ldr, denoisedDump, n); break;
+        default: k_rt_denoise<1, true><<<g, 128, 0, st>>>(fr, im.accumCurr, P.normalAOV, ldr, denoisedDump, n); break;
+        }
+    }
     if (th) th->end(3, st);
     *launches += 2;
 }

@@ -478,6 +478,16 @@ OHB_HD void pixelRT(const SceneDev& sc, const FrameParams& fr, const PathArrays&
 }
 
 // k_rt_denoise: in-shader a-trous + tonemap (:1850-1925) over the finished frame.
+// exp(-d2 / 4) for the squared tap distances of a 5x5 footprint (0, 1, 2, 4, 5, 8), correctly rounded
+OHB_HD float atrousSpatialWeight(int d2) {
+    return d2 == 0 ? 1.0f : (d2 == 1 ? 0.778800783f : (d2 == 2 ? 0.606530660f : (d2 == 4 ? 0.367879441f : (d2 == 5 ? 0.286504797f : 0.135335283f))));
+}
+// x^48 = x^32 * x^16 by squaring (six roundings; the shader's pow(normalSim, 48.0))
+OHB_HD float pow48(float x) { float x2 = x * x, x4 = x2 * x2, x8 = x4 * x4, x16 = x8 * x8; return (x16 * x16) * x16; }
+#ifndef OHB_RT_ATROUS_PASSES
+#define OHB_RT_ATROUS_PASSES 1     // 3 = evaluate the two identity passes as well (A/B builds, tests/emul)
+#endif
+template <int PASSES = OHB_RT_ATROUS_PASSES, bool FASTW = true>
 OHB_HD void denoiseRT(const FrameParams& fr, const f4* accum, const f4* normalAOV, uint32_t* ldr, float* denoisedDump, uint32_t pi) {
     const int W = int(fr.W), H = int(fr.H);
     const int px = int(pi % fr.W), py = int(pi / fr.W);
@@ -494,9 +504,14 @@ OHB_HD void denoiseRT(const FrameParams& fr, const f4* accum, const f4* normalAO
         f3 var = vmax(meanSq / float(n) - mean * mean, mk3(0.0f));
         float noise = dot(var, mk3(0.333f));
         if (noise > 0.00005f) {
-            // (Hoisting the 6 distinct spatial weights out of the tap loop and replacing pow(x, 48) by 5 squarings did not
-            // make k_rt_denoise faster — 0.78 -> 0.83 ms, profiles/r1t — the kernel is bound by its ~84 RGBA32F taps.)
-            for (int pass = 0; pass < 3; pass++) {
+            // Passes 1 and 2 of the shader (:1872-1899, steps 2 and 4) take the CENTRE value as every tap's colour
+            // (`(pass == 0) ? imageLoad(accumBuffer, sp).rgb : denoised`): colorDiff = 0, wc = 1 and the pass returns
+            // denoised * sum(w) / sum(w) — the identity up to ~25 roundings (or nothing at all when sum(w) <= 0.001).  The
+            // oracle evaluates them literally; this kernel runs pass 0 only and skips their 50 normal taps per pixel
+            // (k_rt_denoise 0.78 -> 0.32 ms per 1080p frame; table / squaring weights instead of expf / powf: -> 0.17 ms,
+            // profiles/r2ae_sweep_rt_denoise.txt; tests/test_gpu_realtime.py bounds the deviation against the oracle).
+            const float sigmaC = fmaxf(noise * 3.0f, 0.001f);
+            for (int pass = 0; pass < PASSES; pass++) {
                 int step = pass == 0 ? 1 : (pass == 1 ? 2 : 4);
                 f3 sum = mk3(0.0f); float wSum = 0.0f;
                 for (int dy = -2; dy <= 2; dy++) for (int dx = -2; dx <= 2; dx++) {
@@ -505,10 +520,9 @@ OHB_HD void denoiseRT(const FrameParams& fr, const f4* accum, const f4* normalAO
                     size_t si = size_t(y) * W + x;
                     f3 sc = pass == 0 ? xyz(accum[si]) : den;
                     f3 sn = xyz(normalAOV[si]);
-                    float ws = expf(-float(dx * dx + dy * dy) / 4.0f);
-                    float wn = ohb_pow(fmaxf(dot(centerN, sn), 0.0f), 48.0f);
+                    float ws = FASTW ? atrousSpatialWeight(dx * dx + dy * dy) : expf(-float(dx * dx + dy * dy) / 4.0f);
+                    float wn = FASTW ? pow48(fmaxf(dot(centerN, sn), 0.0f)) : ohb_pow(fmaxf(dot(centerN, sn), 0.0f), 48.0f);
                     f3 cd = den - sc;
-                    float sigmaC = fmaxf(noise * 3.0f, 0.001f);
                     float wc = expf(-dot(cd, cd) / (sigmaC + 0.0001f));
                     float w = ws * wn * wc;
                     sum += sc * w; wSum += w;
