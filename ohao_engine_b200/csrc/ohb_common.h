@@ -86,6 +86,28 @@ OHB_HD f3 reflect(f3 I, f3 N) { return I - N * (2.0f * dot(N, I)); }
 #endif
 OHB_SHARED_FN float ohb_sin(float x) { return sinf(x); }
 OHB_SHARED_FN float ohb_cos(float x) { return cosf(x); }
+// sin and cos of one angle.  OHB_TRIG_MODE 0: sinf + cosf, two argument reductions; 1: sincosf, one reduction, the values
+// sinf / cosf return; 2 (ohb_sincos_turns only): sincospif — no 2*pi rounding of the angle, no slow path (A/B: profiles/r2af)
+#ifndef OHB_TRIG_MODE
+#define OHB_TRIG_MODE 1
+#endif
+OHB_SHARED_FN void ohb_sincos(float x, float& s, float& c) {
+#if OHB_DEVICE_CODE && OHB_TRIG_MODE >= 1
+    sincosf(x, &s, &c);
+#else
+    s = sinf(x); c = cosf(x);
+#endif
+}
+// sin and cos of 2*pi*turns (the shader's `phi = 6.2831853 * u`)
+OHB_SHARED_FN void ohb_sincos_turns(float turns, float& s, float& c) {
+#if OHB_DEVICE_CODE && OHB_TRIG_MODE == 2
+    sincospif(2.0f * turns, &s, &c);
+#elif OHB_DEVICE_CODE && OHB_TRIG_MODE == 1
+    sincosf(6.2831853f * turns, &s, &c);
+#else
+    const float x = 6.2831853f * turns; s = sinf(x); c = cosf(x);
+#endif
+}
 OHB_SHARED_FN float ohb_pow(float x, float e) { return powf(x, e); }
 OHB_SHARED_FN float ohb_atan2(float y, float x) { return atan2f(y, x); }
 OHB_HD f3 vpow(f3 a, float e) { return mk3(ohb_pow(a.x, e), ohb_pow(a.y, e), ohb_pow(a.z, e)); }

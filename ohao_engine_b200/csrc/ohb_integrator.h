@@ -163,8 +163,8 @@ OHB_HD f3 cosineHemisphere(f3 N, f2 u) {   // pt_raygen_offline.rgen:93-100
     f3 T = normalize(cross(up, N));
     f3 B = cross(N, T);
     float r = sqrtf(u.x);
-    float phi = 6.2831853f * u.y;
-    return normalize(T * r * ohb_cos(phi) + B * r * ohb_sin(phi) + N * sqrtf(fmaxf(0.0f, 1.0f - r * r)));
+    float sp, cp; ohb_sincos_turns(u.y, sp, cp);                     // phi = 6.2831853 * u.y
+    return normalize(T * r * cp + B * r * sp + N * sqrtf(fmaxf(0.0f, 1.0f - r * r)));
 }
 #if defined(__CUDACC__)
 static __device__ __host__ __noinline__ f3 cosineHemisphereShared(f3 N, f2 u) { return cosineHemisphere(N, u); }   // 4 call sites, one copy
@@ -178,7 +178,7 @@ OHB_SHARED_FN float ggxD_aniso(f3 N, f3 H, float NdotH, float roughness, float a
     f3 ref = fabsf(dot(up, N)) > 0.97f ? mk3(1, 0, 0) : up;
     f3 T = normalize(ref - N * dot(ref, N));
     f3 B = cross(N, T);
-    float c = ohb_cos(rotation), s = ohb_sin(rotation);
+    float c, s; ohb_sincos(rotation, s, c);
     f3 Tr = T * c + B * s, Br = B * c - T * s;
     float r2 = roughness * roughness;
     float aspect = sqrtf(1.0f - anisotropy * 0.9f);
@@ -214,11 +214,11 @@ OHB_HD void sampleSphereLightSolidAngle(f3 p, f3 center, float r, f2 u, f3& L, f
     float cosThetaMax = sqrtf(fmaxf(0.0f, 1.0f - (r * r) / fmaxf(d2, 1e-8f)));
     float cosTheta = 1.0f - u.x * (1.0f - cosThetaMax);
     float sinTheta = sqrtf(fmaxf(0.0f, 1.0f - cosTheta * cosTheta));
-    float phi = 6.2831853f * u.y;
     f3 up = fabsf(axis.y) < 0.999f ? mk3(0, 1, 0) : mk3(1, 0, 0);
     f3 T = normalize(cross(up, axis));
     f3 B = cross(axis, T);
-    L = normalize(T * (sinTheta * ohb_cos(phi)) + B * (sinTheta * ohb_sin(phi)) + axis * cosTheta);
+    float sp, cp; ohb_sincos_turns(u.y, sp, cp);                     // phi = 6.2831853 * u.y
+    L = normalize(T * (sinTheta * cp) + B * (sinTheta * sp) + axis * cosTheta);
     weight = 6.2831853f * (1.0f - cosThetaMax);
     float b = dot(L, -toCenter);
     float c = d2 - r * r;
@@ -248,8 +248,8 @@ OHB_HD LightSample sampleLight(const SceneDev& sc, Sampler& sm, uint32_t& dimIdx
         f2 u = sm.get2D(dimIdx); dimIdx += 2u;
         float cosT = 1.0f - 2.0f * u.x;
         float sinT = sqrtf(fmaxf(0.0f, 1.0f - cosT * cosT));
-        float phi = 6.2831853f * u.y;
-        f3 offset = mk3(sinT * ohb_cos(phi), sinT * ohb_sin(phi), cosT) * r;
+        float sp, cp; ohb_sincos_turns(u.y, sp, cp);                 // phi = 6.2831853 * u.y
+        f3 offset = mk3(sinT * cp, sinT * sp, cosT) * r;
         f3 toL = (center + offset) - hitPos; float dist = length(toL);
         ls.L = toL / dist; ls.shadowDist = dist - 0.02f;
         if (type < 0.5f) {

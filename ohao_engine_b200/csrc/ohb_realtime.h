@@ -34,8 +34,8 @@ OHB_HD f3 sampleGGXVNDF(f3 Ve, float ax, float ay, f2 u) {
     f3 T1 = lensq > 0.0f ? mk3(-Vh.y, Vh.x, 0.0f) * (1.0f / sqrtf(lensq)) : mk3(1, 0, 0);
     f3 T2 = cross(Vh, T1);
     float r = sqrtf(u.x);
-    float phi = 2.0f * 3.14159265f * u.y;
-    float t1 = r * ohb_cos(phi), t2 = r * ohb_sin(phi);
+    float sp, cp; ohb_sincos_turns(u.y, sp, cp);                     // phi = 2 * 3.14159265 * u.y
+    float t1 = r * cp, t2 = r * sp;
     float s = 0.5f * (1.0f + Vh.z);
     t2 = (1.0f - s) * sqrtf(fmaxf(0.0f, 1.0f - t1 * t1)) + s * t2;
     f3 Nh = t1 * T1 + t2 * T2 + sqrtf(fmaxf(0.0f, 1.0f - t1 * t1 - t2 * t2)) * Vh;
@@ -416,8 +416,8 @@ OHB_HD void pixelRT(const SceneDev& sc, const FrameParams& fr, const PathArrays&
             for (int k = 0; k < 4; k++) {
                 f2 du = sm.get2D(dimIdx); dimIdx += 2u;
                 float rr = 20.0f * (1.0f - 0.15f * float(k)) * sqrtf(du.x);
-                float th = 6.2831853f * du.y;
-                int ox = int(nearbyintf(rr * ohb_cos(th))), oy = int(nearbyintf(rr * ohb_sin(th)));
+                float sth, cth; ohb_sincos_turns(du.y, sth, cth);     // th = 6.2831853 * du.y
+                int ox = int(nearbyintf(rr * cth)), oy = int(nearbyintf(rr * sth));
                 if (ox == 0 && oy == 0) { ox = 1; oy = 0; }
                 int sx = bx + ox, sy = by + oy;
                 sx = sx < 0 ? 0 : (sx > int(fr.W) - 1 ? int(fr.W) - 1 : sx); sy = sy < 0 ? 0 : (sy > int(fr.H) - 1 ? int(fr.H) - 1 : sy);
