@@ -119,6 +119,8 @@ struct ohb_ctx {
     DevBuf hookRays, hookOut, hookAux;
     TimingHooks timing; bool timingOn = false;
     cudaEvent_t evA = nullptr, evB = nullptr, evT0 = nullptr, evT1 = nullptr;
+    // second lane of the offline wavefront (ohb_render): its own stream, fork / film-order / join events
+    cudaStream_t stream2 = nullptr; cudaEvent_t evFork = nullptr, evFilm = nullptr, evJoin = nullptr;
 };
 
 #define OHB_FAIL(ctx, msg) do { (ctx)->err = (msg); return 1; } while (0)
@@ -181,10 +183,10 @@ ohb_ctx* ohb_create(int device_ordinal, uint32_t width, uint32_t height, int pro
     }
     cudaEventCreate(&c->evA); cudaEventCreate(&c->evB); cudaEventCreate(&c->evT0); cudaEventCreate(&c->evT1);
     defaultSettings(c);
-    if (ensureFilm(c) || clearFilm(c) || c->smallCounters.reserve(64 * 4) != cudaSuccess || c->devCounters.reserve(8 * 8) != cudaSuccess) {
+    if (ensureFilm(c) || clearFilm(c) || c->smallCounters.reserve(64 * 4) != cudaSuccess || c->devCounters.reserve(16 * 8) != cudaSuccess) {
         g_createError = c->err.empty() ? "allocation failed" : c->err; ohb_destroy(c); return nullptr;
     }
-    cudaMemsetAsync(c->smallCounters.p, 0, 64 * 4, c->stream); cudaMemsetAsync(c->devCounters.p, 0, 64, c->stream);
+    cudaMemsetAsync(c->smallCounters.p, 0, 64 * 4, c->stream); cudaMemsetAsync(c->devCounters.p, 0, 128, c->stream);
     // dummy 1-float CDFs like the reference when no env is loaded (light_upload.cpp:505-535)
     c->marg.reserve(4); c->cond.reserve(4); c->integral.reserve(4);
     cudaStreamSynchronize(c->stream);
@@ -214,6 +216,10 @@ void ohb_destroy(ohb_ctx* c) {
     if (c->evB) cudaEventDestroy(c->evB);
     if (c->evT0) cudaEventDestroy(c->evT0);
     if (c->evT1) cudaEventDestroy(c->evT1);
+    if (c->evFork) cudaEventDestroy(c->evFork);
+    if (c->evFilm) cudaEventDestroy(c->evFilm);
+    if (c->evJoin) cudaEventDestroy(c->evJoin);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -721,6 +727,9 @@ int ohb_set_tile(ohb_ctx* c, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h) {
     return 0;
 }
 
+#ifndef OHB_LANES_DEFAULT
+#define OHB_LANES_DEFAULT 0     // 0 = by acceleration-structure size, 1 = one lane, 2 = two lanes
+#endif
 int ensurePaths(ohb_ctx* c, uint32_t cap) {
     if (cap <= c->pathCapacity) return 0;
     size_t n = cap;
@@ -858,14 +867,48 @@ int ohb_render(ohb_ctx* c, const float view[16], const float proj[16], uint32_t 
     }
     uint32_t* small = c->smallCounters.as<uint32_t>();
     uint32_t done = 0;
+    // Two lanes (OHB_LANES): a batch's samples are split in two halves that run the wavefront on two streams, each in
+    // its own slice of the path arrays, so the drain of every launch of one lane (persistent CTAs leave as the queue empties) is
+    // filled by the other lane's kernels.  k_film folds sample by sample in fp32 through the stored accumulation image, and the two
+    // film launches are ordered lane 0 -> lane 1 by an event: the image is bit-identical to the one-lane run.  Per-kernel timing
+    // (ohb_enable_timing) needs serial launches and runs one lane.
+    // Measured (profiles/r2ag_sweep_lanes.txt): +1.5 % on the 50 K-triangle scene, +2.2 % on Cornell, -1.1 % on the 2 M-triangle scene,
+    // whose 130 MB of nodes + triangles already overflow the L2 with ONE kernel's working set — so the default (OHB_LANES unset or 0)
+    // runs two lanes only while the acceleration structure is at most a quarter of the 126 MB L2.
+    static const int lanesEnv = []() { const char* e = getenv("OHB_LANES"); return e ? atoi(e) : OHB_LANES_DEFAULT; }();
+    const size_t accelBytes = size_t(c->numActive) * 48u + size_t(c->stats.num_nodes) * 128u;
+    const bool twoLanes = (lanesEnv >= 2 || (lanesEnv == 0 && accelBytes <= (32u << 20))) && !c->timingOn;
+    if (twoLanes && !c->stream2) {
+        CU(c, cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+        CU(c, cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming)); CU(c, cudaEventCreateWithFlags(&c->evFilm, cudaEventDisableTiming)); CU(c, cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
+    }
     while (done < nsamples) {
         uint32_t k = std::min(spb, nsamples - done);
+        const uint32_t kA = (twoLanes && k >= 2u) ? (k + 1u) / 2u : k, kB = k - kA;
         PathArrays P{}; fillPaths(c, P);
-        P.numPixels = numPixels; P.samplesInBatch = k; P.firstSampleIndex = c->sampleIndex;
+        P.numPixels = numPixels; P.samplesInBatch = kA; P.firstSampleIndex = c->sampleIndex;
         FilmArrays F{};
         F.accum = c->accum.as<f4>(); F.ldr = c->ldr.as<uint32_t>(); F.historyCount = c->historyCount; F.sumMode = c->sumMode;
         F.sampleDump = dumpDev ? dumpDev + size_t(done) * c->W * c->H * 4u : nullptr;
-        launchOfflineBatch(s, fr, P, F, small + 4, c->numSMs, c->stream, &c->launches, c->timingOn ? &c->timing : nullptr);
+        if (!kB) launchOfflineBatch(s, fr, P, F, small + 4, c->numSMs, c->stream, &c->launches, c->timingOn ? &c->timing : nullptr, 3);
+        else {
+            PathArrays Q = P; FilmArrays G = F;
+            const size_t base = size_t(numPixels) * kA;      // path index = sample * numPixels + pixel: lane 1 owns the upper samples
+            Q.rayO += base; Q.rayD += base; Q.hit += base; Q.thr += base; Q.rad += base; Q.pendA += base; Q.pendB += base; Q.meta += base;
+            Q.fh0 += base; Q.fh1 += base; Q.fh2 += base; Q.shO += 2 * base; Q.shD += 2 * base;
+            Q.queueIn += base; Q.queueOut += base; Q.queueSorted += base; Q.hitFlag += base; Q.octPerm = nullptr;
+            Q.countIn += 32; Q.countOut += 32; Q.shCount += 32; Q.sortCount += 32; Q.counters += 8; Q.sobolTab += kA;
+            Q.samplesInBatch = kB; Q.firstSampleIndex = c->sampleIndex + kA;
+            P.albedoAOV = nullptr;                           // the AOVs are the first hit of the batch's LAST sample: lane 1 writes them
+            G.historyCount = F.historyCount + kA; G.sampleDump = F.sampleDump ? F.sampleDump + size_t(kA) * c->W * c->H * 4u : nullptr;
+            CU(c, cudaEventRecord(c->evFork, c->stream)); CU(c, cudaStreamWaitEvent(c->stream2, c->evFork, 0));
+            launchOfflineBatch(s, fr, P, F, small + 4, c->numSMs, c->stream, &c->launches, nullptr, 1);
+            launchOfflineBatch(s, fr, Q, G, small + 32 + 4, c->numSMs, c->stream2, &c->launches, nullptr, 1);
+            launchOfflineBatch(s, fr, P, F, small + 4, c->numSMs, c->stream, &c->launches, nullptr, 2);
+            CU(c, cudaEventRecord(c->evFilm, c->stream)); CU(c, cudaStreamWaitEvent(c->stream2, c->evFilm, 0));
+            launchOfflineBatch(s, fr, Q, G, small + 32 + 4, c->numSMs, c->stream2, &c->launches, nullptr, 2);
+            CU(c, cudaEventRecord(c->evJoin, c->stream2)); CU(c, cudaStreamWaitEvent(c->stream, c->evJoin, 0));
+        }
         c->sampleIndex += k; c->historyCount += k; done += k;   // path_tracer_render.cpp:1274-1275
     }
     c->viewChanged = false;
@@ -991,9 +1034,10 @@ int ohb_set_sample_dump(ohb_ctx* c, float* host, size_t cap) { if (!c) return 1;
 int ohb_get_counters(ohb_ctx* c, ohb_counters* out) {
     if (!c || !out) return 1;
     cudaSetDevice(c->device);
-    unsigned long long d[8];
-    CU(c, cudaMemcpyAsync(d, c->devCounters.p, 64, cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long d[16];
+    CU(c, cudaMemcpyAsync(d, c->devCounters.p, 128, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 8; i++) d[i] += d[8 + i];          // the second lane of ohb_render counts in its own block
     memset(out, 0, sizeof(*out));
     out->samples = d[0]; out->closest_rays = d[1]; out->shadow_rays = d[2]; out->closest_hits = d[3]; out->kernel_launches = c->launches;
     return 0;
@@ -1002,7 +1046,7 @@ void ohb_reset_counters(ohb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    cudaMemsetAsync(c->devCounters.p, 0, 64, c->stream);
+    cudaMemsetAsync(c->devCounters.p, 0, 128, c->stream);
     c->launches = 0; c->timing.reset();
 }
 int ohb_enable_timing(ohb_ctx* c, int enable) {

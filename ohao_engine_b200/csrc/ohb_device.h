@@ -47,7 +47,7 @@ void launchHybridGi(const SceneDev& sc, const HybridGiParams& pc, const f4* gPos
 void launchNrdPack(const float* in6, const float* nr4, uint32_t n, f4* packedRad, f4* packedNormal, float* unpackedRgb, cudaStream_t st, uint64_t* launches);
 void launchEnvPdf(const SceneDev& sc, const float* dirs3, uint32_t n, float* pdf, cudaStream_t st, uint64_t* launches);
 void launchOfflineBatch(const SceneDev& sc, const FrameParams& fr, PathArrays P, const FilmArrays& F,
-                        uint32_t* work, int numSMs, cudaStream_t st, uint64_t* launches, TimingHooks* th);
+                        uint32_t* work, int numSMs, cudaStream_t st, uint64_t* launches, TimingHooks* th, int phases = 3);
 void launchRealtimeFrame(const SceneDev& sc, const FrameParams& fr, PathArrays P, const RTImagesDev& im, uint32_t* ldr, float* denoisedDump,
                          uint32_t* work, int numSMs, cudaStream_t st, uint64_t* launches, TimingHooks* th);
 // images of the SVGF denoiser: persistent ping-ponged history (colour, moments, geometry) + per-frame scratch

@@ -717,8 +717,13 @@ __global__ void k_resolve(f4* accum, uint32_t* ldr, uint32_t n, int sumMode) {
 
 // One batch of `samplesInBatch` samples for every pixel of the tile: raygen, (1 + 2*maxBounces)
 // wavefront iterations, film.  All launches are asynchronous on `st`.
+// phases: bit 0 = raygen + wavefront iterations, bit 1 = film (ohb_render runs the two lanes' films in sample order)
 void launchOfflineBatch(const SceneDev& sc, const FrameParams& fr, PathArrays P, const FilmArrays& F,
-                        uint32_t* work, int numSMs, cudaStream_t st, uint64_t* launches, TimingHooks* th) {
+                        uint32_t* work, int numSMs, cudaStream_t st, uint64_t* launches, TimingHooks* th, int phases) {
+    if (!(phases & 1)) {
+        k_film<<<gridFor(P.numPixels, 128), 128, 0, st>>>(fr, P, F); (*launches)++;
+        return;
+    }
     uint32_t total = P.numPixels * P.samplesInBatch;
     k_zero_u32<<<1, 32, 0, st>>>(P.countIn, 1); k_zero_u32<<<1, 32, 0, st>>>(P.countOut, 1);
     k_sobol_tab<<<gridFor(P.samplesInBatch, 64), 64, 0, st>>>(const_cast<u4*>(P.sobolTab), P.firstSampleIndex, P.samplesInBatch); (*launches)++;
@@ -759,6 +764,7 @@ void launchOfflineBatch(const SceneDev& sc, const FrameParams& fr, PathArrays P,
         uint32_t* tq = P.queueIn; P.queueIn = P.queueOut; P.queueOut = tq;
         uint32_t* tc = P.countIn; P.countIn = P.countOut; P.countOut = tc;
     }
+    if (!(phases & 2)) return;
     if (th) th->begin(3, st);
     k_film<<<gridFor(P.numPixels, 128), 128, 0, st>>>(fr, P, F); (*launches)++;
     if (th) th->end(3, st);

@@ -232,6 +232,35 @@ def test_postponing_and_refill_schedules_do_not_change_hits(tmp_path):
     assert (outs[0]["prim"] != 0xFFFFFFFF).sum() > 50000
 
 
+_LANES_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+from ohao_engine_b200 import binding as B, scenes
+ps, cam = scenes.helmet_class(ntris=12000, tex_size=256, env_size=(256, 128)), scenes.helmet_camera()
+W, H = 320, 180
+r = B.Renderer(W, H); r.set_scene(ps)
+samples = r.render(cam.view(), cam.proj(W, H), 5, dump=True)          # 5 samples: lanes of 3 + 2
+r.render(cam.view(), cam.proj(W, H), 7)                               # progressive: 12 accumulated, lanes of 4 + 3
+accum, albedo, normal = r.readback_hdr_buffers(True)
+c = r.counters()
+np.savez(sys.argv[2], samples=samples, accum=accum, albedo=albedo, normal=normal, ldr=r.get_pixels(),
+         counts=np.array([c["samples"], c["closest_rays"], c["shadow_rays"]], np.int64))
+"""
+
+
+def test_two_lanes_render_the_same_image(tmp_path):
+    """ohb_render splits a batch over two streams (OHB_LANES, ohb_api.cu); samples, accumulation image, AOVs, LDR and the ray
+    counters must be bit-identical to the one-lane run (k_film folds sample by sample, films are ordered by an event)."""
+    outs = []
+    for i, env in enumerate([{"OHB_LANES": "1"}, {"OHB_LANES": "2"}]):
+        out = str(tmp_path / f"l{i}.npz")
+        subprocess.check_call([sys.executable, "-c", _LANES_SCRIPT, ROOT, out], env={**os.environ, **env})
+        outs.append(np.load(out))
+    for k in ("samples", "accum", "albedo", "normal", "ldr", "counts"):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+    assert outs[0]["accum"][..., 3].min() == 12.0 and outs[0]["counts"][1] > 320 * 180 * 12
+
+
 def test_pcg_sampler_samples_match_oracle(cornell):
     """SAMPLER_PCG (sampler_pcg.glsl:9-29): dead in the reference's pipelines (quirk Q3) but part of the sampler API."""
     ps, cam = cornell
