@@ -111,6 +111,20 @@ OHB_SHARED_FN void ohb_sincos_turns(float turns, float& s, float& c) {
 OHB_SHARED_FN float ohb_pow(float x, float e) { return powf(x, e); }
 OHB_SHARED_FN float ohb_atan2(float y, float x) { return atan2f(y, x); }
 OHB_HD f3 vpow(f3 a, float e) { return mk3(ohb_pow(a.x, e), ohb_pow(a.y, e), ohb_pow(a.z, e)); }
+// The closest-hit shader's sRGB decode `pow(texel, 2.2)` on x >= 0: x^2 * 2^(0.2 log2 x) — the exponent's error enters scaled
+// by 0.2 instead of 2.2, so MUFU.LG2 / MUFU.EX2 accuracy (2 ulp each) gives <= ~5 ulp against powf at 7 instructions
+// instead of powf's ~50 (8.5 % of the primary k_shade's instructions on the textured scene, profiles/r2ai).  Host code: powf.
+#ifndef OHB_FAST_POW
+#define OHB_FAST_POW 1
+#endif
+OHB_HD float pow22(float x) {
+#if OHB_DEVICE_CODE && OHB_FAST_POW
+    return (x * x) * exp2f(0.2f * __log2f(x));
+#else
+    return ohb_pow(x, 2.2f);
+#endif
+}
+OHB_HD f3 vpow22(f3 a) { return mk3(pow22(a.x), pow22(a.y), pow22(a.z)); }
 OHB_HD float pow5(float x) { float x2 = x * x; return x2 * x2 * x; }
 OHB_HD float maxcomp(f3 a) { return fmaxf(a.x, fmaxf(a.y, a.z)); }
 OHB_HD float signf(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }

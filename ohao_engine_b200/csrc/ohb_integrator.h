@@ -126,7 +126,7 @@ OHB_HD void closestHitShader(const SceneDev& sc, f3 o, f3 d, const ohb_hit& h, P
     f4 mc = ld4(mp), mpar = ld4(mp + 1), mpar2 = ld4(mp + 2);
     uint32_t diffTex = f2u(mc.w), nrmTex = f2u(mpar.z), emTex = f2u(mpar.w), rmTex = f2u(mpar2.x);
     f3 albedo = xyz(mc);
-    if (diffTex != OHB_NO_TEXTURE) albedo *= vpow(xyz(sampleLayer(sc, diffTex, texUV)), 2.2f);
+    if (diffTex != OHB_NO_TEXTURE) albedo *= vpow22(xyz(sampleLayer(sc, diffTex, texUV)));
     if (nrmTex != OHB_NO_TEXTURE) {
         f3 mapN = normalize(xyz(sampleLayer(sc, nrmTex, texUV)) * 2.0f - mk3(1.0f));
         f3 T, B;
@@ -144,7 +144,7 @@ OHB_HD void closestHitShader(const SceneDev& sc, f3 o, f3 d, const ohb_hit& h, P
     if (rmTex != OHB_NO_TEXTURE) { f4 rm = sampleLayer(sc, rmTex, texUV); rough *= rm.y; metal *= rm.z; }
     rough = fmaxf(rough, 0.04f);
     f3 em = mk3(0.0f);
-    if (emTex != OHB_NO_TEXTURE) em = vpow(xyz(sampleLayer(sc, emTex, texUV)), 2.2f);
+    if (emTex != OHB_NO_TEXTURE) em = vpow22(xyz(sampleLayer(sc, emTex, texUV)));
     p.color = em;
     p.attenuation = mk3(rough, clampf(metal, 0.0f, 1.0f), curv);
 }
