@@ -67,22 +67,22 @@ struct Payload { f3 color, attenuation, hitPos, hitNormal, hitAlbedo; float hitD
 
 // pt_miss.rmiss:52-82: dirToEquirect + bilinear fetch x envIntensity (dir normalised).  One shared copy: the miss shader
 // and env NEE both call it (two inlined copies in the fused k_shade).
-OHB_SHARED_FN f4 envRadianceShared(const f4* env, uint32_t envW, uint32_t envH, float envIntensity, float dx, float dy, float dz) {
-    float phi = ohb_atan2(dz, dx);
+OHB_SHARED_FN f4 envRadianceSharedPhi(const f4* env, uint32_t envW, uint32_t envH, float envIntensity, float phi, float dy) {
     float theta = asinf(clampf(dy, -1.0f, 1.0f));
     f2 uv; uv.x = phi / 6.2831853f + 0.5f; uv.y = theta / 3.1415926f + 0.5f;
     float envS = (envIntensity > 0.0f) ? envIntensity : 1.0f;
     f3 c = xyz(sampleEnvTexel4(env, int(envW), int(envH), uv)) * envS;
     return mk4(c, 0.0f);
 }
-OHB_HD f3 envRadiance(const SceneDev& sc, f3 dir) { return xyz(envRadianceShared(sc.env, sc.envW, sc.envH, sc.envIntensity, dir.x, dir.y, dir.z)); }
+OHB_HD f3 envRadiance(const SceneDev& sc, f3 dir) { return xyz(envRadianceSharedPhi(sc.env, sc.envW, sc.envH, sc.envIntensity, ohb_atan2(dir.z, dir.x), dir.y)); }
 OHB_HD void missShader(const SceneDev& sc, const FrameParams& fr, f3 rayDir, Payload& p) {
     p.hitDist = -1.0f;
     bool haveEnv = sc.envMapTexIdx != 0xFFFFFFFFu && sc.env != nullptr;
     if (haveEnv) {
         f3 dir = normalize(rayDir);
-        p.color = envRadiance(sc, dir);
-        p.envPdf = (fr.envW > 0u && fr.envH > 0.0f) ? pdfEnvMap(sc, dir) : 0.0f;
+        const float phi = ohb_atan2(dir.z, dir.x);         // one atan2 for the lookup (dirToEquirect) and the pdf (pdfEnvMap)
+        p.color = xyz(envRadianceSharedPhi(sc.env, sc.envW, sc.envH, sc.envIntensity, phi, dir.y));
+        p.envPdf = (fr.envW > 0u && fr.envH > 0.0f) ? pdfEnvMapPhi(sc, dir.y, phi) : 0.0f;
     } else {
         p.color = mk3(0.0f); p.envPdf = 0.0f;
     }
