@@ -293,7 +293,7 @@ def kernel_table(m, st, workload, integrator, W, H, spp, steps, num_sms=148):
         if x["launches"] == 0: continue
         nunits, bpu = units[k]
         avg = x["ms"] / x["launches"]; upl = nunits / x["launches"]
-        prof = measured_profile(workload, integrator, "k_" + k)
+        prof = measured_profile(workload, integrator, {"bounce": "k_bounce_rt", "film": "k_rt_denoise" if realtime else "k_film"}.get(k, "k_" + k))
         e = {"ms": round(x["ms"], 3), "launches": x["launches"], "share_of_step": round(x["ms"] / ms, 4), "units_per_launch": upl, "avg_launch_ms": avg,
              "measured_dram_bytes_per_unit": prof["dram_bytes_per_unit"] if prof else None, "profile_source": prof["source"] if prof else None}
         if k.startswith("trace_"):

@@ -11,6 +11,8 @@ if len(sys.argv) > 3:
     for line in open(sys.argv[3]):
         if line.startswith("{") and '"kernels"' in line:
             units = {"k_" + k: v["units_per_launch"] for k, v in json.loads(line)["kernels"].items()}
+            if key.endswith("/realtime"):      # timing buckets "bounce" / "film" are k_bounce_rt / k_rt_denoise in the realtime profile
+                units["k_bounce_rt"] = units.get("k_bounce"); units["k_rt_denoise"] = units.get("k_film")
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out))); hdr, un = rows[0], rows[1]
 sc = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
