@@ -289,8 +289,16 @@ OHB_HD uint32_t intersectWideNode(const Trav& t, const u4* gnodes, const TopNode
         const u4* np = tn8.top + size_t(idx) * OHB_WNODE_VECS;
         hdr = ldsu8(np + 2u * (0u ^ swz)); px8 = ldsu8(np + 2u * (1u ^ swz)); py8 = ldsu8(np + 2u * (2u ^ swz)); pz8 = ldsu8(np + 2u * (3u ^ swz));
     } else {
+#if OHB_DEVICE_CODE
+        // the node array is 128-B aligned (cudaMalloc; BLAS sub-arrays start at whole nodes): the piece offset (k ^ swz) << 5 is
+        // OR-ed into the low address word — one LOP3 per piece instead of a 64-bit add with carry
+        const uintptr_t nb = reinterpret_cast<uintptr_t>(gnodes + size_t(idx) * OHB_WNODE_VECS);
+        hdr = ldu8(reinterpret_cast<const u4*>(nb | uintptr_t((0u ^ swz) << 5))); px8 = ldu8(reinterpret_cast<const u4*>(nb | uintptr_t((1u ^ swz) << 5)));
+        py8 = ldu8(reinterpret_cast<const u4*>(nb | uintptr_t((2u ^ swz) << 5))); pz8 = ldu8(reinterpret_cast<const u4*>(nb | uintptr_t((3u ^ swz) << 5)));
+#else
         const u4* np = gnodes + size_t(idx) * OHB_WNODE_VECS;
         hdr = ldu8(np + 2u * (0u ^ swz)); px8 = ldu8(np + 2u * (1u ^ swz)); py8 = ldu8(np + 2u * (2u ^ swz)); pz8 = ldu8(np + 2u * (3u ^ swz));
+#endif
     }
     OHB_STAT_NODE();
     const u4 w0 = hdr.lo, w1 = hdr.hi;
@@ -352,6 +360,9 @@ OHB_HD uint32_t intersectWideNode(const Trav& t, const u4* gnodes, const TopNode
 // triangle test was measured 17 % SLOWER on both workloads, profiles/r1e_sweep.txt: a closest hit that is found
 // late stops culling the nodes behind it.  Triangles are therefore tested right after the node visit.)
 #define OHB_POSTPONE_DEN_DEFAULT 5
+#ifndef OHB_TRAV_PREFETCH
+#define OHB_TRAV_PREFETCH 0          // 1 = keep the runtime-selected node prefetch variants (OHB_PREFETCH knob)
+#endif
 // software prefetch of a node's 128-B line (no register, no scoreboard): mode bit 0 = into L2, bit 1 = into L1, bit 4 = one
 // prefetch per 32-B piece instead of one per line
 OHB_HD void prefetchNode(const u4* np, int mode) {
@@ -374,7 +385,12 @@ OHB_HD uint32_t nextChildOf(const u2& G, uint32_t octinv) {
 // the box tests, before the leaf triangles of this node are tested, bit 12 = four prefetches per node
 template <bool ANY, class Stack, bool TL = false>
 OHB_HD bool travRun(Trav& t, Stack& stack, const SceneDev& s, const TopNodes& top, int minActive, int postponeDenAndPf) {
+#if OHB_TRAV_PREFETCH
     const int postponeDen = postponeDenAndPf & 0xFF, pfSib = (postponeDenAndPf >> 8) & 3, pfKid = (postponeDenAndPf >> 10) & 3, pf4 = (postponeDenAndPf >> 8) & 16;
+#else
+    // the prefetch variants lost 2-12 % (profiles/r2h_sweep_prefetch.txt): compiled out, their per-iteration mode tests with them
+    const int postponeDen = postponeDenAndPf & 0xFF; constexpr int pfSib = 0, pfKid = 0, pf4 = 0;
+#endif
     for (;;) {
         if (t.G.y & 0xFF000000u) {
             // next inner child of the current group, front to back
