@@ -345,11 +345,12 @@ void launchNrdPack(const float* in6, const float* nr4, uint32_t n, f4* packedRad
 // Scheduling knobs of the traversal kernels (the env overrides exist for A/B measurements on the GPU box):
 //   minActive   : pause traversal and refill idle lanes when fewer lanes than this still traverse   (OHB_TRACE_MIN_ACTIVE)
 //   postponeDen : travRun's triangle-postponing threshold                                            (OHB_POSTPONE_DEN)
+#define OHB_TRACE_MIN_ACTIVE_DEFAULT 20
 struct TraceKnobs { int minActive, postponeDen; };
 static TraceKnobs traceKnobs() {
     static const TraceKnobs k = []() {
         auto geti = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
-        TraceKnobs r; r.minActive = geti("OHB_TRACE_MIN_ACTIVE", 20); r.postponeDen = geti("OHB_POSTPONE_DEN", OHB_POSTPONE_DEN_DEFAULT);
+        TraceKnobs r; r.minActive = geti("OHB_TRACE_MIN_ACTIVE", OHB_TRACE_MIN_ACTIVE_DEFAULT); r.postponeDen = geti("OHB_POSTPONE_DEN", OHB_POSTPONE_DEN_DEFAULT);
         if (r.postponeDen == 1) r.postponeDen = 2;      // 1 would postpone every triangle forever; 0 = never postpone
         r.postponeDen = (r.postponeDen & 0xFF) | (geti("OHB_TRACE_PREFETCH", 0) << 8);      // prefetch mode rides in bits 8.. (travRun)
         return r;
@@ -366,6 +367,9 @@ static TraceKnobs traceKnobs() {
 #define OHB_SMEM_TOP 73u
 template <bool ANY, int VAR, class IO, bool TL = false>
 __device__ __forceinline__ void persistentTrace(const SceneDev& sc, uint32_t n, uint32_t* work, IO& io, int minActive, int postponeDen, const uint32_t* perm = nullptr) {
+    // VAR bit 2: the default scheduling knobs as compile-time constants — the per-iteration loads and tests of the two kernel
+    // parameters go away (launchTraceClosest / launchTraceShadow pick this variant when the knobs are at their defaults)
+    if (VAR & 4) { minActive = OHB_TRACE_MIN_ACTIVE_DEFAULT; postponeDen = OHB_POSTPONE_DEN_DEFAULT; }
     const uint32_t lane = threadIdx.x & 31u;
     __shared__ TravStackEntry sStack[(VAR & 1) ? OHB_SMEM_STACK * TRACE_THREADS : 1];
     __shared__ u4 sTop[(VAR & 2) ? OHB_SMEM_TOP * OHB_WNODE_VECS : 1];
@@ -553,11 +557,17 @@ static int traceVar() {
 static void launchTraceClosest(unsigned smGrid8, const SceneDev& sc, const PathArrays& P, uint32_t* work, cudaStream_t st) {
     const TraceKnobs k = traceKnobs();
     if (sc.twoLevel) { k_trace_closest_tl<<<smGrid8 / 8u * 6u, TRACE_THREADS, 0, st>>>(sc, P, work, k.minActive, k.postponeDen & 0xFF); return; }
+    if (traceOcc() == 8 && traceVar() == 0 && k.minActive == OHB_TRACE_MIN_ACTIVE_DEFAULT && k.postponeDen == OHB_POSTPONE_DEN_DEFAULT) {
+        k_trace_closest<8, 4><<<smGrid8, TRACE_THREADS, 0, st>>>(sc, P, work, k.minActive, k.postponeDen); return;
+    }
     OHB_TRACE_DISPATCH(k_trace_closest, sc, P, work, k.minActive, k.postponeDen);
 }
 static void launchTraceShadow(unsigned smGrid8, const SceneDev& sc, const PathArrays& P, uint32_t* work, cudaStream_t st) {
     const TraceKnobs k = traceKnobs();
     if (sc.twoLevel) { k_trace_shadow_tl<<<smGrid8 / 8u * 6u, TRACE_THREADS, 0, st>>>(sc, P, work, k.minActive, k.postponeDen & 0xFF); return; }
+    if (traceOcc() == 8 && traceVar() == 0 && k.minActive == OHB_TRACE_MIN_ACTIVE_DEFAULT && k.postponeDen == OHB_POSTPONE_DEN_DEFAULT) {
+        k_trace_shadow<8, 4><<<smGrid8, TRACE_THREADS, 0, st>>>(sc, P, work, k.minActive, k.postponeDen); return;
+    }
     OHB_TRACE_DISPATCH(k_trace_shadow, sc, P, work, k.minActive, k.postponeDen);
 }
 #define SHADE_THREADS 128
