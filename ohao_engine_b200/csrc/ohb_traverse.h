@@ -141,10 +141,12 @@ static __device__ __host__ __noinline__
 #else
 static inline
 #endif
-void edgeFallback(float Ax, float Ay, float Bx, float By, float Cx, float Cy, float& U, float& V, float& W) {
-    U = float(double(Cx) * double(By) - double(Cy) * double(Bx));
-    V = float(double(Ax) * double(Cy) - double(Ay) * double(Cx));
-    W = float(double(Bx) * double(Ay) - double(By) * double(Ax));
+f3 edgeFallback(float Ax, float Ay, float Bx, float By, float Cx, float Cy) {     // by value: reference parameters put U, V, W into local memory on EVERY test
+    f3 r;
+    r.x = float(double(Cx) * double(By) - double(Cy) * double(Bx));
+    r.y = float(double(Ax) * double(Cy) - double(Ay) * double(Cx));
+    r.z = float(double(Bx) * double(Ay) - double(By) * double(Ax));
+    return r;
 }
 // tp = the 3 rows of one triangle.  Returns true with the candidate when tmin < t <= tlim (the caller rejects
 // t == tlim where that is not a tie to break); id = global triangle id.
@@ -163,7 +165,7 @@ OHB_HD bool intersectTri(const RayPrep& r, const TriRows& q, float tlim, TriHit&
     float U = xsub(xmul(Cx, By), xmul(Cy, Bx));
     float V = xsub(xmul(Ax, Cy), xmul(Ay, Cx));
     float W = xsub(xmul(Bx, Ay), xmul(By, Ax));
-    if (U == 0.0f || V == 0.0f || W == 0.0f) edgeFallback(Ax, Ay, Bx, By, Cx, Cy, U, V, W);
+    if (U == 0.0f || V == 0.0f || W == 0.0f) { const f3 e = edgeFallback(Ax, Ay, Bx, By, Cx, Cy); U = e.x; V = e.y; W = e.z; }
     if (fminf(fminf(U, V), W) < 0.0f && fmaxf(fmaxf(U, V), W) > 0.0f) return false;
     const float det = xadd(xadd(U, V), W);
     if (det == 0.0f) return false;
@@ -360,6 +362,9 @@ OHB_HD uint32_t intersectWideNode(const Trav& t, const u4* gnodes, const TopNode
 // triangle test was measured 17 % SLOWER on both workloads, profiles/r1e_sweep.txt: a closest hit that is found
 // late stops culling the nodes behind it.  Triangles are therefore tested right after the node visit.)
 #define OHB_POSTPONE_DEN_DEFAULT 5
+#ifndef OHB_TRI_UNROLL
+#define OHB_TRI_UNROLL 1          // 0 = never, 1 = any-hit kernels only, 2 = always
+#endif
 #ifndef OHB_TRAV_PREFETCH
 #define OHB_TRAV_PREFETCH 0          // 1 = keep the runtime-selected node prefetch variants (OHB_PREFETCH knob)
 #endif
@@ -436,8 +441,12 @@ OHB_HD bool travRun(Trav& t, Stack& stack, const SceneDev& s, const TopNodes& to
             const f4* triBasePtr = TL ? t.curTris : s.tris;
             const TriRows q0 = loadTri(t.r, triBasePtr + size_t(t.Gt.x + k0) * 3u);
             const TriRows q1 = loadTri(t.r, triBasePtr + size_t(t.Gt.x + k1) * 3u);
+            // Any-hit queries run two copies of the test body; closest-hit queries one body that selects its triangle's twelve
+            // values per pass (12 FSEL + the loop's predicate bookkeeping).  Measured (profiles/r2ar_sweep_tri_test.txt): unrolling
+            // takes 1.5-2 % off k_trace_shadow on both scenes, but adds 0.7 % to k_trace_closest on the 2 M scene (-0.9 % on helmet).
 #ifdef __CUDA_ARCH__
-#pragma unroll 1
+            constexpr int triUnroll = ((OHB_TRI_UNROLL == 2) || (OHB_TRI_UNROLL == 1 && ANY)) ? 2 : 1;
+#pragma unroll (triUnroll)
 #endif
             for (int j = 0; j < 2; j++) {
                 if (j == 1 && !two) break;
