@@ -50,6 +50,21 @@ OHB_HD f3 operator/(f3 a, float s) {
 #endif
     return mk3(a.x * r, a.y * r, a.z * r);
 }
+// "Evaluation-class" division: radiance, BSDF and pdf arithmetic only — never a value that decides where a ray goes (camera
+// rays, sampled directions, shading frames keep IEEE `/`), so a 2-ulp quotient moves a sample by 1e-7 of its radiance and
+// cannot feed the scene's chaotic amplification of path geometry.  Device: MUFU.RCP + multiply instead of the 9-instruction
+// IEEE sequence (6 % of k_shade's instructions, profiles/r2au); with -prec-div=false on EVERYTHING the 2 M scene's per-sample
+// mismatch grew 3.5x (profiles/r2av), which is why the flag is not used.  Host: plain division.
+#ifndef OHB_FAST_EDIV
+#define OHB_FAST_EDIV 1
+#endif
+OHB_HD float ediv(float a, float b) {
+#if defined(__CUDA_ARCH__) && OHB_FAST_EDIV
+    return __fdividef(a, b);
+#else
+    return a / b;
+#endif
+}
 OHB_HD f3 operator/(f3 a, f3 b) { return mk3(a.x / b.x, a.y / b.y, a.z / b.z); }
 OHB_HD f3& operator+=(f3& a, f3 b) { a = a + b; return a; }
 OHB_HD f3& operator*=(f3& a, f3 b) { a = a * b; return a; }

@@ -69,7 +69,7 @@ struct Payload { f3 color, attenuation, hitPos, hitNormal, hitAlbedo; float hitD
 // and env NEE both call it (two inlined copies in the fused k_shade).
 OHB_SHARED_FN f4 envRadianceSharedPhi(const f4* env, uint32_t envW, uint32_t envH, float envIntensity, float phi, float dy) {
     float theta = asinf(clampf(dy, -1.0f, 1.0f));
-    f2 uv; uv.x = phi / 6.2831853f + 0.5f; uv.y = theta / 3.1415926f + 0.5f;
+    f2 uv; uv.x = ediv(phi, 6.2831853f) + 0.5f; uv.y = ediv(theta, 3.1415926f) + 0.5f;
     float envS = (envIntensity > 0.0f) ? envIntensity : 1.0f;
     f3 c = xyz(sampleEnvTexel4(env, int(envW), int(envH), uv)) * envS;
     return mk4(c, 0.0f);
@@ -171,7 +171,7 @@ static __device__ __host__ __noinline__ f3 cosineHemisphereShared(f3 N, f2 u) { 
 #else
 static inline f3 cosineHemisphereShared(f3 N, f2 u) { return cosineHemisphere(N, u); }
 #endif
-OHB_HD float misBalance(float a, float b) { return a / fmaxf(a + b, 1e-6f); }   // mis.glsl:7-9
+OHB_HD float misBalance(float a, float b) { return ediv(a, fmaxf(a + b, 1e-6f)); }   // mis.glsl:7-9
 // anisotropic branch of ggxD_anisoOrIso: one shared, cold copy (anisotropy is 0 unless RTRenderSettings sets it)
 OHB_SHARED_FN float ggxD_aniso(f3 N, f3 H, float NdotH, float roughness, float anisotropy, float rotation) {
     f3 up = mk3(0, 1, 0);
@@ -191,7 +191,7 @@ OHB_HD float ggxD_anisoOrIso(f3 N, f3 H, float NdotH, float roughness, float ani
     if (anisotropy < 0.001f) {
         float a = roughness * roughness, a2 = a * a;
         float denom = NdotH * NdotH * (a2 - 1.0f) + 1.0f;
-        return a2 / (3.14159265f * denom * denom + 0.0001f);
+        return ediv(a2, 3.14159265f * denom * denom + 0.0001f);
     }
     return ggxD_aniso(N, H, NdotH, roughness, anisotropy, rotation);
 }
@@ -254,7 +254,7 @@ OHB_HD LightSample sampleLight(const SceneDev& sc, Sampler& sm, uint32_t& dimIdx
         ls.L = toL / dist; ls.shadowDist = dist - 0.02f;
         if (type < 0.5f) {
             float lcos = fmaxf(dot(-ls.L, normalize(offset)), 0.0f);
-            ls.weight = lcos * area / (dist * dist);
+            ls.weight = ediv(lcos * area, dist * dist);
         } else {
             float cosAngle = dot(-ls.L, lightDir);
             const float d2r = 0.017453292519943295f;
@@ -273,7 +273,7 @@ OHB_HD LightSample sampleLight(const SceneDev& sc, Sampler& sm, uint32_t& dimIdx
         f3 toL = lp - hitPos; float dist = length(toL);
         ls.L = toL / dist;
         float lcos = fmaxf(dot(-ls.L, ln), 0.0f);
-        ls.weight = lcos * ex2.w / (dist * dist);
+        ls.weight = ediv(lcos * ex2.w, dist * dist);
         ls.shadowDist = dist - 0.02f;
     }
     return ls;
@@ -305,10 +305,10 @@ struct ShadeCtx {
         float NdotH = fmaxf(dot(N, H), 0.001f), NdotV = fmaxf(dot(N, V), 0.001f), VdotH = fmaxf(dot(V, H), 0.001f);
         float D;
         if (bounce0) D = ggxD_anisoOrIso(N, H, NdotH, rough, fr.aniso, fr.anisoRot);
-        else { float a = rough * rough, a2 = a * a; float dn = NdotH * NdotH * (a2 - 1.0f) + 1.0f; D = a2 / (3.14159f * dn * dn + 0.0001f); }
+        else { float a = rough * rough, a2 = a * a; float dn = NdotH * NdotH * (a2 - 1.0f) + 1.0f; D = ediv(a2, 3.14159f * dn * dn + 0.0001f); }
         f3 F = schlick(F0, VdotH);
         float k = (rough + 1.0f) * (rough + 1.0f) / 8.0f;
-        float G = (NdotL / (NdotL * (1.0f - k) + k)) * (NdotV / (NdotV * (1.0f - k) + k));
+        float G = ediv(NdotL, NdotL * (1.0f - k) + k) * ediv(NdotV, NdotV * (1.0f - k) + k);
         f3 spec = D * F * G / (4.0f * NdotV * NdotL + 0.001f);
         f3 c;
         if (bounce0) {
@@ -355,16 +355,16 @@ struct ShadeCtx {
         float NdotH = fmaxf(dot(N, H), 0.001f), NdotV = fmaxf(dot(N, V), 0.001f), VdotH = fmaxf(dot(V, H), 0.001f);
         float D;
         if (bounce0) D = ggxD_anisoOrIso(N, H, NdotH, rough, fr.aniso, fr.anisoRot);
-        else { float a = rough * rough, a2 = a * a; float dn = NdotH * NdotH * (a2 - 1.0f) + 1.0f; D = a2 / (OHB_PI * dn * dn + 0.0001f); }
+        else { float a = rough * rough, a2 = a * a; float dn = NdotH * NdotH * (a2 - 1.0f) + 1.0f; D = ediv(a2, OHB_PI * dn * dn + 0.0001f); }
         f3 F = schlick(F0, VdotH);
         float k = (rough + 1.0f) * (rough + 1.0f) / 8.0f;
-        float G = (NdotL / (NdotL * (1.0f - k) + k)) * (NdotV / (NdotV * (1.0f - k) + k));
+        float G = ediv(NdotL, NdotL * (1.0f - k) + k) * ediv(NdotV, NdotV * (1.0f - k) + k);
         f3 spec = D * F * G / (4.0f * NdotV * NdotL + 0.001f);
         f3 kD = (mk3(1.0f) - F) * (1.0f - metal);
         f3 diff = kD * albedo / OHB_PI;
         f3 brdf = diff + spec;
         float specProb = specProbOf(inDir, N, F0, rough, metal);
-        float bsdfPdf = mixf(NdotL / OHB_PI, D * NdotH / (4.0f * VdotH + 1e-4f), specProb);
+        float bsdfPdf = mixf(ediv(NdotL, OHB_PI), ediv(D * NdotH, 4.0f * VdotH + 1e-4f), specProb);
         float w = misBalance(envPdf, bsdfPdf);
         f3 c = bounce0 ? (envRad * brdf * NdotL * w / envPdf) : (thr * envRad * brdf * NdotL * w / envPdf);
         if (clampOn) clampLum(c, fr.fireflyClamp);
@@ -524,8 +524,8 @@ OHB_HD uint32_t bounceBody(const SceneDev& sc, const FrameParams& fr, const Path
                     float NdotH = fmaxf(dot(N, Hs), 0.001f), VdotH = fmaxf(dot(-d, Hs), 0.001f);
                     float Ds;
                     if (primary) Ds = ggxD_anisoOrIso(N, Hs, NdotH, rough, fr.aniso, fr.anisoRot);
-                    else { float as = rough * rough, as2 = as * as; float dn = NdotH * NdotH * (as2 - 1.0f) + 1.0f; Ds = as2 / (OHB_PI * dn * dn + 1e-4f); }
-                    float pdfH = Ds * NdotH / (4.0f * VdotH + 1e-4f);
+                    else { float as = rough * rough, as2 = as * as; float dn = NdotH * NdotH * (as2 - 1.0f) + 1.0f; Ds = ediv(as2, OHB_PI * dn * dn + 1e-4f); }
+                    float pdfH = ediv(Ds * NdotH, 4.0f * VdotH + 1e-4f);
                     lastPdf = primary ? pdfH : specProb * pdfH; lastDelta = false;
                 }
             } else {
@@ -533,7 +533,7 @@ OHB_HD uint32_t bounceBody(const SceneDev& sc, const FrameParams& fr, const Path
                 nextD = cosineHemisphereShared(N, du);
                 thr *= albedo;
                 thr /= fmaxf(1.0f - specProb, 0.01f);
-                lastPdf = (1.0f - specProb) * fmaxf(dot(nextD, N), 0.0f) / OHB_PI; lastDelta = false;
+                lastPdf = ediv((1.0f - specProb) * fmaxf(dot(nextD, N), 0.0f), OHB_PI); lastDelta = false;
             }
             if (primary) {
                 P.fh0[p] = mk4(hp, rough); P.fh1[p] = mk4(N, metal); P.fh2[p] = mk4(albedo, 0.0f);
@@ -556,7 +556,7 @@ OHB_HD uint32_t bounceBody(const SceneDev& sc, const FrameParams& fr, const Path
         nextD = cosineHemisphereShared(fhN, du);
         nextO = fhPos + fhN * 0.01f;
         thr = fhAlbedo;
-        lastPdf = fmaxf(dot(nextD, fhN), 0.0f) / OHB_PI; lastDelta = false;
+        lastPdf = ediv(fmaxf(dot(nextD, fhN), 0.0f), OHB_PI); lastDelta = false;
         if (fr.maxBounces >= 1u) { stage = ST_CHAIN_C; bounce = 1u; } else finished = true;
     }
     P.rad[p] = mk4(rad, 0.0f);

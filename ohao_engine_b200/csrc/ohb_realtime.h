@@ -24,10 +24,10 @@ namespace ohb {
 #define OHB_ST_GI_MISS  (1u << 10)     // finished path's cosine ray escaped: env colour in pay0.xyz
 
 // ggx_aniso.glsl:66-126
-OHB_HD float ggxDiso(float NdotH, float alpha) { float a2 = alpha * alpha; float dn = NdotH * NdotH * (a2 - 1.0f) + 1.0f; return a2 / (3.14159265f * dn * dn + 1e-8f); }
-OHB_HD float smithLambdaGGX(float c, float alpha) { float c2 = c * c; float tan2 = fmaxf(0.0f, 1.0f - c2) / fmaxf(c2, 1e-8f); return 0.5f * (-1.0f + sqrtf(1.0f + alpha * alpha * tan2)); }
-OHB_HD float smithG1GGX(float c, float alpha) { return 1.0f / (1.0f + smithLambdaGGX(c, alpha)); }
-OHB_HD float smithG2overG1GGX(float NdotV, float NdotL, float alpha) { float lv = smithLambdaGGX(NdotV, alpha), ll = smithLambdaGGX(NdotL, alpha); return (1.0f + lv) / (1.0f + lv + ll + 1e-8f); }
+OHB_HD float ggxDiso(float NdotH, float alpha) { float a2 = alpha * alpha; float dn = NdotH * NdotH * (a2 - 1.0f) + 1.0f; return ediv(a2, 3.14159265f * dn * dn + 1e-8f); }
+OHB_HD float smithLambdaGGX(float c, float alpha) { float c2 = c * c; float tan2 = ediv(fmaxf(0.0f, 1.0f - c2), fmaxf(c2, 1e-8f)); return 0.5f * (-1.0f + sqrtf(1.0f + alpha * alpha * tan2)); }
+OHB_HD float smithG1GGX(float c, float alpha) { return ediv(1.0f, 1.0f + smithLambdaGGX(c, alpha)); }
+OHB_HD float smithG2overG1GGX(float NdotV, float NdotL, float alpha) { float lv = smithLambdaGGX(NdotV, alpha), ll = smithLambdaGGX(NdotL, alpha); return ediv(1.0f + lv, 1.0f + lv + ll + 1e-8f); }
 OHB_HD f3 sampleGGXVNDF(f3 Ve, float ax, float ay, f2 u) {
     f3 Vh = normalize(mk3(ax * Ve.x, ay * Ve.y, Ve.z));
     float lensq = Vh.x * Vh.x + Vh.y * Vh.y;
@@ -77,10 +77,10 @@ OHB_HD BrdfEval evalBrdfRT(const FrameParams& fr, f3 N, f3 V, f3 L, f3 albedo, f
     e.NdotL = fmaxf(dot(N, L), 0.0f);
     e.NdotH = fmaxf(dot(N, H), 0.001f); e.NdotV = fmaxf(dot(N, V), 0.001f); e.VdotH = fmaxf(dot(V, H), 0.001f);
     if (bounce0) e.D = ggxD_anisoOrIso(N, H, e.NdotH, rough, fr.aniso, fr.anisoRot);
-    else { float a = rough * rough, a2 = a * a; float dn = e.NdotH * e.NdotH * (a2 - 1.0f) + 1.0f; e.D = a2 / (piDiff * dn * dn + 0.0001f); }
+    else { float a = rough * rough, a2 = a * a; float dn = e.NdotH * e.NdotH * (a2 - 1.0f) + 1.0f; e.D = ediv(a2, piDiff * dn * dn + 0.0001f); }
     f3 F = schlick(F0, e.VdotH);
     float k = (rough + 1.0f) * (rough + 1.0f) / 8.0f;
-    float G = (e.NdotL / (e.NdotL * (1.0f - k) + k)) * (e.NdotV / (e.NdotV * (1.0f - k) + k));
+    float G = ediv(e.NdotL, e.NdotL * (1.0f - k) + k) * ediv(e.NdotV, e.NdotV * (1.0f - k) + k);
     e.spec = e.D * F * G / (4.0f * e.NdotV * e.NdotL + 0.001f);
     e.diff = ((mk3(1.0f) - F) * kdScale) * albedo / piDiff;
     return e;
@@ -105,12 +105,12 @@ OHB_HD void envNEE_RT(ShadeCtx& cx, f3 hp, f3 N, f3 inDir, f3 albedo, f3 F0, flo
     if (!(NdotL > 0.0f && envPdf > 0.0f)) return;
     f3 envRad = envRadiance(cx.sc, envDir);
     BrdfEval e = evalBrdfRT(cx.fr, N, normalize(-inDir), envDir, albedo, F0, rough, kdScale, bounce0, OHB_PI);
-    float pdfDiff = NdotL / OHB_PI;
+    float pdfDiff = ediv(NdotL, OHB_PI);
     float bsdfPdf;
     if (gi) bsdfPdf = pdfDiff;
     else {
         float specProb = specProbOf(inDir, N, F0, rough, metal);
-        float pdfSpec = bounce0 ? smithG1GGX(e.NdotV, rough * rough) * e.D / (4.0f * e.NdotV + 1e-4f) : e.D * e.NdotH / (4.0f * e.VdotH + 1e-4f);
+        float pdfSpec = bounce0 ? ediv(smithG1GGX(e.NdotV, rough * rough) * e.D, 4.0f * e.NdotV + 1e-4f) : ediv(e.D * e.NdotH, 4.0f * e.VdotH + 1e-4f);
         bsdfPdf = mixf(pdfDiff, pdfSpec, specProb);
     }
     float w = misBalance(envPdf, bsdfPdf);
@@ -237,7 +237,7 @@ OHB_HD bool bouncePathRT(const SceneDev& sc, const FrameParams& fr, const PathAr
                 float NdotL = fmaxf(dot(N, refl), 1e-4f), NdotH = fmaxf(dot(N, Hh), 1e-4f), VdotH = fmaxf(dot(V, Hh), 1e-4f);
                 f3 F = F0 + (mk3(1.0f) - F0) * pow5(1.0f - VdotH);
                 thr = F * smithG2overG1GGX(NdotV, NdotL, alpha);
-                lastPdf = smithG1GGX(NdotV, alpha) * ggxDiso(NdotH, alpha) / (4.0f * NdotV) + 1e-6f; lastDelta = false;
+                lastPdf = ediv(smithG1GGX(NdotV, alpha) * ggxDiso(NdotH, alpha), 4.0f * NdotV) + 1e-6f; lastDelta = false;
             }
             P.fh0[p] = mk4(hp, rough); P.fh1[p] = mk4(N, metal); P.fh2[p] = mk4(albedo, q0.w);
             if (fr.maxBounces >= 1u) { stage = ST_CHAIN_B; bounce = 1u; } else chainEnds = true;
@@ -261,15 +261,15 @@ OHB_HD bool bouncePathRT(const SceneDev& sc, const FrameParams& fr, const PathAr
                         f3 Hs = normalize(-d + nextD);
                         float NdotH = fmaxf(dot(N, Hs), 0.001f), VdotH = fmaxf(dot(-d, Hs), 0.001f);
                         float as = rough * rough, as2 = as * as; float dn = NdotH * NdotH * (as2 - 1.0f) + 1.0f;
-                        float Ds = as2 / (OHB_PI * dn * dn + 1e-4f);
-                        lastPdf = specProb * (Ds * NdotH / (4.0f * VdotH + 1e-4f)); lastDelta = false;
+                        float Ds = ediv(as2, OHB_PI * dn * dn + 1e-4f);
+                        lastPdf = specProb * ediv(Ds * NdotH, 4.0f * VdotH + 1e-4f); lastDelta = false;
                     }
                 } else {
                     f2 du = cx.sm.get2D(cx.dimIdx); cx.dimIdx += 2u;
                     nextD = cosineHemisphereShared(N, du);
                     thr *= albedo;
                     thr /= fmaxf(1.0f - specProb, 0.01f);
-                    lastPdf = (1.0f - specProb) * fmaxf(dot(nextD, N), 0.0f) / OHB_PI; lastDelta = false;
+                    lastPdf = ediv((1.0f - specProb) * fmaxf(dot(nextD, N), 0.0f), OHB_PI); lastDelta = false;
                 }
                 if (bounce >= fr.maxBounces) chainEnds = true; else bounce += 1u;
             }
@@ -523,7 +523,7 @@ OHB_HD void denoiseRT(const FrameParams& fr, const f4* accum, const f4* normalAO
                     float ws = FASTW ? atrousSpatialWeight(dx * dx + dy * dy) : expf(-float(dx * dx + dy * dy) / 4.0f);
                     float wn = FASTW ? pow48(fmaxf(dot(centerN, sn), 0.0f)) : ohb_pow(fmaxf(dot(centerN, sn), 0.0f), 48.0f);
                     f3 cd = den - sc;
-                    float wc = expf(-dot(cd, cd) / (sigmaC + 0.0001f));
+                    float wc = expf(ediv(-dot(cd, cd), sigmaC + 0.0001f));
                     float w = ws * wn * wc;
                     sum += sc * w; wSum += w;
                 }
