@@ -608,6 +608,20 @@ struct TileEmit {
         __syncthreads();
     }
 };
+// one round of TWO emitters behind one pair of barriers (k_sort_hits: hits and misses of the same entries)
+__device__ __forceinline__ void tileEmitRound2(TileEmit& a, bool keepA, uint32_t eA, TileEmit& b, bool keepB, uint32_t eB) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned ma = __ballot_sync(0xffffffffu, keepA), mb = __ballot_sync(0xffffffffu, keepB);
+    if (lane == 0u) { a.sW[warp] = uint32_t(__popc(ma)); b.sW[warp] = uint32_t(__popc(mb)); }
+    __syncthreads();
+    uint32_t offA = a.kept, totA = 0u, offB = b.kept, totB = 0u;
+#pragma unroll
+    for (uint32_t w = 0; w < SHADE_THREADS / 32; w++) { const uint32_t ca = a.sW[w], cb = b.sW[w]; if (w < warp) { offA += ca; offB += cb; } totA += ca; totB += cb; }
+    if (keepA) a.sOut[offA + uint32_t(__popc(ma & ((1u << lane) - 1u)))] = eA;
+    if (keepB) b.sOut[offB + uint32_t(__popc(mb & ((1u << lane) - 1u)))] = eB;
+    a.kept += totA; b.kept += totB;
+    __syncthreads();
+}
 #define OHB_TILE_EMIT(name) __shared__ uint32_t name##_out[QTILE], name##_w[SHADE_THREADS / 32], name##_base; TileEmit name{name##_out, name##_w, &name##_base, 0u}
 
 template <bool RT>
@@ -631,12 +645,19 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_sort_hits(PathArrays P) {
     const uint32_t n = *P.countIn;
     for (uint32_t tile = blockIdx.x * QTILE; tile < n; tile += gridDim.x * QTILE) {
         qh.begin(); qm.begin();
+        // all of the tile's entries and flags are requested before the first round: the rounds are separated by barriers, and
+        // loading inside them made every round wait for its own memory round trip (eight in a row per tile)
+        uint32_t ent[QTILE_ROUNDS]; uint8_t flg[QTILE_ROUNDS];
+#pragma unroll
         for (int r = 0; r < QTILE_ROUNDS; r++) {
             const uint32_t i = tile + uint32_t(r) * SHADE_THREADS + threadIdx.x;
-            const bool valid = i < n;
-            const uint32_t e = valid ? P.queueIn[i] : 0u;
-            const bool hit = valid && P.hitFlag[i] != 0u;
-            qh.round(hit, e); qm.round(valid && !hit, e | OHB_Q_MISS);
+            ent[r] = i < n ? P.queueIn[i] : 0u; flg[r] = i < n ? P.hitFlag[i] : uint8_t(0);
+        }
+#pragma unroll
+        for (int r = 0; r < QTILE_ROUNDS; r++) {
+            const uint32_t i = tile + uint32_t(r) * SHADE_THREADS + threadIdx.x;
+            const bool valid = i < n, hit = valid && flg[r] != 0u;
+            tileEmitRound2(qh, hit, ent[r], qm, valid && !hit, ent[r] | OHB_Q_MISS);
         }
         qh.flush(P.sortCount, P.queueSorted, true, 0u); qm.flush(P.sortCount + 1, P.queueSorted, false, n - 1u);
     }
