@@ -202,7 +202,9 @@ uint32_t ohb_frame_index(const ohb_ctx*);              /* getFrameIndex(): curre
 /* One call == `nsamples` consecutive PathTracer::render() calls with this view/proj
  * (offline: sample indices advance by nsamples, one spp each; realtime: nsamples FRAMES of
  * settings.samples_per_frame spp each — ReSTIR GI temporal + spatial reuse, reprojected EMA, a-trous).
- * Asynchronous w.r.t. the host like vkQueueSubmit; readbacks synchronise. */
+ * Asynchronous w.r.t. the host like vkQueueSubmit; readbacks synchronise.  Offline batches may run as two lanes on two
+ * internal streams (OHB_LANES); the lanes join on the context's stream before the call returns, and the accumulation image is
+ * bit-identical to the one-lane result (samples are folded in index order). */
 int ohb_render(ohb_ctx*, const float view[16], const float proj[16], uint32_t nsamples);
 /* Restrict offline rendering to a pixel rectangle (multi-GPU tile sharding, §8e). Default: full frame. */
 int ohb_set_tile(ohb_ctx*, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h);
