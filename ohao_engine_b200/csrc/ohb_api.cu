@@ -740,7 +740,8 @@ int ensurePaths(ohb_ctx* c, uint32_t cap) {
         CU(c, c->pay0.reserve(n * 16)); CU(c, c->pay1.reserve(n * 16)); CU(c, c->pay2.reserve(n * 16)); CU(c, c->pay3.reserve(n * 16));
     }
     CU(c, c->shO.reserve(n * 32)); CU(c, c->shD.reserve(n * 32)); CU(c, c->queueA.reserve(n * 4)); CU(c, c->queueB.reserve(n * 4)); CU(c, c->queueS.reserve(n * 4)); CU(c, c->hitFlag.reserve(n));
-    {   // octant binning (the visibility-ray queue holds up to 2 rays per path): 4096-entry blocks, 8 bins per block
+    static const bool octBin = []() { const char* e = getenv("OHB_OCT_BIN"); return e && atoi(e) != 0; }();
+    if (octBin) {   // octant binning, an A/B variant that is off by default (268 MB at 32 Mi paths): 4096-entry blocks, 8 bins per block; the visibility-ray queue holds up to 2 rays per path
         const size_t blocks = (2 * n + 4095) / 4096;
         CU(c, c->octPerm.reserve(2 * n * 4)); CU(c, c->octHist.reserve(blocks * 8 * 4 + 64)); CU(c, c->octScanTmp.reserve((blocks * 8 / 1024 + 4096) * 4));
     }
