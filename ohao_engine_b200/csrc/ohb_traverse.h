@@ -280,6 +280,9 @@ OHB_HD ohb_hit travResult(const Trav& t) {
 // covers the 5e-7 of arithmetic error above and leaves 7e-7 (a dozen ulp) for the placement error.
 #define OHB_NODE_SWZ(i) ((i) & 3u)
 OHB_HD u8v ldsu8(const u4* p) { u8v r; r.lo = p[0]; r.hi = p[1]; return r; }
+// ORDERED = false (any-hit queries): the inner children keep their slot order — an occlusion test does not care which occluder it
+// finds first, and the octant permutation of the meta bytes is 12 instructions per visit
+template <bool ORDERED = true>
 OHB_HD uint32_t intersectWideNode(const Trav& t, const u4* gnodes, const TopNodes& tn8, uint32_t idx, float thi, uint32_t& childBase, uint32_t& triBase, uint32_t& imask) {
     const RayPrep& r = t.r;
     const uint32_t swz = OHB_NODE_SWZ(idx);
@@ -328,8 +331,8 @@ OHB_HD uint32_t intersectWideNode(const Trav& t, const u4* gnodes, const TopNode
     for (int g = 0; g < 2; g++) {
         // meta bytes: inner children get their slot index XORed with the ray octant (= visit priority)
         uint32_t m4 = g ? w1.w : w1.z;
-        const uint32_t inner4 = m4 & (m4 << 1) & 0x10101010u;                 // 0x10 in the bytes of inner children
-        m4 ^= (inner4 >> 4) * t.octinv;
+        const uint32_t inner4 = ORDERED ? (m4 & (m4 << 1) & 0x10101010u) : 0u;  // 0x10 in the bytes of inner children
+        if (ORDERED) m4 ^= (inner4 >> 4) * t.octinv;
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
@@ -362,6 +365,9 @@ OHB_HD uint32_t intersectWideNode(const Trav& t, const u4* gnodes, const TopNode
 // triangle test was measured 17 % SLOWER on both workloads, profiles/r1e_sweep.txt: a closest hit that is found
 // late stops culling the nodes behind it.  Triangles are therefore tested right after the node visit.)
 #define OHB_POSTPONE_DEN_DEFAULT 5
+#ifndef OHB_ANY_UNORDERED
+#define OHB_ANY_UNORDERED 1      // any-hit queries visit inner children in slot order (no octant permutation)
+#endif
 #ifndef OHB_TRI_UNROLL
 #define OHB_TRI_UNROLL 1          // 0 = never, 1 = any-hit kernels only, 2 = always
 #endif
@@ -400,7 +406,7 @@ OHB_HD bool travRun(Trav& t, Stack& stack, const SceneDev& s, const TopNodes& to
         if (t.G.y & 0xFF000000u) {
             // next inner child of the current group, front to back
             const uint32_t bit = bfind32(t.G.y);
-            const uint32_t slot = (bit - 24u) ^ t.octinv;
+            const uint32_t slot = (OHB_ANY_UNORDERED && ANY) ? (bit - 24u) : ((bit - 24u) ^ t.octinv);
             t.G.y &= ~(1u << bit);
             const uint32_t idx = t.G.x + popc32(t.G.y & 0xFFu & ((1u << slot) - 1u));
             if (t.G.y & 0xFF000000u) {
@@ -408,7 +414,7 @@ OHB_HD bool travRun(Trav& t, Stack& stack, const SceneDev& s, const TopNodes& to
                 if (pfSib) prefetchNode(s.wnodes + size_t(nextChildOf(t.G, t.octinv)) * OHB_WNODE_VECS, pfSib | pf4);
             }
             uint32_t childBase, triBase, imask;
-            const uint32_t hits = intersectWideNode(t, TL ? t.curNodes : s.wnodes, top, idx, t.tlim, childBase, triBase, imask);
+            const uint32_t hits = intersectWideNode<!(OHB_ANY_UNORDERED && ANY)>(t, TL ? t.curNodes : s.wnodes, top, idx, t.tlim, childBase, triBase, imask);
             t.G.x = childBase; t.G.y = (hits & 0xFF000000u) | imask;
             t.Gt.x = triBase; t.Gt.y = hits & 0x00FFFFFFu;
             if (pfKid && (t.G.y & 0xFF000000u) && t.Gt.y) prefetchNode(s.wnodes + size_t(nextChildOf(t.G, t.octinv)) * OHB_WNODE_VECS, pfKid | pf4);
